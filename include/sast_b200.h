@@ -1,0 +1,210 @@
+/*
+ * sast_b200.h -- C ABI of libsast_b200.so: the SAST scene-adaptive sparse-attention
+ * block (SAST, CVPR'24) as hand-written CUDA for NVIDIA B200 (sm_100a).
+ *
+ * The reference (Peterande/SAST) is pure PyTorch: there is no FFI in it to mirror.  The
+ * boundary a reference user sees is the Python module API (sast_b200.SAST_block, MS_WSA,
+ * RNNDetector -- same constructor / forward signatures and state-dict keys); this header
+ * is the plain-C layer underneath it, bound with ctypes.  Each entry
+ * point cites the reference lines it replaces.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns
+ *     every buffer; nothing is allocated, freed or synchronised inside;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - data-dependent counts (selected windows M, selected tokens S, Kmax) are written to
+ *     device memory (sast_selection.counts), never returned to the host;
+ *   - return value: 0 ok; <0 invalid argument (SAST_E_*); >0 a cudaError_t;
+ *   - re-entrant: no global mutable state; concurrent calls on different streams with
+ *     disjoint buffers are safe.
+ *
+ * Feature maps are NHWC fp32 [B,H,W,C] and are never physically partitioned: a "window"
+ * flavour addresses a p0 x p1 patch, a "grid" flavour the (H/p0, W/p1)-strided lattice,
+ * exactly the index maps of ops.py:189-220.
+ */
+#ifndef SAST_B200_H_
+#define SAST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAST_ABI_VERSION 1
+
+enum sast_error {
+  SAST_OK = 0,
+  SAST_E_NULL = -1,      /* a required pointer is NULL            */
+  SAST_E_SHAPE = -2,     /* H % p0, W % p1, C % 32 ... violated   */
+  SAST_E_UNSUPPORTED = -3,
+  SAST_E_WORKSPACE = -4  /* workspace too small                   */
+};
+
+enum sast_flavor {       /* how (window w, token t) maps to a pixel of the NHWC map */
+  SAST_WINDOW = 0,       /* ops.py:189-195 window_partition                         */
+  SAST_GRID = 1,         /* ops.py:206-212 grid_partition                           */
+  SAST_FLAT = 2          /* x is already [B*N, T, C] (MS_WSA.forward called directly) */
+};
+
+enum sast_precision {
+  SAST_FP32 = 0,         /* CUDA-core fp32 FMA everywhere (validation grade)        */
+  SAST_BF16 = 1          /* tcgen05 bf16 operands / fp32 accumulate for GEMMs+attention */
+};
+
+enum sast_dtype { SAST_U8 = 0, SAST_I32 = 1, SAST_F32 = 2, SAST_I64 = 3, SAST_F16 = 4, SAST_BF16_T = 5 };
+
+/* Geometry of one stage's feature map and its partition. T = p0*p1, N = H*W/T. */
+typedef struct sast_geom {
+  int32_t B, H, W, C;
+  int32_t p0, p1;
+} sast_geom;
+
+/*
+ * One layer's selection, device resident.  NW = B*N windows, P = B*H*W tokens.
+ * "Partitioned order" of a token is q = w*T + t with w = b*N + n (the row order of the
+ * reference's [B*N, T, C] tensors).  Replaces the index lists
+ * [index_window, index_token, padding_index, asy_index, K] of SAST.py:123.
+ */
+typedef struct sast_selection {
+  int32_t* counts;    /* [8]  0:M  1:S  2:Kmax  3:number of attention tiles  4..7 reserved */
+  int32_t* win_K;     /* [NW]   selected tokens in window w (0 when the window is dropped)  */
+  int32_t* win_rank;  /* [NW]   rank m of window w among selected windows, or -1            */
+  int32_t* win_row0;  /* [NW+1] first compacted row of window w (exclusive prefix of win_K) */
+  int32_t* sel_win;   /* [NW]   first M entries: ascending ids of selected windows (= index_window) */
+  int32_t* tok_row;   /* [P]    compacted row of token q (partitioned order), or -1          */
+  int32_t* row_tok;   /* [P]    first S entries: token q of compacted row r                 */
+  int32_t* frame_tot; /* [B*4]  per frame: M_b, S_b, Kmax_b, reserved                      */
+  uint8_t* tok_keep;  /* [P]    scratch: keep flag per token, partitioned order             */
+  int32_t* tiles;     /* [NW*4] attention tiles: row0, rows, first selected-window rank, windows */
+} sast_selection;
+
+/* Bytes of one int32 pool able to hold a sast_selection for (NW, P, B); see sast_selection_bind. */
+size_t sast_selection_bytes(int32_t B, int32_t NW, int32_t P);
+/* Carve `pool` (>= sast_selection_bytes, 16-byte aligned) into a sast_selection. */
+int sast_selection_bind(void* pool, int32_t B, int32_t NW, int32_t P, sast_selection* out);
+
+/*
+ * a1  scene sparsity ratio r.  ref: sast_rnn.py:45-60 non_zero_ratio.
+ * x [B,Cin,H,W] of `dtype` (SAST_U8 / SAST_I32 / SAST_F32) -> r [B,4,Cin] fp32, bit-exact:
+ * count of non-zero cells after max-pooling by 4,8,16,32 (int16 wrap), times fp32(B/numel).
+ */
+int sast_nonzero_ratio(const void* x, int32_t dtype, int32_t B, int32_t Cin, int32_t H, int32_t W,
+                       float* r, void* stream);
+
+/*
+ * a4  scoring module + STP weighting.  ref: SAST.py:105-119, 305-328.
+ *   x0 = x + pos;  ctrl = exp(Wc) (r + 1e-6);  s = relu(x0 Ws^T + bs)
+ *   xw = sigmoid(ctrl) sigmoid(s) x0   (NHWC, same layout as x)
+ *   tok_score[p] = sum_c | (amp/ctrl_c) s_c |     (the only thing selection needs)
+ * pos: [H,W,C] table when pos_batch_stride == 0, else [B,H,W,C] with that element stride.
+ * When Ws == NULL (non-first block, SAST.py:124-128) only xw = x + pos is produced.
+ */
+typedef struct sast_score_args {
+  sast_geom g;
+  const float* x;          /* [B,H,W,C] */
+  const float* pos;
+  int64_t pos_batch_stride;
+  const float* r;          /* [B,n_bins] */
+  int32_t n_bins;          /* 20 */
+  const float* ctrl_w;     /* to_controls.weight [C,n_bins] (pre-exp) */
+  const float* score_w;    /* to_scores.weight [C,C] */
+  const float* score_b;    /* to_scores.bias [C] */
+  float amp;
+  float* xw;               /* out [B,H,W,C]; must not alias x */
+  float* tok_score;        /* out [B,H,W] */
+  float* ctrl_scratch;     /* scratch [2*B*C] floats (sigmoid(ctrl), amp/ctrl) */
+} sast_score_args;
+int sast_score_fwd(const sast_score_args* a, void* stream);
+
+/*
+ * a5/a6  scene-adaptive selection.  ref: SAST.py:84-96, 258-281.
+ * mode SAST_SEL_SCORES: from tok_score [B,H,W] (map order): window logit = mean of its T
+ *   token scores, softmax over the frame's N windows, keep if >= thr_win; per kept window
+ *   softmax over its T token scores, keep if >= thr_tok.
+ * mode SAST_SEL_PROBS : from post-softmax probabilities (win_prob [B,N], tok_prob [NW,T],
+ *   partitioned order) -- bit-exact twin of get_score_index_2d21d /
+ *   get_score_index_with_padding on identical fp32 inputs.
+ * mode SAST_SEL_FLAGS : from explicit keep flags (win_flag [NW], tok_flag [NW*T] uint8).
+ * thr_* are the fp32-cast thresholds float((1/N)/(1+BOUNCE)), float((1/T)/(1+BOUNCE)).
+ */
+enum sast_select_mode { SAST_SEL_SCORES = 0, SAST_SEL_PROBS = 1, SAST_SEL_FLAGS = 2 };
+typedef struct sast_select_args {
+  sast_geom g;
+  int32_t flavor;          /* SAST_WINDOW or SAST_GRID (how tok_score is partitioned) */
+  int32_t mode;
+  const float* tok_score;  /* SCORES */
+  const float* win_prob;   /* PROBS  */
+  const float* tok_prob;   /* PROBS  */
+  const uint8_t* win_flag; /* FLAGS  */
+  const uint8_t* tok_flag; /* FLAGS  */
+  float thr_win, thr_tok;
+  float* win_prob_out;     /* optional [B,N]: softmax probabilities (SCORES mode)  */
+  float* tok_prob_out;     /* optional [NW,T] */
+  sast_selection sel;      /* out */
+} sast_select_args;
+int sast_select(const sast_select_args* a, void* stream);
+
+/*
+ * a8-a13  one MS-WSA layer.  ref: SAST.py:199-255 (MS_WSA.forward).
+ *   n1 = LN1(x);  unselected tokens: out = n1.
+ *   selected tokens (compacted, S rows): n2 = LN2(n1); qkv = n2 Wqkv^T + b (head-major
+ *   [h][q,k,v][32]); per window softmax(q k^T / sqrt(32)) v over the window's selected
+ *   tokens only; y = n2 + g1 (o Wp^T + bp); out = y + g2 MLP_GLU(y); scattered back.
+ *   enable_cb: context broadcast (SAST.py:240-246).
+ */
+typedef struct sast_layer_weights {
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  const float *qkv_w, *qkv_b;   /* [3C,C], [3C] (bias may be NULL)                       */
+  const float *proj_w, *proj_b; /* [C,C], [C]                                             */
+  const float *gamma1, *gamma2; /* LayerScale [C] (NULL = identity)                       */
+  const float *mlp1_w, *mlp1_b; /* GLU proj, rows INTERLEAVED value_j, gate_j: [2I,C],[2I] */
+  const float *mlp2_w, *mlp2_b; /* [C,I], [C]                                             */
+  const uint16_t *qkv_w_bf16, *proj_w_bf16, *mlp1_w_bf16, *mlp2_w_bf16; /* SAST_BF16 only */
+  int32_t I;                    /* GLU width */
+  float ln_eps;
+} sast_layer_weights;
+
+typedef struct sast_layer_args {
+  sast_geom g;
+  int32_t flavor;
+  int32_t precision;
+  int32_t enable_cb;
+  const float* x;          /* in  [B,H,W,C] (or [NW,T,C] for SAST_FLAT) */
+  float* out;              /* out, same layout; must not alias x        */
+  sast_layer_weights w;
+  sast_selection sel;
+  void* workspace;
+  size_t workspace_bytes;  /* >= sast_layer_workspace_bytes(P, C, I, B, precision); 256-byte aligned */
+} sast_layer_args;
+size_t sast_layer_workspace_bytes(int64_t P, int32_t C, int32_t I, int32_t B, int32_t precision);
+int sast_layer_fwd(const sast_layer_args* a, void* stream);
+
+/* Standalone gather / scatter of the selected tokens (a9 / a13), for tests and the
+ * HBM-roofline microbenchmark: rows [S,C] <-> map tokens, through sel.row_tok. */
+int sast_gather(const sast_geom* g, int32_t flavor, const float* x, const sast_selection* sel,
+                float* rows, void* stream);
+int sast_scatter(const sast_geom* g, int32_t flavor, const float* rows, const sast_selection* sel,
+                 float* x, void* stream);
+
+/* D[M,N] = A[M,K] W[N,K]^T (+bias): bf16 in, fp32 accumulate on tcgen05, fp32 or bf16 out.
+ * Exposed for unit tests of the tensor-core path. */
+int sast_gemm_bf16(const uint16_t* A, const uint16_t* W, const float* bias, void* D, int32_t d_is_bf16,
+                   int32_t M, int32_t N, int32_t K, void* stream);
+
+/* Number of kernels this library has launched (or recorded into a CUDA graph) since it was
+ * loaded: a monotonically increasing statistics counter, the only process-wide state. */
+uint64_t sast_launch_count(void);
+
+/* Library / build info. */
+int sast_abi_version(void);
+/* sizeof of an ABI struct: 0 sast_geom, 1 sast_selection, 2 sast_score_args, 3 sast_select_args,
+ * 4 sast_layer_weights, 5 sast_layer_args (lets a foreign-language binding verify its mirror). */
+size_t sast_struct_size(int32_t which);
+const char* sast_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAST_B200_H_ */

@@ -1,0 +1,277 @@
+"""RVT-style recurrent backbone around the B200 SAST block -- host-side mirror of the
+reference's ``models/detection/recurrent_backbone/sast_rnn.py`` (+ ``models/layers/rnn.py`` and
+``ConvDownsampling_Cf2Cl`` of ``models/layers/SAST/ops.py``): same class names, constructor
+arguments, forward signature, attributes and state-dict keys, so ``YoloXDetector``
+(models/detection/yolox_extension/models/detector.py:19-41) can build and call it unedited.
+
+The SAST block (the hot path) runs in libsast_b200; the strided-conv stem / downsample and the
+1x1-conv LSTM on either side of it are dense cuDNN/cuBLAS calls kept channels-last so no
+NHWC<->NCHW copy is made (SURVEY.md section 8f lists them as the next rows to fuse)."""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .sast import SAST_block
+
+Tensor = torch.Tensor
+LstmState = Optional[Tuple[Tensor, Tensor]]
+
+
+@torch.no_grad()
+def non_zero_ratio(x: Tensor) -> Tensor:
+    """[B,Cin,H,W] -> [B,4,Cin] (ref: sast_rnn.py:45-60), one kernel, bit-exact."""
+    return ops.nonzero_ratio(x)
+
+
+class PositionEmbeddingSine(nn.Module):
+    """Fixed 2-D sine table (ref: sast_rnn.py:180-219).  ``forward`` returns the reference's
+    B-fold repeated tensor; the SAST block asks for ``table(x)`` ([H,W,C], no repeat) instead."""
+
+    def __init__(self, num_pos_feats=64, temperature=10000, normalize=False, scale=None, input_size=(128, 128, 128)):
+        super().__init__()
+        self.num_pos_feats = num_pos_feats
+        self.temperature = temperature
+        self.normalize = normalize
+        if scale is not None and normalize is False:
+            raise ValueError("normalize should be True if scale is passed")
+        self.scale = 2 * math.pi if scale is None else scale
+        self.pos_embedding = self.generate_position_embedding(input_size)
+
+    def generate_position_embedding(self, input_size) -> Tensor:
+        _, H, W = input_size
+        y = torch.arange(1, H + 1, dtype=torch.float32).view(1, H, 1).expand(1, H, W)
+        x = torch.arange(1, W + 1, dtype=torch.float32).view(1, 1, W).expand(1, H, W)
+        if self.normalize:
+            # tensor / tensor in fp32, as the reference does it (last cumsum entry + eps)
+            y = (y - 0.5) / (y[:, -1:, :] + 1e-6) * self.scale
+            x = (x - 0.5) / (x[:, :, -1:] + 1e-6) * self.scale
+        k = torch.arange(self.num_pos_feats, dtype=torch.float32)
+        div = self.temperature ** (2 * torch.div(k, 2, rounding_mode="floor") / self.num_pos_feats)
+        px, py = x[..., None] / div, y[..., None] / div
+        px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).flatten(3)
+        py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=4).flatten(3)
+        return torch.cat((py, px), dim=3)
+
+    def table(self, x: Tensor) -> Tensor:
+        H, W = x.shape[1:3]
+        if self.pos_embedding.device != x.device:
+            self.pos_embedding = self.pos_embedding.to(x.device)
+        return self.pos_embedding[0, :H, :W, :]
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.table(x).unsqueeze(0).repeat(x.shape[0], 1, 1, 1)
+
+
+class ConvDownsampling_Cf2Cl(nn.Module):
+    """NCHW in, NHWC out: overlapping strided conv (replicate padding, no bias) + LayerNorm
+    (ref: ops.py:54-95)."""
+
+    def __init__(self, dim_in: int, dim_out: int, downsample_factor: int, downsample_cfg):
+        super().__init__()
+        assert downsample_factor in (2, 4, 8)
+        norm_affine = downsample_cfg.get('norm_affine', True)
+        overlap = downsample_cfg.get('overlap', True)
+        if overlap:
+            kernel_size = (downsample_factor - 1) * 2 + 1
+            padding = kernel_size // 2
+        else:
+            kernel_size, padding = downsample_factor, 0
+        self.conv = nn.Conv2d(dim_in, dim_out, kernel_size=kernel_size, padding=padding, stride=downsample_factor,
+                              bias=False, padding_mode='replicate')
+        self.norm = nn.LayerNorm(dim_out, eps=1e-5, elementwise_affine=norm_affine)
+
+    def forward(self, x: Tensor) -> Tensor:
+        y = self.conv(x.contiguous(memory_format=torch.channels_last))
+        y = y.permute(0, 2, 3, 1)                      # NHWC view of the channels-last result
+        return self.norm(y if y.is_contiguous() else y.contiguous())
+
+    @staticmethod
+    def output_is_normed():
+        return True
+
+
+def get_downsample_layer_Cf2Cl(dim_in: int, dim_out: int, downsample_factor: int, downsample_cfg):
+    if downsample_cfg.type == 'patch':
+        return ConvDownsampling_Cf2Cl(dim_in, dim_out, downsample_factor, downsample_cfg)
+    raise NotImplementedError
+
+
+class DWSConvLSTM2d(nn.Module):
+    """Conv-LSTM cell, NCHW logical layout (ref: models/layers/rnn.py:7-69)."""
+
+    def __init__(self, dim: int, dws_conv: bool = True, dws_conv_only_hidden: bool = True,
+                 dws_conv_kernel_size: int = 3, cell_update_dropout: float = 0.):
+        super().__init__()
+        assert isinstance(dws_conv, bool) and isinstance(dws_conv_only_hidden, bool)
+        self.dim = dim
+        xh_dim, gates_dim = dim * 2, dim * 4
+        conv3x3_dws_dim = dim if dws_conv_only_hidden else xh_dim
+        self.conv3x3_dws = nn.Conv2d(conv3x3_dws_dim, conv3x3_dws_dim, kernel_size=dws_conv_kernel_size,
+                                     padding=dws_conv_kernel_size // 2, groups=conv3x3_dws_dim) if dws_conv else nn.Identity()
+        self.conv1x1 = nn.Conv2d(xh_dim, gates_dim, kernel_size=1)
+        self.conv_only_hidden = dws_conv_only_hidden
+        self.cell_update_dropout = nn.Dropout(p=cell_update_dropout)
+
+    def forward(self, x: Tensor, h_and_c_previous: LstmState = None) -> Tuple[Tensor, Tensor]:
+        if h_and_c_previous is None:
+            h_and_c_previous = (torch.zeros_like(x), torch.zeros_like(x))
+        h_tm1, c_tm1 = h_and_c_previous
+        if self.conv_only_hidden:
+            h_tm1 = self.conv3x3_dws(h_tm1)
+        xh = torch.cat((x, h_tm1), dim=1)
+        if not self.conv_only_hidden:
+            xh = self.conv3x3_dws(xh)
+        mix = self.conv1x1(xh)
+        gates, cell_input = torch.tensor_split(mix, [self.dim * 3], dim=1)
+        forget_gate, input_gate, output_gate = torch.tensor_split(torch.sigmoid(gates), 3, dim=1)
+        cell_input = self.cell_update_dropout(torch.tanh(cell_input))
+        c_t = forget_gate * c_tm1 + input_gate * cell_input
+        h_t = output_gate * torch.tanh(c_t)
+        return h_t, c_t
+
+
+class SASTAttentionPairCl(nn.Module):
+    """ref: sast_rnn.py:164-178"""
+
+    def __init__(self, dim: int, skip_first_norm: bool, attention_cfg, first_block: bool = False):
+        super().__init__()
+        self.att = SAST_block(dim=dim, attention_cfg=attention_cfg, first_block=first_block)
+        self.first_block = first_block
+
+    def forward(self, x: Tensor, pos_emb: nn.Module, r: Tensor, index_list):
+        x, p_loss, index_list = self.att(x, pos_emb, r, index_list)
+        return x, p_loss, r, index_list
+
+
+class RNNDetectorStage(nn.Module):
+    """NCHW in / NCHW out (ref: sast_rnn.py:221-287)."""
+
+    def __init__(self, dim_in: int, stage_dim: int, spatial_downsample_factor: int, num_blocks: int,
+                 enable_token_masking: bool, T_max_chrono_init: Optional[int], stage_cfg,
+                 overload_size: Tuple[int, int, int], enable_lstm: bool):
+        super().__init__()
+        assert isinstance(num_blocks, int) and num_blocks > 0
+        downsample_cfg, lstm_cfg, attention_cfg = stage_cfg.downsample, stage_cfg.lstm, stage_cfg.attention
+        self.downsample_cf2cl = get_downsample_layer_Cf2Cl(dim_in, stage_dim, spatial_downsample_factor, downsample_cfg)
+        self.att_blocks = nn.ModuleList([
+            SASTAttentionPairCl(dim=stage_dim, skip_first_norm=i == 0 and self.downsample_cf2cl.output_is_normed(),
+                                attention_cfg=attention_cfg, first_block=i == 0) for i in range(num_blocks)])
+        self.lstm = DWSConvLSTM2d(dim=stage_dim, dws_conv=lstm_cfg.dws_conv,
+                                  dws_conv_only_hidden=lstm_cfg.dws_conv_only_hidden,
+                                  dws_conv_kernel_size=lstm_cfg.dws_conv_kernel_size,
+                                  cell_update_dropout=lstm_cfg.get('drop_cell_update', 0)) if enable_lstm else None
+        self.pos_emb = PositionEmbeddingSine(stage_dim // 2, normalize=True, input_size=overload_size)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, 1, stage_dim), requires_grad=True) if enable_token_masking else None
+        if self.mask_token is not None:
+            torch.nn.init.normal_(self.mask_token, std=.02)
+
+    def forward(self, x: Tensor, h_and_c_previous: LstmState = None, token_mask: Optional[Tensor] = None,
+                r: Tensor = None):
+        x = self.downsample_cf2cl(x)                    # N C H W -> N H W C
+        if token_mask is not None:
+            assert self.mask_token is not None, 'No mask token present in this stage'
+            x[token_mask] = self.mask_token
+        P = 0
+        index_list = None
+        for blk in self.att_blocks:
+            x, p_loss, r, index_list = blk(x, self.pos_emb, r, index_list)
+            P += p_loss
+        x = x.permute(0, 3, 1, 2)                       # NCHW view, channels-last memory: no copy
+        if self.lstm is not None:
+            h_c_tuple = self.lstm(x, h_and_c_previous)
+            x = h_c_tuple[0]
+        else:
+            h_c_tuple = (x, x)
+        return x, h_c_tuple, P
+
+
+class BaseDetector(nn.Module):
+    def get_stage_dims(self, stages: Tuple[int, ...]) -> Tuple[int, ...]:
+        raise NotImplementedError
+
+    def get_strides(self, stages: Tuple[int, ...]) -> Tuple[int, ...]:
+        raise NotImplementedError
+
+
+class RNNDetector(BaseDetector):
+    """ref: sast_rnn.py:67-162"""
+
+    def __init__(self, mdl_config):
+        super().__init__()
+        in_channels = mdl_config.input_channels
+        embed_dim = mdl_config.embed_dim
+        dim_multiplier_per_stage = tuple(mdl_config.dim_multiplier)
+        num_blocks_per_stage = tuple(mdl_config.num_blocks)
+        T_max_chrono_init_per_stage = tuple(mdl_config.T_max_chrono_init)
+        enable_masking = mdl_config.enable_masking
+        num_stages = len(num_blocks_per_stage)
+        assert num_stages == 4
+        assert isinstance(embed_dim, int)
+        assert num_stages == len(dim_multiplier_per_stage) == len(T_max_chrono_init_per_stage)
+
+        compile_cfg = mdl_config.get('compile', None)
+        if compile_cfg is not None and compile_cfg.enable:
+            print('sast_b200: `compile.enable` ignored -- the backbone runs hand-written kernels, capture it in a '
+                  'CUDA graph instead (sast_b200.runner.GraphedBackbone)')
+
+        input_dim = in_channels
+        patch_size = mdl_config.stem.patch_size
+        stride = 1
+        self.stage_dims = [embed_dim * x for x in dim_multiplier_per_stage]
+        self.stages = nn.ModuleList()
+        self.strides = []
+        in_res_h, in_res_w = mdl_config.in_res_hw
+        initial_size = (1, in_res_h, in_res_w)
+        for stage_idx, (num_blocks, T_max) in enumerate(zip(num_blocks_per_stage, T_max_chrono_init_per_stage)):
+            factor = patch_size if stage_idx == 0 else 2
+            stage_dim = self.stage_dims[stage_idx]
+            overload_size = (1, initial_size[1] // factor, initial_size[2] // factor)
+            initial_size = overload_size
+            stage = RNNDetectorStage(dim_in=input_dim, stage_dim=stage_dim, spatial_downsample_factor=factor,
+                                     num_blocks=num_blocks, enable_token_masking=enable_masking and stage_idx == 0,
+                                     T_max_chrono_init=T_max, stage_cfg=mdl_config.stage, overload_size=overload_size,
+                                     enable_lstm=True)
+            stride = stride * factor
+            self.strides.append(stride)
+            input_dim = stage_dim
+            self.stages.append(stage)
+        self.num_stages = num_stages
+
+    def get_stage_dims(self, stages: Tuple[int, ...]) -> Tuple[int, ...]:
+        idx = [x - 1 for x in stages]
+        assert min(idx) >= 0 and max(idx) < len(self.stages), idx
+        return tuple(self.stage_dims[i] for i in idx)
+
+    def get_strides(self, stages: Tuple[int, ...]) -> Tuple[int, ...]:
+        idx = [x - 1 for x in stages]
+        assert min(idx) >= 0 and max(idx) < len(self.stages), idx
+        return tuple(self.strides[i] for i in idx)
+
+    def forward(self, x: Tensor, prev_states: Optional[List[LstmState]] = None, token_mask: Optional[Tensor] = None):
+        if prev_states is None:
+            prev_states = [None] * self.num_stages
+        assert len(prev_states) == self.num_stages
+        states: List[Tuple[Tensor, Tensor]] = []
+        output: Dict[int, Tensor] = {}
+        r = non_zero_ratio(x)
+        x = x.float()
+        P = []
+        for stage_idx, stage in enumerate(self.stages):
+            x, state, p = stage(x, prev_states[stage_idx], token_mask if stage_idx == 0 else None, r[:, stage_idx])
+            states.append(state)
+            output[stage_idx + 1] = state[0]
+            P.append(p)
+        return output, states, P
+
+
+def build_recurrent_backbone(backbone_cfg):
+    """ref: models/detection/recurrent_backbone/__init__.py:6-11"""
+    if backbone_cfg.name == 'SASTRNN':
+        return RNNDetector(backbone_cfg)
+    raise NotImplementedError

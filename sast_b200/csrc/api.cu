@@ -1,0 +1,26 @@
+// Library info entry points.
+#include "common.cuh"
+#include <atomic>
+
+static std::atomic<unsigned long long> g_launches{0};
+extern "C" void sast_count_launch_(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" uint64_t sast_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int sast_abi_version(void) { return SAST_ABI_VERSION; }
+
+extern "C" const char* sast_build_info(void) {
+  return "libsast_b200 abi " "1" " sm_100a nvcc " __DATE__;
+}
+
+// sizeof() of the ABI structs as this library was compiled, so that a binding can verify its mirror.
+extern "C" size_t sast_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(sast_geom);
+    case 1: return sizeof(sast_selection);
+    case 2: return sizeof(sast_score_args);
+    case 3: return sizeof(sast_select_args);
+    case 4: return sizeof(sast_layer_weights);
+    case 5: return sizeof(sast_layer_args);
+  }
+  return 0;
+}

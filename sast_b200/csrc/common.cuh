@@ -1,0 +1,96 @@
+// Shared device helpers for libsast_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/sast_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsast_b200 is written for sm_100a (NVIDIA B200) only"
+#endif
+
+#define SAST_CHECK_PTR(p) do { if ((p) == nullptr) return SAST_E_NULL; } while (0)
+// every kernel launch goes through this: error check + statistics counter (see sast_launch_count)
+extern "C" void sast_count_launch_(void);
+#define SAST_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; sast_count_launch_(); } while (0)
+
+namespace sast {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Geom {
+  int B, H, W, C, p0, p1, T, N, NW;
+  long long P;
+};
+
+__host__ __device__ inline Geom make_geom(const sast_geom& g, int flavor) {
+  Geom o;
+  o.B = g.B; o.H = g.H; o.W = g.W; o.C = g.C; o.p0 = g.p0; o.p1 = g.p1;
+  o.T = g.p0 * g.p1;
+  o.N = (g.H * g.W) / o.T;
+  o.NW = g.B * o.N;
+  o.P = (long long)g.B * g.H * g.W;
+  (void)flavor;
+  return o;
+}
+
+inline int check_geom(const sast_geom& g, int flavor) {
+  if (g.B <= 0 || g.H <= 0 || g.W <= 0 || g.C <= 0 || g.p0 <= 0 || g.p1 <= 0) return SAST_E_SHAPE;
+  if (flavor != SAST_FLAT && (g.H % g.p0 != 0 || g.W % g.p1 != 0)) return SAST_E_SHAPE;
+  if (flavor == SAST_FLAT && ((long long)g.H * g.W) % (g.p0 * g.p1) != 0) return SAST_E_SHAPE;
+  if (g.p0 * g.p1 > 128) return SAST_E_UNSUPPORTED;   // a window's tokens must fit one 128-row tile
+  if ((long long)g.B * g.H * g.W >= (1ll << 31) / 4) return SAST_E_UNSUPPORTED;
+  return SAST_OK;
+}
+
+// (window n of a frame, token t) -> pixel index inside the frame (y*W + x).
+// WINDOW: ops.py:189-195, GRID: ops.py:206-212, FLAT: identity on n*T+t.
+__device__ __forceinline__ int frame_pixel(int n, int t, int H, int W, int p0, int p1, int flavor) {
+  if (flavor == SAST_WINDOW) {
+    const int wj = W / p1;
+    const int i = n / wj, j = n - i * wj;
+    const int u = t / p1, v = t - u * p1;
+    return (i * p0 + u) * W + j * p1 + v;
+  } else if (flavor == SAST_GRID) {
+    const int wb = W / p1, ha = H / p0;
+    const int a = n / wb, b = n - a * wb;
+    const int gi = t / p1, gj = t - gi * p1;
+    return (gi * ha + a) * W + gj * wb + b;
+  }
+  return n * (p0 * p1) + t;
+}
+
+// token q = w*T + t in partitioned order -> global pixel index (b*H*W + y*W + x)
+__device__ __forceinline__ long long token_pixel(long long q, const Geom& g, int flavor) {
+  if (flavor == SAST_FLAT) return q;
+  const int w = (int)(q / g.T), t = (int)(q - (long long)w * g.T);
+  const int b = w / g.N, n = w - b * g.N;
+  return (long long)b * g.H * g.W + frame_pixel(n, t, g.H, g.W, g.p0, g.p1, flavor);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+}  // namespace sast

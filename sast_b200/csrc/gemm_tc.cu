@@ -1,0 +1,256 @@
+// Token-wise GEMMs of the MS-WSA layer on the 5th-gen tensor cores (SAST_BF16 path):
+//   D[M,N] = A[M,K] W[N,K]^T (+ bias) with the layer's fused epilogues (layer.cuh: Epi).
+// A = compacted activations (bf16, row-major = K-major), W = nn.Linear weight [N,K] (K-major):
+// the canonical TN shape, so both operands are TMA-loaded as SWIZZLE_128B tiles and fed to
+// tcgen05.mma straight from shared memory; the fp32 accumulator lives in TMEM.
+//
+// CTA = one 128 x BN output tile, 6 warps:
+//   warp 0   TMA producer   (one lane; ring of kStages {A 128x64, W BNx64} bf16 tiles)
+//   warp 1   TMEM allocator + MMA issuer (one lane; tcgen05.mma M=128,N=BN,K=16, 4 per k-block)
+//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns per warp (warp w owns TMEM lanes
+//            32*(w%4)..+31 = output rows), bias / LayerScale / residual / GLU / scatter in registers.
+// M (= number of selected tokens) is read from device memory; CTAs past it exit at once.
+// K tails (K % 64 != 0) rely on TMA zero fill and issue only the k-steps that hold data.
+#include "layer.cuh"
+#include "ptx.cuh"
+
+namespace sast {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192, TC_MAX_STAGES = 4;
+constexpr uint32_t TC_TMEM_COLS = 128;   // >= max BN, power of two
+
+struct TcSmem {            // lives after the operand ring (which needs 1024-byte alignment)
+  uint64_t full[TC_MAX_STAGES];
+  uint64_t empty[TC_MAX_STAGES];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
+  uint4 pk;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(v[0], v[1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[2], v[3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[4], v[5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[6], v[7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+  *reinterpret_cast<uint4*>(dst) = pk;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                             const __grid_constant__ CUtensorMap map_w,
+                                                             const float* __restrict__ bias, int N, int K, int BN, int stages,
+                                                             const int* __restrict__ counts, int m_static, EpiParams ep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int M = counts ? counts[1] : m_static;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  if (m0 >= M) return;
+
+  // carve shared memory: ring first (1024-aligned), bookkeeping after
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = TC_BM * TC_BK * 2, w_bytes = (uint32_t)BN * TC_BK * 2;
+  const uint32_t stage_bytes = a_bytes + w_bytes;
+  TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)stages * stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&map_a);
+    ptx::tma_prefetch_desc(&map_w);
+    for (int s = 0; s < stages; ++s) { ptx::mbar_init(&sm->full[s], 1); ptx::mbar_init(&sm->empty[s], 1); }
+    ptx::mbar_init(&sm->tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TC_TMEM_COLS>(&sm->tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_d = sm->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t round = (uint32_t)(kb / stages);
+        ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
+        uint8_t* sa = base + (size_t)s * stage_bytes;
+        ptx::mbar_arrive_expect_tx(&sm->full[s], stage_bytes);
+        ptx::tma_load_2d(sa, &map_a, &sm->full[s], kb * TC_BK, m0);
+        ptx::tma_load_2d(sa + a_bytes, &map_w, &sm->full[s], kb * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, (uint32_t)BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t round = (uint32_t)(kb / stages);
+        ptx::mbar_wait(&sm->full[s], round & 1);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
+        const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
+        const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
+        const int krem = K - kb * TC_BK;
+        const int ksteps = krem >= TC_BK ? 4 : (krem + 15) / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+          ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        }
+        ptx::umma_commit(&sm->empty[s]);          // frees the smem slot when these MMAs retire
+      }
+      ptx::umma_commit(&sm->tmem_full);           // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+    const int quarter = warp & 3;
+    const int row = m0 + quarter * 32 + lane;
+    ptx::mbar_wait(&sm->tmem_full, 0);
+    ptx::tc_fence_after();
+    const bool row_ok = row < M;
+    long long pix = 0;
+    if (EPI == EPI_SCATTER && row_ok) pix = token_pixel(ep.row_tok[row], ep.g, ep.flavor);
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t raw[32];
+      ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, raw);
+      ptx::tmem_ld_wait();
+      if (!row_ok) continue;
+      const int n = n0 + c0;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + n + j);
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      }
+      if (EPI == EPI_GLU) {
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+        __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n / 2;
+        store_bf16x8(dst, o);
+        store_bf16x8(dst + 8, o + 8);
+      } else {
+        if (EPI == EPI_RESID || EPI == EPI_SCATTER) {
+          const float* rp = ep.resid + (size_t)row * ep.ldr + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n + j);
+            v[j] = r4.x + g4.x * v[j]; v[j + 1] = r4.y + g4.y * v[j + 1];
+            v[j + 2] = r4.z + g4.z * v[j + 2]; v[j + 3] = r4.w + g4.w * v[j + 3];
+          }
+        }
+        if (ep.out_f32) {
+          float* dst = EPI == EPI_SCATTER ? ep.out_f32 + pix * ep.C + n : ep.out_f32 + (size_t)row * ep.ldo + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (EPI != EPI_SCATTER && ep.out_bf16) {
+          __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, v + j);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TC_TMEM_COLS>(tmem_d);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;     // idempotent lookup; benign race
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = 64 cols x box_rows, SWIZZLE_128B
+int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return (int)cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+template <int EPI>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* bias, int N, int K, int BN, const int* counts,
+                     long long max_rows, int m_static, const EpiParams& ep, cudaStream_t st) {
+  const int nkb = (K + TC_BK - 1) / TC_BK;
+  const int stages = nkb < TC_MAX_STAGES ? nkb : TC_MAX_STAGES;
+  const size_t smem = 1024 + (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + sizeof(TcSmem);
+  static bool attr_done = false;   // per-instantiation; the attribute is idempotent
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  const dim3 grid((unsigned)((max_rows + TC_BM - 1) / TC_BM), (unsigned)(N / BN));
+  gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(ma, mw, bias, N, K, BN, stages, counts, m_static, ep);
+  SAST_LAUNCH_CHECK();
+  return SAST_OK;
+}
+
+static int pick_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : (N % 32 == 0 ? 32 : 0)); }
+
+int launch_gemm_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, int N, int K, const int* counts,
+                   long long max_rows, int epi, const EpiParams& ep, cudaStream_t st) {
+  const int BN = pick_bn(N);
+  if (BN == 0 || K % 8 != 0 || lda % 8 != 0) return SAST_E_SHAPE;
+  CUtensorMap ma, mw;
+  int rc = make_tmap_bf16_2d(&ma, A, max_rows, K, lda, TC_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&mw, W, N, K, K, BN);
+  if (rc) return rc;
+  switch (epi) {
+    case EPI_STORE: return launch_tc<EPI_STORE>(ma, mw, bias, N, K, BN, counts, max_rows, 0, ep, st);
+    case EPI_RESID: return launch_tc<EPI_RESID>(ma, mw, bias, N, K, BN, counts, max_rows, 0, ep, st);
+    case EPI_GLU: return launch_tc<EPI_GLU>(ma, mw, bias, N, K, BN, counts, max_rows, 0, ep, st);
+    case EPI_SCATTER: return launch_tc<EPI_SCATTER>(ma, mw, bias, N, K, BN, counts, max_rows, 0, ep, st);
+  }
+  return SAST_E_UNSUPPORTED;
+}
+
+}  // namespace sast
+
+extern "C" int sast_gemm_bf16(const uint16_t* A, const uint16_t* W, const float* bias, void* D, int32_t d_is_bf16, int32_t M,
+                              int32_t N, int32_t K, void* stream) {
+  using namespace sast;
+  SAST_CHECK_PTR(A); SAST_CHECK_PTR(W); SAST_CHECK_PTR(D);
+  if (M <= 0 || N <= 0 || K <= 0) return SAST_E_SHAPE;
+  const int BN = pick_bn(N);
+  if (BN == 0 || K % 8 != 0) return SAST_E_SHAPE;
+  CUtensorMap ma, mw;
+  int rc = make_tmap_bf16_2d(&ma, A, M, K, K, TC_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&mw, W, N, K, K, BN);
+  if (rc) return rc;
+  EpiParams ep{};
+  ep.ldo = N;
+  if (d_is_bf16) ep.out_bf16 = (__nv_bfloat16*)D; else ep.out_f32 = (float*)D;
+  return launch_tc<EPI_STORE>(ma, mw, bias, N, K, BN, nullptr, M, M, ep, (cudaStream_t)stream);
+}

@@ -1,0 +1,372 @@
+"""torch custom ops (`torch.ops.sast.*`) over the C ABI of libsast_b200.so.
+
+Every op takes/returns fp32 NHWC CUDA tensors, launches on the current CUDA stream, never
+synchronises with the host and has no CPU implementation: calling one with CPU tensors raises.
+Selections live on the device inside an int32 "pool" tensor (see ``sast_selection`` in
+include/sast_b200.h); :class:`Selection` binds a pool to the C struct and can lazily
+materialise the reference's index lists when a caller really asks for them."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+
+
+def _geom(B, H, W, Cc, p0, p1) -> L.Geom:
+    return L.Geom(int(B), int(H), int(W), int(Cc), int(p0), int(p1))
+
+
+def _f32c(t: Tensor, name: str) -> Tensor:
+    L.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def thresholds(N: int, T: int, bounce: float) -> Tuple[float, float]:
+    """fp32-cast thresholds exactly as torch evaluates ``x >= d / (1 + b)`` (SAST.py:262,272)."""
+    return float(np.float32((1 / N) / (1 + bounce))), float(np.float32((1 / T) / (1 + bounce)))
+
+
+# --------------------------------------------------------------------------------------------
+# a1  non_zero_ratio
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("sast::nonzero_ratio", mutates_args=())
+def nonzero_ratio(x: Tensor) -> Tensor:
+    L.require_cuda(x, "x")
+    if x.dtype == torch.uint8:
+        dt = L.U8
+    elif x.dtype == torch.int32:
+        dt = L.I32
+    elif x.dtype == torch.float32:
+        dt = L.F32
+    else:  # other integer / float types: one cast, same values
+        x = x.to(torch.float32 if x.is_floating_point() else torch.int32)
+        dt = L.F32 if x.is_floating_point() else L.I32
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    r = torch.empty(B, 4, Cin, device=x.device, dtype=torch.float32)
+    L.check(L.lib().sast_nonzero_ratio(x.data_ptr(), dt, B, Cin, H, W, r.data_ptr(), L.stream_ptr(x.device)),
+            "sast_nonzero_ratio")
+    return r
+
+
+@nonzero_ratio.register_fake
+def _(x):
+    return x.new_empty(x.shape[0], 4, x.shape[1], dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# a4  scoring + STP weighting
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("sast::score_fwd", mutates_args=())
+def score_fwd(x: Tensor, pos: Tensor, r: Tensor, ctrl_w: Tensor, score_w: Tensor, score_b: Tensor,
+              amp: float) -> Tuple[Tensor, Tensor]:
+    x = _f32c(x, "x")
+    B, H, W, Cc = x.shape
+    pos = _f32c(pos, "pos")
+    if pos.dim() == 4 and pos.shape[0] == 1:
+        pos = pos[0]
+    pstride = 0 if pos.dim() == 3 else H * W * Cc
+    assert pos.shape[-3:] == (H, W, Cc), f"pos shape {tuple(pos.shape)} does not match x {tuple(x.shape)}"
+    r = _f32c(r, "r")
+    xw = torch.empty_like(x)
+    tok = torch.empty(B, H, W, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(2 * B * Cc, device=x.device, dtype=torch.float32)
+    a = L.ScoreArgs(_geom(B, H, W, Cc, 1, 1), x.data_ptr(), pos.data_ptr(), pstride, r.data_ptr(), r.shape[1],
+                    _f32c(ctrl_w, "ctrl_w").data_ptr(), _f32c(score_w, "score_w").data_ptr(),
+                    _f32c(score_b, "score_b").data_ptr(), float(amp), xw.data_ptr(), tok.data_ptr(),
+                    scratch.data_ptr())
+    L.check(L.lib().sast_score_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_score_fwd")
+    return xw, tok
+
+
+@score_fwd.register_fake
+def _(x, pos, r, ctrl_w, score_w, score_b, amp):
+    return torch.empty_like(x, dtype=torch.float32), x.new_empty(x.shape[:3], dtype=torch.float32)
+
+
+@torch.library.custom_op("sast::add_pos", mutates_args=())
+def add_pos(x: Tensor, pos: Tensor) -> Tensor:
+    x = _f32c(x, "x")
+    B, H, W, Cc = x.shape
+    pos = _f32c(pos, "pos")
+    if pos.dim() == 4 and pos.shape[0] == 1:
+        pos = pos[0]
+    pstride = 0 if pos.dim() == 3 else H * W * Cc
+    out = torch.empty_like(x)
+    a = L.ScoreArgs(_geom(B, H, W, Cc, 1, 1), x.data_ptr(), pos.data_ptr(), pstride, 0, 0, 0, 0, 0, 0.0,
+                    out.data_ptr(), 0, 0)
+    L.check(L.lib().sast_score_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_score_fwd(add_pos)")
+    return out
+
+
+@add_pos.register_fake
+def _(x, pos):
+    return torch.empty_like(x, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# a5/a6  selection
+# --------------------------------------------------------------------------------------------
+def _pool_alloc(B, NW, P, device) -> Tensor:
+    nbytes = L.lib().sast_selection_bytes(B, NW, P)
+    return torch.empty((nbytes + 3) // 4, device=device, dtype=torch.int32)
+
+
+def _bind(pool: Tensor, B, NW, P) -> L.Selection:
+    s = L.Selection()
+    L.check(L.lib().sast_selection_bind(pool.data_ptr(), B, NW, P, C.byref(s)), "sast_selection_bind")
+    return s
+
+
+def _select_impl(mode: int, B, H, W, p0, p1, flavor, thr_win, thr_tok, device, tok_score=None, win_prob=None,
+                 tok_prob=None, win_flag=None, tok_flag=None, want_probs=False):
+    T = p0 * p1
+    N = (H * W) // T
+    NW, P = B * N, B * H * W
+    pool = _pool_alloc(B, NW, P, device)
+    sel = _bind(pool, B, NW, P)
+    wp = torch.empty(B, N, device=device, dtype=torch.float32) if want_probs else None
+    tp = torch.zeros(NW, T, device=device, dtype=torch.float32) if want_probs else None
+    a = L.SelectArgs(_geom(B, H, W, 32, p0, p1), int(flavor), mode, L.ptr(tok_score), L.ptr(win_prob),
+                     L.ptr(tok_prob), L.ptr(win_flag), L.ptr(tok_flag), float(thr_win), float(thr_tok),
+                     L.ptr(wp), L.ptr(tp), sel)
+    L.check(L.lib().sast_select(C.byref(a), L.stream_ptr(device)), "sast_select")
+    return pool, wp, tp
+
+
+@torch.library.custom_op("sast::select", mutates_args=())
+def select(tok_score: Tensor, p0: int, p1: int, flavor: int, thr_win: float, thr_tok: float) -> Tensor:
+    tok_score = _f32c(tok_score, "tok_score")
+    B, H, W = tok_score.shape
+    return _select_impl(L.SEL_SCORES, B, H, W, p0, p1, flavor, thr_win, thr_tok, tok_score.device,
+                        tok_score=tok_score)[0]
+
+
+@select.register_fake
+def _(tok_score, p0, p1, flavor, thr_win, thr_tok):
+    B, H, W = tok_score.shape
+    n = (8 + 4 * (B * H * W // (p0 * p1)) * 3 + 2 * B * H * W + 64) * 2
+    return tok_score.new_empty(n, dtype=torch.int32)
+
+
+def select_with_probs(tok_score: Tensor, p0, p1, flavor, thr_win, thr_tok):
+    """Like :func:`select` but also returns the softmax probabilities the kernel thresholded."""
+    tok_score = _f32c(tok_score, "tok_score")
+    B, H, W = tok_score.shape
+    return _select_impl(L.SEL_SCORES, B, H, W, p0, p1, flavor, thr_win, thr_tok, tok_score.device,
+                        tok_score=tok_score, want_probs=True)
+
+
+def select_from_probs(win_prob: Tensor, tok_prob: Tensor, H: int, W: int, p0: int, p1: int, thr_win: float,
+                      thr_tok: float) -> Tensor:
+    """Tier-A twin of get_score_index_2d21d / get_score_index_with_padding: thresholds on given
+    fp32 probabilities.  win_prob [B,N]; tok_prob [B*N,T] (rows of dropped windows are ignored)."""
+    win_prob, tok_prob = _f32c(win_prob, "win_prob"), _f32c(tok_prob, "tok_prob")
+    B = win_prob.shape[0]
+    return _select_impl(L.SEL_PROBS, B, H, W, p0, p1, L.FLAT, thr_win, thr_tok, win_prob.device,
+                        win_prob=win_prob, tok_prob=tok_prob)[0]
+
+
+def select_from_flags(win_flag: Tensor, tok_flag: Tensor, B: int, H: int, W: int, p0: int, p1: int) -> Tensor:
+    L.require_cuda(win_flag, "win_flag")
+    win_flag = win_flag.to(torch.uint8).contiguous()
+    tok_flag = tok_flag.to(torch.uint8).contiguous()
+    return _select_impl(L.SEL_FLAGS, B, H, W, p0, p1, L.FLAT, 0.0, 0.0, win_flag.device, win_flag=win_flag,
+                        tok_flag=tok_flag)[0]
+
+
+class Selection:
+    """One layer's device-resident selection (replaces the reference's index list
+    [index_window, index_token, padding_index, asy_index, K], SAST.py:123).
+
+    Behaves like that 5-element list when indexed / iterated -- the int64 tensors are built on
+    first use (this synchronises with the device; the fast path never does it)."""
+
+    def __init__(self, pool: Tensor, B: int, H: int, W: int, p0: int, p1: int,
+                 tok_prob: Optional[Tensor] = None, given: Optional[Sequence[Tensor]] = None):
+        self.pool, self.B, self.H, self.W, self.p0, self.p1 = pool, B, H, W, p0, p1
+        self.T = p0 * p1
+        self.N = (H * W) // self.T
+        self.NW, self.P = B * self.N, B * H * W
+        self.struct = _bind(pool, B, self.NW, self.P)
+        self.tok_prob = tok_prob
+        self._lists = list(given) if given is not None else None
+
+    # -- device views (no sync) -------------------------------------------------------------
+    def _view(self, field: str, n: int) -> Tensor:
+        off = (getattr(self.struct, field) - self.pool.data_ptr()) // 4
+        return self.pool[off:off + n]
+
+    @property
+    def counts(self) -> Tensor:
+        return self._view("counts", 8)
+
+    @property
+    def win_K(self) -> Tensor:
+        return self._view("win_K", self.NW)
+
+    @property
+    def tok_row(self) -> Tensor:
+        return self._view("tok_row", self.P)
+
+    @property
+    def row_tok(self) -> Tensor:
+        return self._view("row_tok", self.P)
+
+    @property
+    def sel_win(self) -> Tensor:
+        return self._view("sel_win", self.NW)
+
+    # -- reference-style lists (syncs) ----------------------------------------------------------
+    def lists(self) -> List[Tensor]:
+        if self._lists is None:
+            M, S, Kmax = self.counts[:3].tolist()
+            iw = self.sel_win[:M].long()
+            K = self.win_K[iw].long()
+            q = self.row_tok[:S].long()                       # token ids w*T+t, ascending
+            rank = self._view("win_rank", self.NW).long()
+            asy = rank[q // self.T] * self.T + q % self.T   # compacted [M*T] space
+            # index_token = selected U padding per window, Kmax entries, padding = highest-probability
+            # unselected tokens (what torch.topk(sorted=False) returns as a set); order is arbitrary.
+            keep = torch.zeros(M * self.T, dtype=torch.bool, device=self.pool.device)
+            keep[asy] = True
+            if self.tok_prob is not None:
+                pr = self.tok_prob.view(self.NW, self.T)[iw]
+            else:
+                pr = torch.zeros(M, self.T, device=self.pool.device)
+            key = pr + keep.view(M, self.T).float() * 2.0     # selected first, then by probability
+            top = torch.topk(key, k=max(Kmax, 0), dim=1, sorted=False)[1] if M > 0 else key.new_zeros(0, 0).long()
+            it = (top + torch.arange(M, device=top.device).view(-1, 1) * self.T).reshape(-1)
+            pad = it[~keep[it]]
+            self._lists = [iw, it, pad, asy, K]
+        return self._lists
+
+    def __iter__(self):
+        return iter(self.lists())
+
+    def __getitem__(self, i):
+        return self.lists()[i]
+
+    def __len__(self):
+        return 5
+
+    def num_selected(self) -> Tensor:
+        """S as a 0-dim device tensor (no sync)."""
+        return self.counts[1]
+
+
+def selection_from_lists(index_window: Tensor, asy_index: Tensor, B: int, H: int, W: int, p0: int, p1: int,
+                         given: Optional[Sequence[Tensor]] = None) -> Selection:
+    """Build a device selection from reference-style index tensors (MS_WSA.forward called with
+    explicit indices, SAST.py:199-201)."""
+    T = p0 * p1
+    NW = B * (H * W // T)
+    dev = index_window.device
+    wf = torch.zeros(NW, dtype=torch.uint8, device=dev)
+    wf[index_window.long()] = 1
+    tf = torch.zeros(NW * T, dtype=torch.uint8, device=dev)
+    if asy_index.numel():
+        a = asy_index.long()
+        tf[index_window.long()[a // T] * T + a % T] = 1
+    pool = select_from_flags(wf, tf, B, H, W, p0, p1)
+    return Selection(pool, B, H, W, p0, p1, given=given)
+
+
+# --------------------------------------------------------------------------------------------
+# a8-a13  one MS-WSA layer
+# --------------------------------------------------------------------------------------------
+WEIGHT_ORDER = ("ln1_w", "ln1_b", "ln2_w", "ln2_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "gamma1", "gamma2",
+                "mlp1_w", "mlp1_b", "mlp2_w", "mlp2_b", "qkv_w_bf16", "proj_w_bf16", "mlp1_w_bf16", "mlp2_w_bf16")
+
+
+@torch.library.custom_op("sast::layer_fwd", mutates_args=())
+def layer_fwd(x: Tensor, pool: Tensor, weights: List[Tensor], p0: int, p1: int, flavor: int, precision: int,
+              enable_cb: bool, mlp_inner: int, ln_eps: float) -> Tensor:
+    """x [B,H,W,C] fp32 NHWC -> same shape (flavor WINDOW or GRID)."""
+    x = _f32c(x, "x")
+    L.require_cuda(pool, "pool")
+    B, H, W, Cc = x.shape
+    g = _geom(B, H, W, Cc, p0, p1)
+    out = torch.empty_like(x)
+    P = x.numel() // Cc
+    lib = L.lib()
+    sel = _bind(pool, g.B, (g.H * g.W // (g.p0 * g.p1)) * g.B, P)
+    nbytes = lib.sast_layer_workspace_bytes(P, Cc, mlp_inner, g.B, precision)
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    w = L.LayerWeights()
+    assert len(weights) == len(WEIGHT_ORDER)
+    for name, t in zip(WEIGHT_ORDER, weights):
+        setattr(w, name, t.data_ptr() if t.numel() else 0)
+    w.I, w.ln_eps = int(mlp_inner), float(ln_eps)
+    a = L.LayerArgs(g, int(flavor), int(precision), int(bool(enable_cb)), x.data_ptr(), out.data_ptr(), w, sel,
+                    ws.data_ptr(), nbytes)
+    L.check(lib.sast_layer_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_layer_fwd")
+    return out
+
+
+@layer_fwd.register_fake
+def _(x, pool, weights, p0, p1, flavor, precision, enable_cb, mlp_inner, ln_eps):
+    return torch.empty_like(x, dtype=torch.float32)
+
+
+def layer_fwd_flat(x: Tensor, sel: Selection, weights, precision, enable_cb, mlp_inner, ln_eps, B: int) -> Tensor:
+    """MS_WSA on an already partitioned [B*N,T,C] tensor (frames matter only for context broadcast)."""
+    x = _f32c(x, "x")
+    NWn, T, Cc = x.shape
+    out = torch.empty_like(x)
+    lib = L.lib()
+    N = NWn // B
+    g = _geom(B, N, T, Cc, 1, T)   # FLAT: a "frame" is N rows of T tokens, window n = row n
+    nbytes = lib.sast_layer_workspace_bytes(NWn * T, Cc, mlp_inner, B, precision)
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    w = L.LayerWeights()
+    for name, t in zip(WEIGHT_ORDER, weights):
+        setattr(w, name, t.data_ptr() if t.numel() else 0)
+    w.I, w.ln_eps = int(mlp_inner), float(ln_eps)
+    a = L.LayerArgs(g, L.FLAT, int(precision), int(bool(enable_cb)), x.data_ptr(), out.data_ptr(), w,
+                    sel.struct, ws.data_ptr(), nbytes)
+    L.check(lib.sast_layer_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_layer_fwd")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# standalone gather / scatter and the tensor-core GEMM (tests, microbenchmarks)
+# --------------------------------------------------------------------------------------------
+def gather_rows(x: Tensor, sel: Selection, flavor: int) -> Tensor:
+    x = _f32c(x, "x")
+    Cc = x.shape[-1]
+    rows = torch.zeros(sel.P, Cc, device=x.device, dtype=torch.float32)
+    g = _geom(sel.B, sel.H, sel.W, Cc, sel.p0, sel.p1)
+    L.check(L.lib().sast_gather(C.byref(g), flavor, x.data_ptr(), C.byref(sel.struct), rows.data_ptr(),
+                                L.stream_ptr(x.device)), "sast_gather")
+    return rows
+
+
+def scatter_rows(rows: Tensor, sel: Selection, flavor: int, x: Tensor) -> Tensor:
+    """In place: x[token of row r] = rows[r] for the S selected rows."""
+    rows = _f32c(rows, "rows")
+    Cc = x.shape[-1]
+    g = _geom(sel.B, sel.H, sel.W, Cc, sel.p0, sel.p1)
+    L.check(L.lib().sast_scatter(C.byref(g), flavor, rows.data_ptr(), C.byref(sel.struct), x.data_ptr(),
+                                 L.stream_ptr(x.device)), "sast_scatter")
+    return x
+
+
+def gemm_bf16(A: Tensor, Wt: Tensor, bias: Optional[Tensor] = None, out_bf16: bool = False) -> Tensor:
+    """D = A @ Wt.T (+ bias) on tcgen05; A [M,K] bf16, Wt [N,K] bf16."""
+    L.require_cuda(A, "A")
+    A, Wt = A.contiguous(), Wt.contiguous()
+    M, K = A.shape
+    N = Wt.shape[0]
+    D = torch.empty(M, N, device=A.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    L.check(L.lib().sast_gemm_bf16(A.data_ptr(), Wt.data_ptr(), L.ptr(bias), D.data_ptr(), int(out_bf16), M, N, K,
+                                   L.stream_ptr(A.device)), "sast_gemm_bf16")
+    return D

@@ -1,0 +1,374 @@
+"""SAST block on B200 -- host-side mirror of the reference's ``models/layers/SAST/SAST.py``
+and ``models/layers/SAST/ops.py`` (same class names, constructor arguments, forward
+signatures and state-dict keys), executing through ``torch.ops.sast.*`` (libsast_b200.so).
+
+What differs from the reference, by design:
+  * the feature map stays NHWC end to end -- window / grid partitions are index maps inside
+    the kernels, never copies (ref ops.py:189-220 copies the map 7 times per block);
+  * selection lives on the device (:class:`sast_b200.ops.Selection`); ``forward`` never
+    synchronises.  The returned ``index_count`` is a :class:`LazyCount` and each entry of the
+    returned index list behaves like the reference's 5-tensor list on demand;
+  * there is no CPU path: parameters and inputs must be CUDA tensors.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+
+Tensor = torch.Tensor
+
+
+def default_precision() -> int:
+    """SAST_B200_PRECISION=fp32 selects the CUDA-core validation path; default bf16 tensor cores."""
+    return L.FP32 if os.environ.get("SAST_B200_PRECISION", "bf16").lower() == "fp32" else L.BF16
+
+
+# ------------------------------------------------------------------------------------------
+# small pieces of ops.py the block is built from (state-dict compatible)
+# ------------------------------------------------------------------------------------------
+class LayerScale(nn.Module):
+    """ref: ops.py:178-186"""
+
+    def __init__(self, dim: int, init_values: float = 1e-5, inplace: bool = False):
+        super().__init__()
+        self.inplace = inplace
+        self.gamma = nn.Parameter(init_values * torch.ones(dim))
+
+    def forward(self, x):
+        return x.mul_(self.gamma) if self.inplace else x * self.gamma
+
+
+class GLU(nn.Module):
+    """ref: ops.py:111-137 (channel-last only here)"""
+
+    def __init__(self, dim_in: int, dim_out: int, channel_last: bool = True, act_layer=nn.GELU, bias: bool = True):
+        super().__init__()
+        assert channel_last, "sast_b200 keeps everything channel-last"
+        self.proj = nn.Linear(dim_in, dim_out * 2, bias=bias)
+        self.act_layer = act_layer()
+
+    def forward(self, x):
+        val, gate = torch.tensor_split(self.proj(x), 2, dim=-1)
+        return val * self.act_layer(gate)
+
+
+class MLP(nn.Module):
+    """ref: ops.py:140-175.  Gated (GLU) by default with inner width floor(dim*ratio*2/3/32)*32."""
+
+    def __init__(self, dim: int, channel_last: bool = True, expansion_ratio: int = 4, act_layer=nn.GELU,
+                 gated: bool = True, bias: bool = True, drop_prob: float = 0.):
+        super().__init__()
+        assert channel_last and gated, "sast_b200 implements the gated channel-last MLP the reference instantiates"
+        inner = math.floor(int(dim * expansion_ratio) * 2 / 3 / 32) * 32
+        self.inner_dim = inner
+        self.net = nn.Sequential(GLU(dim, inner, True, act_layer, bias), nn.Dropout(p=drop_prob),
+                                 nn.Linear(inner, dim, bias=bias))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+def _act_layer(name: str):
+    if name != "gelu":
+        raise NotImplementedError(f"mlp_activation={name!r}: the fused GLU epilogue implements erf-GELU only")
+    return nn.GELU
+
+
+# index maps of ops.py:189-220, kept for API parity (the kernels never call them)
+def window_partition(x: Tensor, window_size: Tuple[int, int]) -> Tensor:
+    B, H, W, C = x.shape
+    assert H % window_size[0] == 0, f'height ({H}) must be divisible by window ({window_size[0]})'
+    assert W % window_size[1] == 0, f'width ({W}) must be divisible by window ({window_size[1]})'
+    x = x.reshape(B, H // window_size[0], window_size[0], W // window_size[1], window_size[1], C)
+    return x.permute(0, 1, 3, 2, 4, 5).reshape(-1, window_size[0], window_size[1], C)
+
+
+def window_reverse(windows: Tensor, window_size: Tuple[int, int], img_size: Tuple[int, int]) -> Tensor:
+    H, W = img_size
+    C = windows.shape[-1]
+    x = windows.reshape(-1, H // window_size[0], W // window_size[1], window_size[0], window_size[1], C)
+    return x.permute(0, 1, 3, 2, 4, 5).reshape(-1, H, W, C)
+
+
+def grid_partition(x: Tensor, grid_size: Tuple[int, int]) -> Tensor:
+    B, H, W, C = x.shape
+    assert H % grid_size[0] == 0, f'height {H} must be divisible by grid {grid_size[0]}'
+    assert W % grid_size[1] == 0, f'width {W} must be divisible by grid {grid_size[1]}'
+    x = x.reshape(B, grid_size[0], H // grid_size[0], grid_size[1], W // grid_size[1], C)
+    return x.permute(0, 2, 4, 1, 3, 5).reshape(-1, grid_size[0], grid_size[1], C)
+
+
+def grid_reverse(windows: Tensor, grid_size: Tuple[int, int], img_size: Tuple[int, int]) -> Tensor:
+    H, W = img_size
+    C = windows.shape[-1]
+    x = windows.reshape(-1, H // grid_size[0], W // grid_size[1], grid_size[0], grid_size[1], C)
+    return x.permute(0, 3, 1, 4, 2, 5).reshape(-1, H, W, C)
+
+
+# ------------------------------------------------------------------------------------------
+class LazyCount:
+    """Selected-token count kept on the device; turns into a Python number when used as one.
+
+    The reference returns ``len(asy_index) // B`` (SAST.py:136,159), which costs a host sync
+    per layer.  Callers only ever add these up and divide (modules/detection.py:158,196-199)."""
+
+    __slots__ = ("_t",)
+
+    def __init__(self, t: Tensor):
+        self._t = t
+
+    def __int__(self):
+        return int(self._t.item())
+
+    __index__ = __int__
+
+    def __float__(self):
+        return float(int(self))
+
+    def __add__(self, other):
+        if isinstance(other, LazyCount):
+            return LazyCount(self._t + other._t)
+        if isinstance(other, int) and other == 0:
+            return self
+        return int(self) + other
+
+    __radd__ = __add__
+
+    def __sub__(self, o): return int(self) - o
+    def __rsub__(self, o): return o - int(self)
+    def __mul__(self, o): return int(self) * o
+    __rmul__ = __mul__
+    def __truediv__(self, o): return int(self) / o
+    def __rtruediv__(self, o): return o / int(self)
+    def __floordiv__(self, o): return int(self) // o
+    def __eq__(self, o): return int(self) == o
+    def __lt__(self, o): return int(self) < o
+    def __le__(self, o): return int(self) <= o
+    def __gt__(self, o): return int(self) > o
+    def __ge__(self, o): return int(self) >= o
+    def __hash__(self): return hash(int(self))
+    def __repr__(self): return f"LazyCount({int(self)})"
+    def __format__(self, spec): return format(int(self), spec)
+
+
+class PositiveLinear(nn.Module):
+    """Linear layer with exp()-positive weights (ref: SAST.py:305-328).  The product is folded
+    into the scoring kernel; ``forward`` exists for API parity."""
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_features))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1 / math.sqrt(self.in_features)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, input):
+        return nn.functional.linear(input, torch.exp(self.weight), self.bias)
+
+
+class MS_WSA(nn.Module):
+    """Masked Sparse Window (multi-head) Self-Attention, channels-last (ref: SAST.py:167-255).
+
+    Parameters are laid out exactly as in the reference (including the ``sub_layers`` aliases,
+    SAST.py:194); compute happens in ``torch.ops.sast.layer_fwd``."""
+
+    def __init__(self, dim: int, dim_head: int = 32, bias: bool = True,
+                 sub_layer_params: Optional[Sequence] = None, norms: Sequence[nn.Module] = None):
+        super().__init__()
+        if dim_head != 32 or dim % 32 != 0:
+            raise NotImplementedError("libsast_b200 attention kernels are built for dim_head == 32")
+        self.num_heads = dim // dim_head
+        self.dim_head = dim_head
+        self.scale = dim_head ** -0.5
+        self.dim = dim
+        self.qkv = nn.Linear(dim, dim * 3, bias=bias)
+        self.proj = nn.Linear(dim, dim, bias=bias)
+        self.norm1 = norms[0]
+        ls_init_value, drop_path, mlp_expand_ratio, mlp_act_layer, mlp_bias, drop_mlp = sub_layer_params
+        if drop_path > 0 or drop_mlp > 0:
+            raise NotImplementedError("drop_path / drop_mlp > 0 are not fused (shipped configs use 0)")
+        self.ls1 = LayerScale(dim=dim, init_values=ls_init_value) if ls_init_value > 0 else nn.Identity()
+        self.drop1 = nn.Identity()
+        self.norm2 = norms[1]
+        self.mlp = MLP(dim=dim, channel_last=True, expansion_ratio=mlp_expand_ratio, act_layer=mlp_act_layer,
+                       bias=mlp_bias, drop_prob=drop_mlp)
+        self.ls2 = LayerScale(dim=dim, init_values=ls_init_value) if ls_init_value > 0 else nn.Identity()
+        self.drop2 = nn.Identity()
+        self.sub_layers = nn.ModuleList([self.ls1, self.drop1, self.norm2, self.mlp, self.ls2, self.drop2])
+        self.eps = 1e-6
+        self.precision = default_precision()
+        self._pack_key = None
+        self._packed: Optional[List[Tensor]] = None
+
+    # -- weights in the order the C ABI wants them (sast_layer_weights) ------------------------
+    def packed_weights(self) -> List[Tensor]:
+        glu = self.mlp.net[0].proj
+        out = self.mlp.net[2]
+        srcs = [self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias, self.qkv.weight,
+                self.qkv.bias, self.proj.weight, self.proj.bias,
+                getattr(self.ls1, "gamma", None), getattr(self.ls2, "gamma", None),
+                glu.weight, glu.bias, out.weight, out.bias]
+        key = tuple((None if t is None else (t.data_ptr(), t._version)) for t in srcs) + (self.precision,)
+        if key == self._pack_key:
+            return self._packed
+        dev = self.qkv.weight.device
+        L.require_cuda(self.qkv.weight, "MS_WSA parameters")
+        empty = torch.empty(0, device=dev)
+        I = self.mlp.inner_dim
+
+        def f(t):
+            return empty if t is None else t.detach().float().contiguous()
+
+        # GLU rows interleaved value_j, gate_j so that the GEMM epilogue sees each pair side by side
+        w1 = glu.weight.detach().float()
+        w1i = torch.stack((w1[:I], w1[I:]), dim=1).reshape(2 * I, -1).contiguous()
+        b1i = empty if glu.bias is None else torch.stack((glu.bias.detach().float()[:I], glu.bias.detach().float()[I:]),
+                                                          dim=1).reshape(-1).contiguous()
+        ws = [f(self.norm1.weight), f(self.norm1.bias), f(self.norm2.weight), f(self.norm2.bias), f(self.qkv.weight),
+              f(self.qkv.bias), f(self.proj.weight), f(self.proj.bias), f(srcs[8]), f(srcs[9]), w1i, b1i,
+              f(out.weight), f(out.bias)]
+        if self.precision == L.BF16:
+            ws += [ws[4].to(torch.bfloat16), ws[6].to(torch.bfloat16), w1i.to(torch.bfloat16), ws[12].to(torch.bfloat16)]
+        else:
+            ws += [empty, empty, empty, empty]
+        self._pack_key, self._packed = key, ws
+        return ws
+
+    def run(self, x: Tensor, sel: ops.Selection, flavor: int, enable_CB: bool) -> Tensor:
+        """x [B,H,W,C] NHWC with a window/grid selection -> [B,H,W,C]."""
+        return ops.layer_fwd(x, sel.pool, self.packed_weights(), sel.p0, sel.p1, flavor, self.precision,
+                             bool(enable_CB), self.mlp.inner_dim, float(self.norm1.eps))
+
+    def forward(self, x: Tensor, index_window: Tensor, index_token: Tensor, padding_index: Tensor,
+                asy_index: Tensor, M: int, B: int, enable_CB: bool) -> Tensor:
+        """Reference signature (SAST.py:199-201): x is the partitioned [B*N,T,C] tensor and the
+        selection comes as explicit index tensors."""
+        shape = x.shape
+        C = shape[-1]
+        x3 = x.reshape(shape[0], -1, C)
+        NW, T = x3.shape[:2]
+        sel = ops.selection_from_lists(index_window, asy_index, int(B), NW // int(B), T, 1, T)
+        y = ops.layer_fwd_flat(x3, sel, self.packed_weights(), self.precision, bool(enable_CB), self.mlp.inner_dim,
+                               float(self.norm1.eps), int(B))
+        return y.view(*shape)
+
+
+class SAST_block(nn.Module):
+    """SAST block = window layer + grid layer (ref: SAST.py:24-164)."""
+
+    def __init__(self, dim: int, attention_cfg, first_block: bool = False):
+        super().__init__()
+        norm_eps = attention_cfg.get('norm_eps', 1e-5)
+        partition_size = attention_cfg.partition_size
+        dim_head = attention_cfg.get('dim_head', 32)
+        attention_bias = attention_cfg.get('attention_bias', True)
+        mlp_act_string = attention_cfg.mlp_activation
+        mlp_bias = attention_cfg.get('mlp_bias', True)
+        mlp_expand_ratio = attention_cfg.get('mlp_ratio', 4)
+        drop_path = attention_cfg.get('drop_path', 0.0)
+        drop_mlp = attention_cfg.get('drop_mlp', 0.0)
+        ls_init_value = attention_cfg.get('ls_init_value', 1e-5)
+        if isinstance(partition_size, int):
+            partition_size = (partition_size, partition_size)
+        else:
+            partition_size = tuple(partition_size)
+            assert len(partition_size) == 2
+        self.partition_size = partition_size
+        sub_layer_params = (ls_init_value, drop_path, mlp_expand_ratio, _act_layer(mlp_act_string), mlp_bias, drop_mlp)
+        self.enable_CB = attention_cfg.get('enable_CB', False)
+
+        def norm():
+            return nn.LayerNorm(dim, eps=norm_eps)
+
+        self.win_attn = MS_WSA(dim, dim_head=dim_head, bias=attention_bias, sub_layer_params=sub_layer_params,
+                               norms=[norm(), norm()])
+        self.grid_attn = MS_WSA(dim, dim_head=dim_head, bias=attention_bias, sub_layer_params=sub_layer_params,
+                                norms=[norm(), norm()])
+        if first_block:
+            self.to_scores = nn.Linear(dim, dim)
+            self.to_controls = PositiveLinear(20, dim, bias=False)
+            torch.nn.init.constant_(self.to_controls.weight, 1)
+            self.act = nn.ReLU()
+        self.amp_value = attention_cfg.get('AMP', 2e-4)
+        self.bounce_value = attention_cfg.get('BOUNCE', 1e-3)
+        self.first_block = first_block
+        self.B, self.N, self.dim = None, None, dim
+
+    @staticmethod
+    def _position(pos_emb, x: Tensor) -> Tensor:
+        """[H,W,C] table when the callable can provide one (no B-fold repeat), else its output."""
+        if hasattr(pos_emb, "table"):
+            return pos_emb.table(x)
+        return pos_emb(x) if callable(pos_emb) else pos_emb
+
+    def _as_selection(self, lst, B, H, W) -> ops.Selection:
+        if isinstance(lst, ops.Selection):
+            return lst
+        iw, it, pad, asy, K = lst
+        return ops.selection_from_lists(iw, asy, B, H, W, *self.partition_size, given=lst)
+
+    def _partition_attn(self, x: Tensor, pos_emb, r: Tensor, index_list):
+        B, H, W, C = x.shape
+        p0, p1 = self.partition_size
+        assert H % p0 == 0, f'height ({H}) must be divisible by window ({p0})'
+        assert W % p1 == 0, f'width ({W}) must be divisible by window ({p1})'
+        T = p0 * p1
+        N = H * W // T
+        self.B, self.N = B, N
+        pos = self._position(pos_emb, x)
+        if self.first_block:
+            xw, tok = ops.score_fwd(x, pos, r, self.to_controls.weight, self.to_scores.weight, self.to_scores.bias,
+                                    float(self.amp_value))
+            thr_w, thr_t = ops.thresholds(N, T, self.bounce_value)
+            sel1 = ops.Selection(ops.select(tok, p0, p1, L.WINDOW, thr_w, thr_t), B, H, W, p0, p1)
+            sel2 = ops.Selection(ops.select(tok, p0, p1, L.GRID, thr_w, thr_t), B, H, W, p0, p1)
+            sel1.tok_score, sel2.tok_score = tok, tok
+        else:
+            xw = ops.add_pos(x, pos)
+            sel1 = self._as_selection(index_list[0], B, H, W)
+            sel2 = self._as_selection(index_list[1], B, H, W)
+        x1 = self.win_attn.run(xw, sel1, L.WINDOW, self.enable_CB)
+        x2 = self.grid_attn.run(x1, sel2, L.GRID, self.enable_CB)
+        count = LazyCount(sel1.counts[1] // B + sel2.counts[1] // B)
+        return x2, count, [sel1, sel2]
+
+    def forward(self, x: Tensor, pos_emb, r: Tensor, index_list):
+        return self._partition_attn(x, pos_emb, r, index_list)
+
+
+# reference-named helpers (ref: SAST.py:258-281), running on the device through the kernels
+def get_score_index_2d21d(x: Tensor, d: float, b: float) -> Tensor:
+    """2-D window index selection: ascending flat ids of entries >= d/(1+b)."""
+    Bn, N = x.shape
+    thr = float(torch.tensor(d / (1 + b), dtype=torch.float32))
+    dummy = torch.zeros(Bn * N, 1, device=x.device)
+    pool = ops.select_from_probs(x, dummy, N, 1, 1, 1, thr, float("inf"))
+    s = ops.Selection(pool, Bn, N, 1, 1, 1)
+    return s.sel_win[: int(s.counts[0])].long()
+
+
+def get_score_index_with_padding(x: Tensor, d: float, b: float):
+    """2-D token index selection (with and without padding)."""
+    M, T = x.shape
+    thr = float(torch.tensor(d / (1 + b), dtype=torch.float32))
+    ones = torch.ones(1, M, device=x.device)
+    pool = ops.select_from_probs(ones, x, M, T, 1, T, 0.0, thr)
+    s = ops.Selection(pool, 1, M, T, 1, T, tok_prob=x)
+    iw, it, pad, asy, K = s.lists()
+    return it, asy, K

@@ -1,0 +1,113 @@
+"""SAST_block / MS_WSA / RNNDetector on the GPU against the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+
+import sast_b200
+from oracle import sast_oracle as O
+from oracle.golden_common import event_histogram
+from sast_b200 import _lib as L
+from sast_b200 import ops
+from gpu_common import DEV, build_backbone, build_block, pos_module, sel_mask
+
+pytestmark = pytest.mark.gpu
+
+BLOCKS = ["block_c64_w6x10", "block_c128_w8x10_b1", "block_c64_cb", "block_c64_dense", "block_c256_w3x5"]
+# tolerance on the block output (LayerNorm-scaled activations, LayerScale gamma ~0.5 so the
+# attention/MLP branch is fully visible): fp32 path = summation-order noise; bf16 path = bf16
+# operand rounding through 4 GEMMs + attention per layer, two layers.
+TOL = {L.FP32: 2e-4, L.BF16: 6e-2}
+
+
+def _compare_lists(lists, g, li):
+    iw, it, pad, asy, K = [t.cpu() for t in lists]
+    assert torch.equal(iw, g.t(f"l{li}_iw")), f"layer {li}: index_window"
+    assert torch.equal(asy, g.t(f"l{li}_asy")), f"layer {li}: asy_index"
+    assert torch.equal(K, g.t(f"l{li}_K")), f"layer {li}: K"
+    assert set(asy.tolist()) <= set(it.tolist()) and len(it) == len(iw) * int(K.max())
+    assert set(pad.tolist()) == set(it.tolist()) - set(asy.tolist())
+
+
+@pytest.mark.parametrize("precision", [L.FP32, L.BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("name", BLOCKS)
+def test_block_golden(golden, name, precision):
+    g = golden(name)
+    m = g.meta
+    blk, _ = build_block(m, precision)
+    pos = pos_module(m)
+    with torch.no_grad():
+        y, cnt, lists = blk(g.t("x").to(DEV), pos, g.t("r").to(DEV), None)
+    assert int(cnt) == int(g.arrays["count"])
+    for li in range(2):
+        _compare_lists(lists[li], g, li)
+    err = (y.cpu() - g.t("y")).abs().max().item()
+    assert err < TOL[precision], err
+    if "y2" in g:   # second (non-first) block re-using the first block's selection (SAST.py:124-128,149-150)
+        m2 = dict(m)
+        blk2, _ = build_block(m2, precision, first_block=False, shapes_key="shapes2", seed_key="seed2")
+        with torch.no_grad():
+            y2, cnt2, _ = blk2(g.t("y").to(DEV), pos, g.t("r").to(DEV), lists)
+            # ... and the same through reference-style index tensors
+            ref_lists = [[g.t(f"l{li}_{k}").to(DEV) for k in ("iw", "it", "pad", "asy", "K")] for li in range(2)]
+            y2b, cnt2b, _ = blk2(g.t("y").to(DEV), pos, g.t("r").to(DEV), ref_lists)
+        assert int(cnt2) == int(g.arrays["count2"]) == int(cnt2b)
+        assert (y2.cpu() - g.t("y2")).abs().max().item() < TOL[precision]
+        assert torch.equal(y2, y2b)
+
+
+@pytest.mark.parametrize("precision", [L.FP32, L.BF16], ids=["fp32", "bf16"])
+def test_ms_wsa_reference_signature(golden, precision):
+    """MS_WSA.forward(x, index_window, index_token, padding_index, asy_index, M, B, enable_CB) on a
+    partitioned tensor (ref: SAST.py:199-201) against the oracle's sparse form."""
+    g = golden("block_c64_cb")
+    m = g.meta
+    blk, params = build_block(m, precision)
+    part = tuple(m["part"])
+    xw, _ = O.scoring(g.t("x"), O.position_table(m["H"], m["W"], m["C"]), g.t("r"), params, part, m["AMP"])
+    lst = [g.t(f"l0_{k}") for k in ("iw", "it", "pad", "asy", "K")]
+    for cb in (False, True):
+        ref = O.ms_wsa(xw, *lst[:4], len(lst[0]), m["B"], cb, O.sub(params, "win_attn"))
+        with torch.no_grad():
+            got = blk.win_attn(xw.to(DEV), *[t.to(DEV) for t in lst[:4]], len(lst[0]), m["B"], cb)
+        assert got.shape == ref.shape
+        assert (got.cpu() - ref).abs().max().item() < TOL[precision]
+    # nothing selected: every token keeps norm1(x)  (SAST.py:206-208)
+    empty = torch.zeros(0, dtype=torch.long, device=DEV)
+    with torch.no_grad():
+        got = blk.win_attn(xw.to(DEV), empty, empty, empty, empty, 0, m["B"], False)
+    ref = torch.nn.functional.layer_norm(xw, (m["C"],), params["win_attn.norm1.weight"], params["win_attn.norm1.bias"], 1e-5)
+    assert (got.cpu() - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("precision", [L.FP32, L.BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["backbone_e32", "backbone_e32_nb2_mask_cb"])
+def test_backbone_golden(golden, name, precision):
+    """RNNDetector: two recurrent steps with carried LSTM state against the reference."""
+    g = golden(name)
+    m = g.meta
+    net, _ = build_backbone(m, precision)
+    H, W = m["in_res_hw"]
+    x0 = event_histogram(m["B"], 20, H, W, m["x_density"][0], seed=m["x_seeds"][0]).to(DEV)
+    x1 = event_histogram(m["B"], 20, H, W, m["x_density"][1], seed=m["x_seeds"][1]).to(DEV)
+    tm = g.t("token_mask").to(DEV) if "token_mask" in g else None
+    with torch.no_grad():
+        f0, s0, p0 = net(x0, None, tm)
+        f1, s1, p1 = net(x1, s0, tm)
+    ref_p = g.arrays["P0"].tolist() + g.arrays["P1"].tolist()
+    got_p = [int(v) for v in p0] + [int(v) for v in p1]
+    # selected-token counts: exact in fp32 up to threshold flips (<= 0.1 %), looser for bf16 whose
+    # rounding feeds the next stage's scores
+    rel = 1e-3 if precision == L.FP32 else 2e-2
+    for a, b in zip(got_p, ref_p):
+        assert abs(a - b) <= max(2, rel * b), (got_p, ref_p)
+    tol = 5e-4 if precision == L.FP32 else 8e-2
+    for st in (1, 2, 3, 4):
+        h = f1[st]
+        assert h.shape[1] == m["embed_dim"] * 2 ** (st - 1)
+        hh = h[:, :, ::2, ::2] if st == 1 else h
+        diff = (hh.cpu() - g.t(f"h1_s{st}")).abs()
+        # a flipped token changes its own output visibly: bound the fraction of such outliers, and the rest tightly
+        frac_bad = (diff > tol).float().mean().item()
+        assert frac_bad < (1e-3 if precision == L.FP32 else 2e-2), (st, frac_bad, diff.max().item())
+        s_ref, a_ref = g.arrays[f"sum1_s{st}"]
+        assert abs(h.double().abs().sum().item() - a_ref) / a_ref < (1e-4 if precision == L.FP32 else 5e-3)

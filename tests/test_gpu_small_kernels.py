@@ -1,0 +1,73 @@
+"""non_zero_ratio (bit-exact), scoring/STP weighting and the tcgen05 GEMM through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sast_oracle as O
+from oracle.golden_common import event_histogram, make_params
+from sast_b200 import _lib as L
+from sast_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_nonzero_ratio_golden(golden):
+    g = golden("small_fns")
+    for nm in ("u8", "i32", "f32"):
+        x = g.t(f"nzr_{nm}_x")
+        assert torch.equal(ops.nonzero_ratio(x.to(DEV)).cpu(), g.t(f"nzr_{nm}_r")), nm
+
+
+@pytest.mark.parametrize("shape,dtype", [((8, 20, 384, 640), torch.uint8), ((2, 20, 256, 320), torch.int32),
+                                         ((1, 20, 250, 300), torch.float32), ((2, 3, 100, 36), torch.uint8)])
+def test_nonzero_ratio_full_size(shape, dtype):
+    """Bit-exact at the 1 Mpx B=8 size, ragged sizes and negative values (max-pool semantics)."""
+    B, C, H, W = shape
+    x = event_histogram(B, C, H, W, 0.03, seed=H).to(dtype)
+    if dtype == torch.float32:
+        x = x - 2.0 * (x == 3)          # some negative cells: max-pool of {-2, 0} is 0 -> not counted
+    assert torch.equal(ops.nonzero_ratio(x.to(DEV)).cpu(), O.non_zero_ratio(x))
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 12, 20, 64), (1, 16, 30, 128), (2, 6, 10, 256), (1, 4, 5, 512), (3, 7, 9, 32), (2, 12, 20, 96)])
+def test_score_fwd(B, H, W, C):
+    """a4: weighted map within fp32 round-off of the reference formula; per-token score (what
+    selection thresholds) within 1e-5 relative."""
+    shapes = {"to_scores.weight": (C, C), "to_scores.bias": (C,), "to_controls.weight": (C, 20)}
+    p = make_params(shapes, seed=C + H)
+    gen = torch.Generator().manual_seed(C)
+    x = torch.randn(B, H, W, C, generator=gen)
+    r = torch.rand(B, 20, generator=gen) * 0.05
+    pos = O.position_table(H, W, C)
+    amp = 2e-3
+    # oracle on the un-partitioned map: partition (1,1) keeps map order
+    xw_ref, scores = O.scoring(x, pos, r, p, (1, 1), amp)
+    xw_ref = xw_ref.reshape(B, H, W, C)
+    tok_ref = scores.abs().sum(-1).reshape(B, H, W)
+    xw, tok = ops.score_fwd(x.to(DEV), pos.to(DEV), r.to(DEV), p["to_controls.weight"].to(DEV),
+                            p["to_scores.weight"].to(DEV), p["to_scores.bias"].to(DEV), amp)
+    assert (xw.cpu() - xw_ref).abs().max() < 2e-5
+    assert ((tok.cpu() - tok_ref).abs() / tok_ref.abs().clamp_min(1e-12)).max() < 2e-5
+    # batched pos (reference-style repeated tensor) gives the same result
+    xw2, tok2 = ops.score_fwd(x.to(DEV), pos[None].repeat(B, 1, 1, 1).to(DEV), r.to(DEV), p["to_controls.weight"].to(DEV),
+                              p["to_scores.weight"].to(DEV), p["to_scores.bias"].to(DEV), amp)
+    assert torch.equal(xw2, xw) and torch.equal(tok2, tok)
+    assert torch.equal(ops.add_pos(x.to(DEV), pos.to(DEV)).cpu(), x + pos)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 192, 64), (1000, 128, 128), (257, 320, 160), (128, 512, 1344),
+                                   (64, 32, 32), (4096, 1536, 512), (130, 96, 96)])
+def test_gemm_tcgen05(M, N, K):
+    """tcgen05 GEMM vs a torch fp32 reference on the same bf16-rounded operands (fp32
+    accumulate: only summation order differs)."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=gen).to(torch.bfloat16)
+    Wt = (torch.randn(N, K, generator=gen) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=gen)
+    ref = A.float() @ Wt.float().t() + bias
+    D = ops.gemm_bf16(A.to(DEV), Wt.to(DEV), bias.to(DEV))
+    assert (D.cpu() - ref).abs().max() < 1e-3 * max(1.0, K ** 0.5 / 8)
+    Db = ops.gemm_bf16(A.to(DEV), Wt.to(DEV), None, out_bf16=True)
+    ref_b = (A.float() @ Wt.float().t())
+    assert (Db.float().cpu() - ref_b).abs().max() < 4e-2

