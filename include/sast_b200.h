@@ -68,16 +68,19 @@ typedef struct sast_geom {
  * [index_window, index_token, padding_index, asy_index, K] of SAST.py:123.
  */
 typedef struct sast_selection {
-  int32_t* counts;    /* [8]  0:M  1:S  2:Kmax  3:number of attention tiles  4..7 reserved */
+  int32_t* counts;    /* [8]  0:M  1:S  2:Kmax  3..7 reserved                                   */
   int32_t* win_K;     /* [NW]   selected tokens in window w (0 when the window is dropped)  */
   int32_t* win_rank;  /* [NW]   rank m of window w among selected windows, or -1            */
   int32_t* win_row0;  /* [NW+1] first compacted row of window w (exclusive prefix of win_K) */
   int32_t* sel_win;   /* [NW]   first M entries: ascending ids of selected windows (= index_window) */
   int32_t* tok_row;   /* [P]    compacted row of token q (partitioned order), or -1          */
   int32_t* row_tok;   /* [P]    first S entries: token q of compacted row r                 */
-  int32_t* frame_tot; /* [B*4]  per frame: M_b, S_b, Kmax_b, reserved                      */
+  int32_t* row_pix;   /* [P]    first S entries: NHWC pixel index (b*H*W + y*W + x) of row r */
+  float*   win_logit; /* [NW]   scratch: mean token score of window w (SCORES mode)         */
   uint8_t* tok_keep;  /* [P]    scratch: keep flag per token, partitioned order             */
-  int32_t* tiles;     /* [NW*4] attention tiles: row0, rows, first selected-window rank, windows */
+  int32_t* tiles;     /* [NW*2] attention tiles (consecutive windows of one frame, <= 128 rows):
+                                tiles[2w] = rows of the tile led by window w (0 = not a leader),
+                                tiles[2w+1] = one past the tile's last window                */
 } sast_selection;
 
 /* Bytes of one int32 pool able to hold a sast_selection for (NW, P, B); see sast_selection_bind. */
@@ -114,7 +117,7 @@ typedef struct sast_score_args {
   float amp;
   float* xw;               /* out [B,H,W,C]; must not alias x */
   float* tok_score;        /* out [B,H,W] */
-  float* ctrl_scratch;     /* scratch [2*B*C] floats (sigmoid(ctrl), amp/ctrl) */
+  float* ctrl_scratch;     /* scratch floats: 2*B*C (sigmoid(ctrl), amp/ctrl) + ceil(C/64)*B*H*W (partial scores) */
 } sast_score_args;
 int sast_score_fwd(const sast_score_args* a, void* stream);
 
@@ -145,6 +148,10 @@ typedef struct sast_select_args {
   sast_selection sel;      /* out */
 } sast_select_args;
 int sast_select(const sast_select_args* a, void* stream);
+/* Same, producing a second selection `sel_b` under partition flavour `flavor_b` from the same
+ * inputs in the same launches (a first block needs the window and the grid selection of one
+ * score map, SAST.py:138-147).  sel_b == NULL behaves like sast_select. */
+int sast_select2(const sast_select_args* a, int32_t flavor_b, const sast_selection* sel_b, void* stream);
 
 /*
  * a8-a13  one MS-WSA layer.  ref: SAST.py:199-255 (MS_WSA.forward).

@@ -30,8 +30,8 @@ class Geom(C.Structure):
 class Selection(C.Structure):
     _fields_ = [("counts", C.c_void_p), ("win_K", C.c_void_p), ("win_rank", C.c_void_p),
                 ("win_row0", C.c_void_p), ("sel_win", C.c_void_p), ("tok_row", C.c_void_p),
-                ("row_tok", C.c_void_p), ("frame_tot", C.c_void_p), ("tok_keep", C.c_void_p),
-                ("tiles", C.c_void_p)]
+                ("row_tok", C.c_void_p), ("row_pix", C.c_void_p), ("win_logit", C.c_void_p),
+                ("tok_keep", C.c_void_p), ("tiles", C.c_void_p)]
 
 
 class ScoreArgs(C.Structure):
@@ -78,6 +78,7 @@ def _load():
         "sast_nonzero_ratio": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
         "sast_score_fwd": (C.c_int, [C.POINTER(ScoreArgs), vp]),
         "sast_select": (C.c_int, [C.POINTER(SelectArgs), vp]),
+        "sast_select2": (C.c_int, [C.POINTER(SelectArgs), i32, C.POINTER(Selection), vp]),
         "sast_layer_workspace_bytes": (sz, [i64, i32, i32, i32, i32]),
         "sast_layer_fwd": (C.c_int, [C.POINTER(LayerArgs), vp]),
         "sast_gather": (C.c_int, [C.POINTER(Geom), i32, vp, C.POINTER(Selection), vp, vp]),
@@ -97,7 +98,7 @@ def _load():
 
 
 EXPORTS = ("sast_abi_version", "sast_build_info", "sast_struct_size", "sast_launch_count", "sast_selection_bytes", "sast_selection_bind",
-           "sast_nonzero_ratio", "sast_score_fwd", "sast_select", "sast_layer_workspace_bytes",
+           "sast_nonzero_ratio", "sast_score_fwd", "sast_select", "sast_select2", "sast_layer_workspace_bytes",
            "sast_layer_fwd", "sast_gather", "sast_scatter", "sast_gemm_bf16")
 
 _lib = None

@@ -1,13 +1,209 @@
-// Attention over the compacted rows (SAST_BF16 path): per selected window and head,
-// softmax(q k^T / sqrt(32)) v over the window's selected tokens.   (replaces SAST.py:219-229)
+// Attention over the compacted rows on the 5th-gen tensor cores (SAST_BF16 path):
+// per attention tile (consecutive selected windows of one frame, <= 128 compacted rows, packed
+// by select_scan_kernel) and head:  S = Q K^T (tcgen05, fp32 in TMEM) -> block-diagonal softmax
+// (a row only sees the keys of its own window) -> P (bf16, shared memory) -> O = P V (tcgen05)
+// -> O / rowsum -> bf16.                                                (replaces SAST.py:219-229)
 //
-// v1: bf16 in / bf16 out with fp32 CUDA-core math (one thread per query row, K/V staged in
-// shared memory as fp32).  The compacted buffer has no padding rows, so no column mask exists.
-// TODO(round 2): tcgen05 S = Q K^T / P V tiles over greedy 128-row window groups (sel.tiles).
+// The compacted buffer holds selected tokens only, so the reference's -1e4 column mask for
+// padding (SAST.py:223-226) has no counterpart: the only mask is "same window".
+//
+// CTA = 128 threads, thread t <-> tile row t <-> TMEM lane t.  Thread 0 issues TMA and MMA.
+//   Q,K,V tiles [128 x 32] bf16: TMA boxes out of the qkv buffer ([rows, 3C], head-major
+//   [h][q,k,v][32]) in SWIZZLE_64B; Q,K are K-major operands, V is the MN-major B operand of PV.
+//   P [128 x 128] bf16 is written by the softmax threads in the SWIZZLE_128B K-major layout.
 #include "layer.cuh"
+#include "ptx.cuh"
 
 namespace sast {
 
+constexpr uint32_t AT_TMEM_COLS = 256;     // S: columns [0,128), O: columns [128,160)
+constexpr int AT_TILE = 8192;              // one 128 x 32 bf16 operand tile
+
+struct AttnSmem {
+  uint64_t bar_load, bar_s, bar_o;
+  uint32_t tmem_base;
+};
+
+// K-major, SWIZZLE_64B: rows of 64 bytes (32 bf16), 8-row atoms 512 bytes apart
+__device__ __forceinline__ uint64_t desc_sw64_kmajor(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                  // SWIZZLE_64B
+  return d;
+}
+// MN-major, SWIZZLE_64B: one K index (key) per 64-byte row of 32 MN elements, 8-key atoms 512 bytes apart
+__device__ __forceinline__ uint64_t desc_sw64_mnmajor(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(512 >> 4) << 16;         // LBO: next 32-wide MN block (unused, N = 32)
+  d |= (uint64_t)(512 >> 4) << 32;         // SBO: next 8 keys
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                           __nv_bfloat16* __restrict__ att, int C, int heads_per_cta,
+                                                           const int* __restrict__ tiles, const int* __restrict__ win_row0,
+                                                           const int* __restrict__ row_tok, int T) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int w = blockIdx.x;
+  const int rows = tiles[2 * w];
+  if (rows == 0) return;                                   // not a tile leader
+  const int row0 = win_row0[w];
+  const int t = threadIdx.x, warp = t >> 5;
+
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = base;
+  uint8_t* sK = base + AT_TILE;
+  uint8_t* sV = base + 2 * AT_TILE;
+  uint8_t* sP = base + 4 * AT_TILE;                        // 32 KB, 1024-aligned
+  AttnSmem* sm = reinterpret_cast<AttnSmem*>(base + 8 * AT_TILE);
+
+  if (t == 0) {
+    ptx::tma_prefetch_desc(&map_qkv);
+    ptx::mbar_init(&sm->bar_load, 1);
+    ptx::mbar_init(&sm->bar_s, 1);
+    ptx::mbar_init(&sm->bar_o, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc<AT_TMEM_COLS>(&sm->tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_s = sm->tmem_base;
+  const uint32_t tmem_o = tmem_s + 128;
+  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+
+  // key range of this row: the compacted rows of its own window
+  int lo = 0, hi = 0;
+  if (t < rows) {
+    const int wi = row_tok[row0 + t] / T;
+    lo = win_row0[wi] - row0;
+    hi = win_row0[wi + 1] - row0;
+  }
+  const int rows16 = (rows + 15) & ~15;
+  const float sc = 0.17677669529663688110f * 1.44269504088896340736f;   // 32^-0.5 * log2(e)
+
+  const int h_begin = blockIdx.y * heads_per_cta;
+  for (int hi_ = 0; hi_ < heads_per_cta; ++hi_) {
+    const int h = h_begin + hi_;
+    const uint32_t ph = (uint32_t)(hi_ & 1);
+    if (t == 0) {
+      ptx::mbar_arrive_expect_tx(&sm->bar_load, 3 * AT_TILE);
+      ptx::tma_load_2d(sQ, &map_qkv, &sm->bar_load, h * 96, row0);
+      ptx::tma_load_2d(sK, &map_qkv, &sm->bar_load, h * 96 + 32, row0);
+      ptx::tma_load_2d(sV, &map_qkv, &sm->bar_load, h * 96 + 64, row0);
+      ptx::mbar_wait(&sm->bar_load, ph);
+      ptx::tc_fence_after();
+      const uint32_t id_s = idesc_bf16(128, 128, 0);
+      const uint64_t dq = desc_sw64_kmajor(ptx::smem_u32(sQ)), dk = desc_sw64_kmajor(ptx::smem_u32(sK));
+      ptx::umma_f16_ss(tmem_s, dq, dk, id_s, 0u);
+      ptx::umma_f16_ss(tmem_s, dq + 2, dk + 2, id_s, 1u);          // +32 bytes: dims 16..31
+      ptx::umma_commit(&sm->bar_s);
+    }
+    ptx::mbar_wait(&sm->bar_s, ph);
+    ptx::tc_fence_after();
+
+    // ---- softmax over this row's window (two passes over TMEM: max, then exp / sum / P) ----
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < rows16; c0 += 32) {
+      uint32_t raw[32];
+      ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = c0 + j;
+        if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(raw[j]));
+      }
+    }
+    float sum = 0.f;
+    const int r8 = t & 7;
+    uint8_t* prow = sP + (t >> 3) * 1024 + r8 * 128;
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t pk[16];
+      if (c0 < rows16) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const int col = c0 + j;
+          const float p0 = (col >= lo && col < hi) ? exp2f((__uint_as_float(raw[j]) - mx) * sc) : 0.f;
+          const float p1 = (col + 1 >= lo && col + 1 < hi) ? exp2f((__uint_as_float(raw[j + 1]) - mx) * sc) : 0.f;
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          // the row sum uses the bf16-rounded probabilities the PV product will see
+          const float2 f2 = __bfloat1622float2(b2);
+          sum += f2.x + f2.y;
+          pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+      }
+      // 32 keys = 4 chunks of 16 bytes, SWIZZLE_128B K-major: chunk index XOR (row % 8)
+      const int kb = c0 >> 6;
+      const int cbase = (c0 & 63) >> 3;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int chunk = (cbase + cc) ^ r8;
+        *reinterpret_cast<uint4*>(prow + kb * 16384 + chunk * 16) = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+      }
+    }
+    // V rows past the tile may be uninitialised memory (0 * NaN = NaN): zero the ones the PV product reads
+    if (t >= rows && t < rows16) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(sV + t * 64 + cc * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    ptx::fence_proxy_async();                               // generic-proxy smem writes -> visible to tcgen05
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (t == 0) {
+      ptx::tc_fence_after();
+      const uint32_t id_o = idesc_bf16(128, 32, 1);
+      const uint32_t pa = ptx::smem_u32(sP), va = ptx::smem_u32(sV);
+      for (int ks = 0; ks < rows16 / 16; ++ks) {
+        const uint64_t dp = ptx::umma_desc_sw128_kmajor(pa + (ks >> 2) * 16384) + (uint64_t)((ks & 3) * 2);
+        const uint64_t dv = desc_sw64_mnmajor(va + ks * 1024);
+        ptx::umma_f16_ss(tmem_o, dp, dv, id_o, ks ? 1u : 0u);
+      }
+      ptx::umma_commit(&sm->bar_o);
+    }
+    ptx::mbar_wait(&sm->bar_o, ph);
+    ptx::tc_fence_after();
+    {
+      uint32_t raw[32];
+      ptx::tmem_ld_32x32(tmem_o + lane_sel, raw);
+      ptx::tmem_ld_wait();
+      if (t < rows) {
+        const float il = 1.0f / sum;
+        __nv_bfloat16* dst = att + (size_t)(row0 + t) * C + h * 32;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint4 o;
+          __nv_bfloat162 b2;
+          b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 0]) * il, __uint_as_float(raw[cc * 8 + 1]) * il); o.x = *reinterpret_cast<uint32_t*>(&b2);
+          b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 2]) * il, __uint_as_float(raw[cc * 8 + 3]) * il); o.y = *reinterpret_cast<uint32_t*>(&b2);
+          b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 4]) * il, __uint_as_float(raw[cc * 8 + 5]) * il); o.z = *reinterpret_cast<uint32_t*>(&b2);
+          b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 6]) * il, __uint_as_float(raw[cc * 8 + 7]) * il); o.w = *reinterpret_cast<uint32_t*>(&b2);
+          *reinterpret_cast<uint4*>(dst + cc * 8) = o;
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();          // everyone is done with S, O and the smem tiles before the next head reuses them
+    ptx::tc_fence_after();
+  }
+  if (warp == 0) ptx::tmem_dealloc<AT_TMEM_COLS>(tmem_s);
+}
+
+// ---- CUDA-core variant (debug / A-B knob SAST_B200_ATTN=simt): one thread per query row ----
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* o) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -29,7 +225,7 @@ __global__ void __launch_bounds__(128) attention_bf16_kernel(const __nv_bfloat16
   const int ld = 3 * C;
   float* ks = kv;
   float* vs = kv + (size_t)K * 32;
-  for (int i = threadIdx.x; i < K * 8; i += blockDim.x) {      // 8 x 16-byte chunks per row: 4 of k, 4 of v
+  for (int i = threadIdx.x; i < K * 8; i += blockDim.x) {
     const int r = i >> 3, c = i & 7;
     const uint4 u = *reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + r) * ld + h * 96 + 32 + c * 8);
     bf16x8_to_f32(u, c < 4 ? ks + r * 32 + c * 8 : vs + r * 32 + (c - 4) * 8);
@@ -38,7 +234,7 @@ __global__ void __launch_bounds__(128) attention_bf16_kernel(const __nv_bfloat16
   const int i = threadIdx.x;
   if (i >= K) return;
   float q[32], o[32];
-  const float scale = 0.17677669529663688110f;   // 32^-0.5
+  const float scale = 0.17677669529663688110f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const uint4 u = *reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + i) * ld + h * 96 + c * 8);
@@ -66,19 +262,41 @@ __global__ void __launch_bounds__(128) attention_bf16_kernel(const __nv_bfloat16
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 pk;
-    __nv_bfloat162 t;
-    t = __floats2bfloat162_rn(o[c * 8 + 0], o[c * 8 + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(o[c * 8 + 2], o[c * 8 + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(o[c * 8 + 4], o[c * 8 + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(o[c * 8 + 6], o[c * 8 + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+    __nv_bfloat162 t2;
+    t2 = __floats2bfloat162_rn(o[c * 8 + 0], o[c * 8 + 1]); pk.x = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2bfloat162_rn(o[c * 8 + 2], o[c * 8 + 3]); pk.y = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2bfloat162_rn(o[c * 8 + 4], o[c * 8 + 5]); pk.z = *reinterpret_cast<uint32_t*>(&t2);
+    t2 = __floats2bfloat162_rn(o[c * 8 + 6], o[c * 8 + 7]); pk.w = *reinterpret_cast<uint32_t*>(&t2);
     *reinterpret_cast<uint4*>(dst + c * 8) = pk;
   }
 }
 
+int make_tmap_bf16_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows,
+                       int swizzle_bytes);
+
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, const sast_selection& sel, int NW, int T,
-                        cudaStream_t st) {
-  const size_t smem = (size_t)T * 64 * sizeof(float);
-  attention_bf16_kernel<<<dim3(NW, C / 32), 128, smem, st>>>(qkv, att, C, sel.win_K, sel.win_row0);
+                        long long max_rows, int variant, cudaStream_t st) {
+  const int heads = C / 32;
+  if (variant == 1) {
+    const size_t smem = (size_t)T * 64 * sizeof(float);
+    attention_bf16_kernel<<<dim3(NW, heads), 128, smem, st>>>(qkv, att, C, sel.win_K, sel.win_row0);
+    SAST_LAUNCH_CHECK();
+    return SAST_OK;
+  }
+  CUtensorMap mq;
+  int rc = make_tmap_bf16_box(&mq, qkv, max_rows, 3 * C, 3 * C, 32, 128, 64);
+  if (rc) return rc;
+  static bool attr_done = false;
+  const size_t smem = 1024 + 8 * AT_TILE + sizeof(AttnSmem);
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  // enough CTAs to fill the chip: all heads in one CTA when there are many tiles, one head per CTA otherwise
+  int hpc = heads;
+  while (hpc > 1 && (long long)NW * (heads / hpc) < 4 * 148 && hpc % 2 == 0) hpc /= 2;
+  attention_tc_kernel<<<dim3(NW, heads / hpc), 128, smem, st>>>(mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     ptx::tc_fence_after();
     const bool row_ok = row < M;
     long long pix = 0;
-    if (EPI == EPI_SCATTER && row_ok) pix = token_pixel(ep.row_tok[row], ep.g, ep.flavor);
+    if (EPI == EPI_SCATTER && row_ok) pix = ep.row_pix[row];
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t raw[32];
       ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, raw);
@@ -183,18 +183,26 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = 64 cols x box_rows, SWIZZLE_128B
-int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_rows) {
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_cols x box_rows,
+// swizzle span = box_cols * 2 bytes (64 or 128)
+int make_tmap_bf16_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows,
+                       int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return (int)cudaErrorNotSupported;
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_rows) {
+  return make_tmap_bf16_box(m, ptr, rows, cols, ld, TC_BK, box_rows, 128);
 }
 
 template <int EPI>

@@ -17,97 +17,125 @@
 // This file holds the orchestration and the fp32 CUDA-core kernels (SAST_FP32, validation
 // grade); the tcgen05 kernels of SAST_BF16 live in gemm_tc.cu / attn_tc.cu.
 #include "layer.cuh"
+#include <cstdlib>
 
 namespace sast {
 
 // ------------------------------------------------------------------------------------------
 // gather + LN1 (+ LN2)
 // ------------------------------------------------------------------------------------------
-template <int NV>   // float4 per lane: C <= 128*NV
+template <int LPT>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPT / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// LPT lanes cooperate on one token (NV float4 each: C <= 4*LPT*NV); every lane group handles TPW
+// tokens per pass with all of their loads issued before the first use (memory-level parallelism
+// is what this HBM-bound kernel lives on).
+template <int LPT, int NV, int TPW>
 __global__ void __launch_bounds__(256) gather_ln_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                         const float* __restrict__ w1, const float* __restrict__ b1,
                                                         const float* __restrict__ w2, const float* __restrict__ b2,
                                                         float eps, const int* __restrict__ tok_row, Geom g, int flavor,
                                                         float* __restrict__ n2f, __nv_bfloat16* __restrict__ n2h) {
+  constexpr int GROUPS = 32 / LPT;
   const int lane = threadIdx.x & 31;
-  const long long q = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= g.P) return;
+  const int sub = lane / LPT, l = lane % LPT;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long q0 = (warp * GROUPS + sub) * TPW;
   const int C = g.C;
-  const long long pix = token_pixel(q, g, flavor);
-  const float* xp = x + pix * C;
-  float4 v[NV];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
-    v[i] = c < C ? *reinterpret_cast<const float4*>(xp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
   const float inv_c = 1.0f / (float)C;
-  float mean = warp_sum(s) * inv_c;
-  float ss = 0.f;
+
+  float4 v[TPW][NV];
+  long long pix[TPW];
+  int row[TPW];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
-    if (c < C) {
-      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-      ss += (a * a + b * b) + (cc * cc + d * d);
-    }
-  }
-  float rstd = rsqrtf(warp_sum(ss) * inv_c + eps);
-  s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
-    if (c < C) {
-      const float4 gw = *reinterpret_cast<const float4*>(w1 + c);
-      const float4 gb = *reinterpret_cast<const float4*>(b1 + c);
-      v[i].x = (v[i].x - mean) * rstd * gw.x + gb.x;
-      v[i].y = (v[i].y - mean) * rstd * gw.y + gb.y;
-      v[i].z = (v[i].z - mean) * rstd * gw.z + gb.z;
-      v[i].w = (v[i].w - mean) * rstd * gw.w + gb.w;
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-  }
-  const int row = tok_row[q];
-  if (row < 0) {   // unselected: keeps norm1(x)
-    float* op = out + pix * C;
+  for (int j = 0; j < TPW; ++j) {
+    const long long q = q0 + j;
+    const bool ok = q < g.P;
+    pix[j] = ok ? token_pixel(q, g, flavor) : 0;
+    row[j] = ok ? tok_row[q] : -1;
+    const float* xp = x + pix[j] * C;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 4;
-      if (c < C) *reinterpret_cast<float4*>(op + c) = v[i];
-    }
-    return;
-  }
-  mean = warp_sum(s) * inv_c;
-  ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
-    if (c < C) {
-      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-      ss += (a * a + b * b) + (cc * cc + d * d);
+      const int c = (l + LPT * i) * 4;
+      v[j][i] = (ok && c < C) ? *reinterpret_cast<const float4*>(xp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  rstd = rsqrtf(warp_sum(ss) * inv_c + eps);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (lane + 32 * i) * 4;
-    if (c < C) {
-      const float4 gw = *reinterpret_cast<const float4*>(w2 + c);
-      const float4 gb = *reinterpret_cast<const float4*>(b2 + c);
-      float4 o;
-      o.x = (v[i].x - mean) * rstd * gw.x + gb.x;
-      o.y = (v[i].y - mean) * rstd * gw.y + gb.y;
-      o.z = (v[i].z - mean) * rstd * gw.z + gb.z;
-      o.w = (v[i].w - mean) * rstd * gw.w + gb.w;
-      *reinterpret_cast<float4*>(n2f + (size_t)row * C + c) = o;
-      if (n2h) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(n2h + (size_t)row * C + c) = pk;
+  for (int j = 0; j < TPW; ++j) {
+    const bool ok = q0 + j < g.P;          // uniform inside the lane group
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
+    float mean = group_sum<LPT>(s) * inv_c;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (l + LPT * i) * 4;
+      if (c < C) {
+        const float a = v[j][i].x - mean, b = v[j][i].y - mean, cc = v[j][i].z - mean, d = v[j][i].w - mean;
+        ss += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    float rstd = rsqrtf(group_sum<LPT>(ss) * inv_c + eps);
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (l + LPT * i) * 4;
+      if (c < C) {
+        const float4 gw = *reinterpret_cast<const float4*>(w1 + c);
+        const float4 gb = *reinterpret_cast<const float4*>(b1 + c);
+        v[j][i].x = (v[j][i].x - mean) * rstd * gw.x + gb.x;
+        v[j][i].y = (v[j][i].y - mean) * rstd * gw.y + gb.y;
+        v[j][i].z = (v[j][i].z - mean) * rstd * gw.z + gb.z;
+        v[j][i].w = (v[j][i].w - mean) * rstd * gw.w + gb.w;
+        s += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
+      }
+    }
+    // second norm only matters for selected tokens, but the shuffles must be executed by every lane
+    mean = group_sum<LPT>(s) * inv_c;
+    ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (l + LPT * i) * 4;
+      if (c < C) {
+        const float a = v[j][i].x - mean, b = v[j][i].y - mean, cc = v[j][i].z - mean, d = v[j][i].w - mean;
+        ss += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    rstd = rsqrtf(group_sum<LPT>(ss) * inv_c + eps);
+    if (!ok) continue;
+    if (row[j] < 0) {   // unselected: keeps norm1(x)   (SAST.py:251-254)
+      float* op = out + pix[j] * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (l + LPT * i) * 4;
+        if (c < C) *reinterpret_cast<float4*>(op + c) = v[j][i];
+      }
+      continue;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (l + LPT * i) * 4;
+      if (c < C) {
+        const float4 gw = *reinterpret_cast<const float4*>(w2 + c);
+        const float4 gb = *reinterpret_cast<const float4*>(b2 + c);
+        float4 o;
+        o.x = (v[j][i].x - mean) * rstd * gw.x + gb.x;
+        o.y = (v[j][i].y - mean) * rstd * gw.y + gb.y;
+        o.z = (v[j][i].z - mean) * rstd * gw.z + gb.z;
+        o.w = (v[j][i].w - mean) * rstd * gw.w + gb.w;
+        *reinterpret_cast<float4*>(n2f + (size_t)row[j] * C + c) = o;
+        if (n2h) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(n2h + (size_t)row[j] * C + c) = pk;
+        }
       }
     }
   }
@@ -180,7 +208,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       if (EPI == EPI_RESID) {
         *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + n) = o;
       } else {
-        const long long pix = token_pixel(ep.row_tok[row], ep.g, ep.flavor);
+        const long long pix = ep.row_pix[row];
         *reinterpret_cast<float4*>(ep.out_f32 + pix * ep.C + n) = o;
       }
     }
@@ -259,7 +287,8 @@ __global__ void cb_mean_kernel(const float* __restrict__ m, int C, const int* __
 
 __global__ void cb_scatter_kernel(const float* __restrict__ m, const float* __restrict__ y, const float* __restrict__ mean,
                                   const float* __restrict__ gamma, const int* __restrict__ counts,
-                                  const int* __restrict__ row_tok, Geom g, int flavor, float* __restrict__ out) {
+                                  const int* __restrict__ row_tok, const int* __restrict__ row_pix, Geom g,
+                                  float* __restrict__ out) {
   const int S = counts[1];
   const int c4 = g.C / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)S * c4; i += (long long)gridDim.x * blockDim.x) {
@@ -271,7 +300,7 @@ __global__ void cb_scatter_kernel(const float* __restrict__ m, const float* __re
     const float4 mu = *reinterpret_cast<const float4*>(mean + (size_t)b * g.C + c);
     float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
     if (gamma) gm = *reinterpret_cast<const float4*>(gamma + c);
-    const long long pix = token_pixel(q, g, flavor);
+    const long long pix = row_pix[row];
     *reinterpret_cast<float4*>(out + pix * g.C + c) =
         make_float4(yv.x + gm.x * (0.5f * mv.x + 0.5f * mu.x), yv.y + gm.y * (0.5f * mv.y + 0.5f * mu.y),
                     yv.z + gm.z * (0.5f * mv.z + 0.5f * mu.z), yv.w + gm.w * (0.5f * mv.w + 0.5f * mu.w));
@@ -281,27 +310,53 @@ __global__ void cb_scatter_kernel(const float* __restrict__ m, const float* __re
 // ------------------------------------------------------------------------------------------
 // standalone gather / scatter of selected rows (tests + HBM microbenchmark)
 // ------------------------------------------------------------------------------------------
-template <bool GATHER>
+template <bool GATHER, int LPT, int NV>
 __global__ void __launch_bounds__(256) rows_copy_kernel(float* __restrict__ map, float* __restrict__ rows,
-                                                        const int* __restrict__ counts, const int* __restrict__ row_tok,
-                                                        Geom g, int flavor) {
+                                                        const int* __restrict__ counts, const int* __restrict__ row_pix, int C) {
+  constexpr int GROUPS = 32 / LPT, RPG = 4;              // rows per lane group per pass
   const int S = counts[1];
-  const int c4 = g.C / 4;
-  const int lanes = c4 < 32 ? c4 : 32;                 // lanes cooperating on one row
-  const int rows_per_warp = 32 / lanes;
   const int lane = threadIdx.x & 31;
-  const int sub = lane / lanes, l = lane % lanes;
+  const int sub = lane / LPT, l = lane % LPT;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long r = warp * rows_per_warp + sub; r < S; r += nwarps * rows_per_warp) {
-    if (sub >= rows_per_warp) break;
-    const long long pix = token_pixel(row_tok[r], g, flavor);
-    float4* mp = reinterpret_cast<float4*>(map + pix * g.C);
-    float4* rp = reinterpret_cast<float4*>(rows + (size_t)r * g.C);
-    for (int c = l; c < c4; c += lanes) {
-      if (GATHER) rp[c] = mp[c]; else mp[c] = rp[c];
+  for (long long r0 = (warp * GROUPS + sub) * RPG; r0 < S; r0 += nwarps * GROUPS * RPG) {
+    long long pix[RPG];
+#pragma unroll
+    for (int j = 0; j < RPG; ++j) pix[j] = r0 + j < S ? row_pix[r0 + j] : -1;
+    float4 v[RPG][NV];
+#pragma unroll
+    for (int j = 0; j < RPG; ++j) {
+      const float* src = GATHER ? map + pix[j] * C : rows + (r0 + j) * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (l + LPT * i) * 4;
+        if (pix[j] >= 0 && c < C) v[j][i] = *reinterpret_cast<const float4*>(src + c);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RPG; ++j) {
+      float* dst = GATHER ? rows + (r0 + j) * C : map + pix[j] * C;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (l + LPT * i) * 4;
+        if (pix[j] >= 0 && c < C) *reinterpret_cast<float4*>(dst + c) = v[j][i];
+      }
     }
   }
+}
+
+template <bool GATHER>
+static int launch_rows_copy(float* map, float* rows, const sast_selection* sel, int C, cudaStream_t st) {
+  const dim3 grid(148 * 8), block(256);
+  if (C <= 32) rows_copy_kernel<GATHER, 8, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 64) rows_copy_kernel<GATHER, 16, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 128) rows_copy_kernel<GATHER, 32, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 256) rows_copy_kernel<GATHER, 32, 2><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 512) rows_copy_kernel<GATHER, 32, 4><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 1024) rows_copy_kernel<GATHER, 32, 8><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else return SAST_E_UNSUPPORTED;
+  SAST_LAUNCH_CHECK();
+  return SAST_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -327,6 +382,15 @@ size_t layer_workspace_layout(long long P, int C, int I, int B, int precision, v
   return off;
 }
 
+static int attention_variant() {
+  static int v = -1;     // read once; debug / A-B knob only
+  if (v < 0) {
+    const char* e = getenv("SAST_B200_ATTN");
+    v = (e && e[0] == 's') ? 1 : 0;
+  }
+  return v;
+}
+
 template <int EPI>
 static int launch_gemm_f32(const float* A, int lda, const float* W, const float* bias, int N, int K, const int* counts,
                            long long max_rows, const EpiParams& ep, cudaStream_t st) {
@@ -336,20 +400,25 @@ static int launch_gemm_f32(const float* A, int lda, const float* W, const float*
   return SAST_OK;
 }
 
-static int launch_gather_ln(const sast_layer_args& a, const Geom& g, const LayerWorkspace& ws, cudaStream_t st) {
-  const int nv = (g.C + 127) / 128;
-  const unsigned grid = (unsigned)((g.P + 7) / 8);
-#define SAST_GLN(NV)                                                                                                   \
-  gather_ln_kernel<NV><<<grid, 256, 0, st>>>(a.x, a.out, a.w.ln1_w, a.w.ln1_b, a.w.ln2_w, a.w.ln2_b, a.w.ln_eps,        \
-                                             a.sel.tok_row, g, a.flavor, ws.n2f, ws.n2h)
-  if (nv <= 1) SAST_GLN(1);
-  else if (nv <= 2) SAST_GLN(2);
-  else if (nv <= 4) SAST_GLN(4);
-  else if (nv <= 8) SAST_GLN(8);
-  else return SAST_E_UNSUPPORTED;
-#undef SAST_GLN
+template <int LPT, int NV, int TPW>
+static int launch_gather_ln_t(const sast_layer_args& a, const Geom& g, const LayerWorkspace& ws, cudaStream_t st) {
+  const long long tok_per_cta = 8ll * (32 / LPT) * TPW;
+  const unsigned grid = (unsigned)((g.P + tok_per_cta - 1) / tok_per_cta);
+  gather_ln_kernel<LPT, NV, TPW><<<grid, 256, 0, st>>>(a.x, a.out, a.w.ln1_w, a.w.ln1_b, a.w.ln2_w, a.w.ln2_b, a.w.ln_eps,
+                                                        a.sel.tok_row, g, a.flavor, ws.n2f, ws.n2h);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
+}
+
+static int launch_gather_ln(const sast_layer_args& a, const Geom& g, const LayerWorkspace& ws, cudaStream_t st) {
+  const int C = g.C;
+  if (C <= 32) return launch_gather_ln_t<8, 1, 4>(a, g, ws, st);
+  if (C <= 64) return launch_gather_ln_t<16, 1, 4>(a, g, ws, st);
+  if (C <= 128) return launch_gather_ln_t<32, 1, 4>(a, g, ws, st);
+  if (C <= 256) return launch_gather_ln_t<32, 2, 4>(a, g, ws, st);
+  if (C <= 512) return launch_gather_ln_t<32, 4, 2>(a, g, ws, st);
+  if (C <= 1024) return launch_gather_ln_t<32, 8, 1>(a, g, ws, st);
+  return SAST_E_UNSUPPORTED;
 }
 
 }  // namespace sast
@@ -369,8 +438,8 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
   const sast_layer_weights& w = a.w;
   SAST_CHECK_PTR(w.ln1_w); SAST_CHECK_PTR(w.ln1_b); SAST_CHECK_PTR(w.ln2_w); SAST_CHECK_PTR(w.ln2_b);
   SAST_CHECK_PTR(w.qkv_w); SAST_CHECK_PTR(w.proj_w); SAST_CHECK_PTR(w.mlp1_w); SAST_CHECK_PTR(w.mlp2_w);
-  SAST_CHECK_PTR(a.sel.counts); SAST_CHECK_PTR(a.sel.tok_row); SAST_CHECK_PTR(a.sel.row_tok);
-  SAST_CHECK_PTR(a.sel.win_K); SAST_CHECK_PTR(a.sel.win_row0);
+  SAST_CHECK_PTR(a.sel.counts); SAST_CHECK_PTR(a.sel.tok_row); SAST_CHECK_PTR(a.sel.row_tok); SAST_CHECK_PTR(a.sel.row_pix);
+  SAST_CHECK_PTR(a.sel.win_K); SAST_CHECK_PTR(a.sel.win_row0); SAST_CHECK_PTR(a.sel.tiles);
   const Geom g = make_geom(a.g, a.flavor);
   const int C = g.C, I = w.I;
   if (C % 32 != 0 || I % 32 != 0 || I <= 0 || C > 1024) return SAST_E_SHAPE;
@@ -389,7 +458,7 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
   if (rc) return rc;
 
   EpiParams ep{};
-  ep.g = g; ep.flavor = a.flavor; ep.C = C; ep.row_tok = a.sel.row_tok;
+  ep.C = C; ep.row_pix = a.sel.row_pix;
 
   if (a.precision == SAST_FP32) {
     // qkv
@@ -422,7 +491,7 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
     ep.out_bf16 = (__nv_bfloat16*)ws.qkv; ep.ldo = 3 * C;
     rc = launch_gemm_tc(ws.n2h, C, (const __nv_bfloat16*)w.qkv_w_bf16, w.qkv_b, 3 * C, C, a.sel.counts, g.P, EPI_STORE, ep, st);
     if (rc) return rc;
-    rc = launch_attention_tc((const __nv_bfloat16*)ws.qkv, (__nv_bfloat16*)ws.att, C, a.sel, g.NW, g.T, st);
+    rc = launch_attention_tc((const __nv_bfloat16*)ws.qkv, (__nv_bfloat16*)ws.att, C, a.sel, g.NW, g.T, g.P, attention_variant(), st);
     if (rc) return rc;
     ep.out_f32 = ws.yf; ep.out_bf16 = ws.yh; ep.ldo = C; ep.resid = ws.n2f; ep.ldr = C; ep.gamma = w.gamma1;
     rc = launch_gemm_tc((const __nv_bfloat16*)ws.att, C, (const __nv_bfloat16*)w.proj_w_bf16, w.proj_b, C, C, a.sel.counts, g.P,
@@ -446,7 +515,7 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
   if (a.enable_cb) {
     cb_mean_kernel<<<dim3(g.B, (C + 31) / 32), dim3(32, 8), 0, st>>>(ws.mtmp, C, a.sel.win_row0, g.N, 1.0f / (float)(g.N * g.T), ws.cbmean);
     SAST_LAUNCH_CHECK();
-    cb_scatter_kernel<<<148 * 8, 256, 0, st>>>(ws.mtmp, ws.yf, ws.cbmean, w.gamma2, a.sel.counts, a.sel.row_tok, g, a.flavor, a.out);
+    cb_scatter_kernel<<<148 * 8, 256, 0, st>>>(ws.mtmp, ws.yf, ws.cbmean, w.gamma2, a.sel.counts, a.sel.row_tok, a.sel.row_pix, g, a.out);
     SAST_LAUNCH_CHECK();
   }
   return SAST_OK;
@@ -455,23 +524,19 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
 extern "C" int sast_gather(const sast_geom* gp, int32_t flavor, const float* x, const sast_selection* sel, float* rows, void* stream) {
   using namespace sast;
   SAST_CHECK_PTR(gp); SAST_CHECK_PTR(x); SAST_CHECK_PTR(sel); SAST_CHECK_PTR(rows);
+  SAST_CHECK_PTR(sel->counts); SAST_CHECK_PTR(sel->row_pix);
   int rc = check_geom(*gp, flavor);
   if (rc) return rc;
   if (gp->C % 4 != 0) return SAST_E_SHAPE;
-  const Geom g = make_geom(*gp, flavor);
-  rows_copy_kernel<true><<<148 * 8, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(x), rows, sel->counts, sel->row_tok, g, flavor);
-  SAST_LAUNCH_CHECK();
-  return SAST_OK;
+  return launch_rows_copy<true>(const_cast<float*>(x), rows, sel, gp->C, (cudaStream_t)stream);
 }
 
 extern "C" int sast_scatter(const sast_geom* gp, int32_t flavor, const float* rows, const sast_selection* sel, float* x, void* stream) {
   using namespace sast;
   SAST_CHECK_PTR(gp); SAST_CHECK_PTR(x); SAST_CHECK_PTR(sel); SAST_CHECK_PTR(rows);
+  SAST_CHECK_PTR(sel->counts); SAST_CHECK_PTR(sel->row_pix);
   int rc = check_geom(*gp, flavor);
   if (rc) return rc;
   if (gp->C % 4 != 0) return SAST_E_SHAPE;
-  const Geom g = make_geom(*gp, flavor);
-  rows_copy_kernel<false><<<148 * 8, 256, 0, (cudaStream_t)stream>>>(x, const_cast<float*>(rows), sel->counts, sel->row_tok, g, flavor);
-  SAST_LAUNCH_CHECK();
-  return SAST_OK;
+  return launch_rows_copy<false>(x, const_cast<float*>(rows), sel, gp->C, (cudaStream_t)stream);
 }

@@ -20,9 +20,7 @@ struct EpiParams {
   const float* resid;      // [rows, ldr] fp32
   int ldr;
   const float* gamma;      // [N] or nullptr (identity)
-  const int* row_tok;      // compacted row -> token q (partitioned order), for EPI_SCATTER
-  Geom g;
-  int flavor;
+  const int* row_pix;      // compacted row -> NHWC pixel index, for EPI_SCATTER
   int C;                   // channels of the NHWC map (EPI_SCATTER)
 };
 
@@ -43,7 +41,8 @@ size_t layer_workspace_layout(long long P, int C, int I, int B, int precision, v
 // tensor-core launchers (gemm_tc.cu / attn_tc.cu); M is read on the device from counts[1]
 int launch_gemm_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, int N, int K,
                    const int* counts, long long max_rows, int epi, const EpiParams& ep, cudaStream_t st);
+// variant 0: tcgen05 tiles; 1: CUDA-core kernel (debug knob SAST_B200_ATTN=simt)
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, const sast_selection& sel, int NW, int T,
-                        cudaStream_t st);
+                        long long max_rows, int variant, cudaStream_t st);
 
 }  // namespace sast

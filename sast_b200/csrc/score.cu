@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ x,
                                                     long long pos_bstride, const float* __restrict__ Ws,
                                                     const float* __restrict__ bs, const float* __restrict__ sig,
                                                     const float* __restrict__ inv, int HW, int C, long long P,
-                                                    float* __restrict__ xw, float* __restrict__ tok_score) {
+                                                    float* __restrict__ xw, float* __restrict__ l1_out) {
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ x,
   const long long lpos = ltok_ok ? ((ltok / HW) * pos_bstride + (ltok % HW) * (long long)C) : 0;
 
   float l1[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int n0 = 0; n0 < C; n0 += BN) {
+  {
+    const int n0 = blockIdx.y * BN;      // one 64-wide slice of output channels per CTA
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -108,8 +109,17 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ x,
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     const long long tok = m0 + ty * 4 + i;
-    if (tx == 0 && tok < P) tok_score[tok] = v;
+    if (tx == 0 && tok < P) l1_out[(long long)blockIdx.y * P + tok] = v;   // partial over this channel slice
   }
+}
+
+// tok_score[p] = sum over channel slices, in slice order (deterministic)
+__global__ void score_reduce_kernel(const float* __restrict__ part, int ny, long long P, float* __restrict__ tok_score) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float s = 0.f;
+  for (int y = 0; y < ny; ++y) s += part[(long long)y * P + p];
+  tok_score[p] = s;
 }
 
 __global__ void add_pos_kernel(const float4* __restrict__ x, const float4* __restrict__ pos, long long pos_bstride4,
@@ -146,9 +156,15 @@ extern "C" int sast_score_fwd(const sast_score_args* a, void* stream) {
   float* inv = a->ctrl_scratch + (size_t)g.B * g.C;
   sast::controls_kernel<<<g.B, 128, 0, st>>>(a->r, a->ctrl_w, a->n_bins, g.C, a->amp, sig, inv);
   SAST_LAUNCH_CHECK();
-  const int grid = (int)((P + sast::BM - 1) / sast::BM);
+  const int ny = (g.C + sast::BN - 1) / sast::BN;
+  const dim3 grid((unsigned)((P + sast::BM - 1) / sast::BM), ny);
+  float* part = ny == 1 ? a->tok_score : a->ctrl_scratch + 2 * (size_t)g.B * g.C;
   sast::score_kernel<<<grid, 256, 0, st>>>(a->x, a->pos, a->pos_batch_stride, a->score_w, a->score_b, sig, inv, HW, g.C, P,
-                                           a->xw, a->tok_score);
+                                           a->xw, part);
   SAST_LAUNCH_CHECK();
+  if (ny > 1) {
+    sast::score_reduce_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(part, ny, P, a->tok_score);
+    SAST_LAUNCH_CHECK();
+  }
   return SAST_OK;
 }

@@ -2,14 +2,18 @@
 // (replaces SAST.py:84-96 window_selection/token_selection and :258-281
 //  get_score_index_2d21d / get_score_index_with_padding, plus the isin() at :122/:147).
 //
-// Two launches, one CTA per frame each, no host round trip:
-//   select_flags_kernel  : softmax + threshold (or thresholds on given probabilities, or
-//                          given flags) -> keep flag per window and per token, K per window,
-//                          per-frame totals.  Warp per window; token keep via __ballot_sync.
-//   select_index_kernel  : exclusive prefix sums (ranks of kept windows, compacted row of each
-//                          kept token) across frames and windows -> win_rank, sel_win,
-//                          win_row0, tok_row, row_tok, counts{M,S,Kmax}.  Ballot/popc prefix
-//                          inside a window, shuffle scans across windows.
+// Four small launches, no host round trip, both partition flavours of a block (window layer and
+// grid layer share the same per-token scores, SAST.py:141-142) batched along gridDim.z:
+//   win_logit_kernel     : warp per window, mean of its T token scores.
+//   select_flags_kernel  : CTA per 8 windows: frame softmax statistics over the N logits, window
+//                          keep = prob >= thr_win; per kept window softmax over T token scores,
+//                          keep via __ballot_sync, K = popc.  (Or thresholds on given
+//                          probabilities / given flags: modes PROBS, FLAGS.)
+//   select_scan_kernel   : CTA per frame: exclusive prefix sums across frames and windows ->
+//                          win_rank, sel_win, win_row0, counts{M,S,Kmax}; greedy packing of
+//                          consecutive windows into <=128-row attention tiles.
+//   select_tokens_kernel : warp per window: ballot/popc prefix inside the window -> tok_row,
+//                          row_tok, row_pix (compacted row <-> token <-> NHWC pixel).
 // The compare is `prob >= thr` on fp32 with thr = fp32((1/N)/(1+BOUNCE)) exactly as torch
 // evaluates `x >= d / (1 + b)`; ids come out ascending like torch.nonzero.
 #include "common.cuh"
@@ -17,6 +21,16 @@
 namespace sast {
 
 constexpr int kSelThreads = 256;
+constexpr int kSelWarps = kSelThreads / 32;
+
+struct SelectParams {
+  sast_select_args a;      // primary selection (a.flavor, a.sel)
+  sast_selection sel_b;    // optional second selection over the same scores
+  int flavor_b;
+};
+
+__device__ __forceinline__ const sast_selection& pick_sel(const SelectParams& p, int z) { return z == 0 ? p.a.sel : p.sel_b; }
+__device__ __forceinline__ int pick_flavor(const SelectParams& p, int z) { return z == 0 ? p.a.flavor : p.flavor_b; }
 
 __device__ __forceinline__ float block_reduce_max(float v, float* red) {
   v = warp_max(v);
@@ -37,105 +51,103 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
   return r;
 }
 
-__global__ void __launch_bounds__(kSelThreads) select_flags_kernel(sast_select_args a) {
-  extern __shared__ float sm[];
-  const Geom g = make_geom(a.g, a.flavor);
-  float* wlogit = sm;                        // [N]
-  int* wkeep = reinterpret_cast<int*>(sm + g.N);  // [N]
-  __shared__ float red[kSelThreads / 32];
-  __shared__ int tot[3];
-  const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int HW = g.H * g.W;
-  const float* fs = a.tok_score ? a.tok_score + (size_t)b * HW : nullptr;
-  if (threadIdx.x < 3) tot[threadIdx.x] = 0;
+__global__ void __launch_bounds__(kSelThreads) win_logit_kernel(SelectParams p) {
+  const int flavor = pick_flavor(p, blockIdx.z);
+  const sast_selection& sel = pick_sel(p, blockIdx.z);
+  const Geom g = make_geom(p.a.g, flavor);
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * kSelWarps + (threadIdx.x >> 5);
+  if (w >= g.NW) return;
+  const int b = w / g.N, n = w - b * g.N;
+  const float* fs = p.a.tok_score + (size_t)b * g.H * g.W;
+  float s = 0.f;
+  for (int t = lane; t < g.T; t += 32) s += fs[frame_pixel(n, t, g.H, g.W, g.p0, g.p1, flavor)];
+  s = warp_sum(s);
+  if (lane == 0) sel.win_logit[w] = s / (float)g.T;
+}
 
-  // ---- windows -------------------------------------------------------------------------
-  if (a.mode == SAST_SEL_SCORES) {
-    for (int n = wid; n < g.N; n += nwarp) {
-      float s = 0.f;
-      for (int t = lane; t < g.T; t += 32) s += fs[frame_pixel(n, t, g.H, g.W, g.p0, g.p1, a.flavor)];
-      s = warp_sum(s);
-      if (lane == 0) wlogit[n] = s / (float)g.T;
-    }
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int n = threadIdx.x; n < g.N; n += blockDim.x) mx = fmaxf(mx, wlogit[n]);
-    mx = block_reduce_max(mx, red);
-    float se = 0.f;
-    for (int n = threadIdx.x; n < g.N; n += blockDim.x) se += expf(wlogit[n] - mx);
-    se = block_reduce_sum(se, red);
-    for (int n = threadIdx.x; n < g.N; n += blockDim.x) {
-      const float p = expf(wlogit[n] - mx) / se;
-      wkeep[n] = p >= a.thr_win;
-      if (a.win_prob_out) a.win_prob_out[(size_t)b * g.N + n] = p;
-    }
-  } else if (a.mode == SAST_SEL_PROBS) {
-    for (int n = threadIdx.x; n < g.N; n += blockDim.x) wkeep[n] = a.win_prob[(size_t)b * g.N + n] >= a.thr_win;
-  } else {
-    for (int n = threadIdx.x; n < g.N; n += blockDim.x) wkeep[n] = a.win_flag[(size_t)b * g.N + n] != 0;
+__global__ void __launch_bounds__(kSelThreads) select_flags_kernel(SelectParams p) {
+  const int flavor = pick_flavor(p, blockIdx.z);
+  const sast_selection& sel = pick_sel(p, blockIdx.z);
+  const sast_select_args& a = p.a;
+  const Geom g = make_geom(a.g, flavor);
+  __shared__ float red[kSelWarps];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = blockIdx.x * kSelWarps + wid;
+  const int w = b * g.N + n;
+
+  // ---- window keep ----------------------------------------------------------------------
+  float mx = 0.f, se = 1.f;
+  if (a.mode == SAST_SEL_SCORES) {   // frame softmax statistics, identical in every CTA of the frame
+    const float* wl = sel.win_logit + (size_t)b * g.N;
+    float m = -INFINITY;
+    for (int i = threadIdx.x; i < g.N; i += blockDim.x) m = fmaxf(m, wl[i]);
+    mx = block_reduce_max(m, red);
+    float e = 0.f;
+    for (int i = threadIdx.x; i < g.N; i += blockDim.x) e += expf(wl[i] - mx);
+    se = block_reduce_sum(e, red);
   }
-  __syncthreads();
+  if (n >= g.N) return;               // warp-uniform, after the block-wide reductions
+  bool wkeep;
+  if (a.mode == SAST_SEL_SCORES) {
+    const float pw = expf(sel.win_logit[w] - mx) / se;
+    wkeep = pw >= a.thr_win;
+    if (a.win_prob_out && blockIdx.z == 0 && lane == 0) a.win_prob_out[w] = pw;
+  } else if (a.mode == SAST_SEL_PROBS) {
+    wkeep = a.win_prob[w] >= a.thr_win;
+  } else {
+    wkeep = a.win_flag[w] != 0;
+  }
 
-  // ---- tokens --------------------------------------------------------------------------
-  int accM = 0, accS = 0, accK = 0;
-  for (int n = wid; n < g.N; n += nwarp) {
-    const int w = b * g.N + n;
-    const size_t q0 = (size_t)w * g.T;
-    if (!wkeep[n]) {
-      for (int t = lane; t < g.T; t += 32) a.sel.tok_keep[q0 + t] = 0;
-      if (lane == 0) { a.sel.win_K[w] = 0; a.sel.win_rank[w] = -1; }
-      continue;
-    }
-    float v[4];
-    bool keep[4];
-    if (a.mode == SAST_SEL_SCORES) {
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int t = i * 32 + lane;
-        v[i] = t < g.T ? fs[frame_pixel(n, t, g.H, g.W, g.p0, g.p1, a.flavor)] : -INFINITY;
-        mx = fmaxf(mx, v[i]);
-      }
-      mx = warp_max(mx);
-      float se = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[i] = (i * 32 + lane < g.T) ? expf(v[i] - mx) : 0.f;
-        se += v[i];
-      }
-      se = warp_sum(se);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int t = i * 32 + lane;
-        const float p = v[i] / se;
-        keep[i] = t < g.T && p >= a.thr_tok;
-        if (a.tok_prob_out && t < g.T) a.tok_prob_out[q0 + t] = p;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int t = i * 32 + lane;
-        keep[i] = false;
-        if (t < g.T) keep[i] = a.mode == SAST_SEL_PROBS ? (a.tok_prob[q0 + t] >= a.thr_tok) : (a.tok_flag[q0 + t] != 0);
-      }
-    }
-    int K = 0;
+  // ---- tokens ------------------------------------------------------------------------------
+  const size_t q0 = (size_t)w * g.T;
+  if (!wkeep) {
+    for (int t = lane; t < g.T; t += 32) sel.tok_keep[q0 + t] = 0;
+    if (lane == 0) { sel.win_K[w] = 0; sel.win_rank[w] = -1; }
+    return;
+  }
+  float v[4];
+  bool keep[4];
+  if (a.mode == SAST_SEL_SCORES) {
+    const float* fs = a.tok_score + (size_t)b * g.H * g.W;
+    float tm = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = i * 32 + lane;
-      K += __popc(__ballot_sync(kFull, keep[i]));
-      if (t < g.T) a.sel.tok_keep[q0 + t] = keep[i] ? 1 : 0;
+      v[i] = t < g.T ? fs[frame_pixel(n, t, g.H, g.W, g.p0, g.p1, flavor)] : -INFINITY;
+      tm = fmaxf(tm, v[i]);
     }
-    if (lane == 0) { a.sel.win_K[w] = K; a.sel.win_rank[w] = 0; }
-    accM += 1; accS += K; accK = max(accK, K);
+    tm = warp_max(tm);
+    float ts = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = (i * 32 + lane < g.T) ? expf(v[i] - tm) : 0.f;
+      ts += v[i];
+    }
+    ts = warp_sum(ts);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = i * 32 + lane;
+      const float pt = v[i] / ts;
+      keep[i] = t < g.T && pt >= a.thr_tok;
+      if (a.tok_prob_out && blockIdx.z == 0 && t < g.T) a.tok_prob_out[q0 + t] = pt;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = i * 32 + lane;
+      keep[i] = false;
+      if (t < g.T) keep[i] = a.mode == SAST_SEL_PROBS ? (a.tok_prob[q0 + t] >= a.thr_tok) : (a.tok_flag[q0 + t] != 0);
+    }
   }
-  if (lane == 0) {
-    atomicAdd(&tot[0], accM);
-    atomicAdd(&tot[1], accS);
-    atomicMax(&tot[2], accK);
+  int K = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = i * 32 + lane;
+    K += __popc(__ballot_sync(kFull, keep[i]));
+    if (t < g.T) sel.tok_keep[q0 + t] = keep[i] ? 1 : 0;
   }
-  __syncthreads();
-  if (threadIdx.x < 3) a.sel.frame_tot[b * 4 + threadIdx.x] = tot[threadIdx.x];
+  if (lane == 0) { sel.win_K[w] = K; sel.win_rank[w] = 0; }
 }
 
 // exclusive scan of two ints over the block; returns block totals through tot0/tot1
@@ -160,58 +172,105 @@ __device__ __forceinline__ void block_excl_scan2(int v0, int v1, int& e0, int& e
   e1 = b1 + i1 - v1;
 }
 
-__global__ void __launch_bounds__(kSelThreads) select_index_kernel(sast_select_args a) {
-  const Geom g = make_geom(a.g, a.flavor);
-  __shared__ int ws[kSelThreads / 32][2];
-  __shared__ int base[2];
-  const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  if (threadIdx.x == 0) {
-    int m = 0, s = 0;
-    for (int i = 0; i < b; ++i) { m += a.sel.frame_tot[i * 4]; s += a.sel.frame_tot[i * 4 + 1]; }
-    base[0] = m; base[1] = s;
-    if (b == g.B - 1) {
-      int M = m + a.sel.frame_tot[b * 4], S = s + a.sel.frame_tot[b * 4 + 1], Kmax = 0;
-      for (int i = 0; i < g.B; ++i) Kmax = max(Kmax, a.sel.frame_tot[i * 4 + 2]);
-      a.sel.counts[0] = M; a.sel.counts[1] = S; a.sel.counts[2] = Kmax; a.sel.counts[3] = 0;
-      a.sel.win_row0[g.NW] = S;
-    }
+__global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p) {
+  const int flavor = pick_flavor(p, blockIdx.z);
+  const sast_selection& sel = pick_sel(p, blockIdx.z);
+  const Geom g = make_geom(p.a.g, flavor);
+  extern __shared__ int kbuf[];          // [N] K of this frame's windows (for the tile packer)
+  __shared__ int ws[kSelWarps][2];
+  __shared__ int red3[kSelWarps][3];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  // totals of all earlier frames (int adds: order-independent)
+  int m = 0, s = 0, km = 0;
+  for (int w = threadIdx.x; w < b * g.N; w += blockDim.x) {
+    const int K = sel.win_K[w];
+    m += sel.win_rank[w] >= 0; s += K; km = max(km, K);
   }
+  m = warp_sum_i(m); s = warp_sum_i(s); km = warp_max_i(km);
+  if (lane == 0) { red3[wid][0] = m; red3[wid][1] = s; red3[wid][2] = km; }
   __syncthreads();
-  int run_m = base[0], run_s = base[1];
+  int run_m = 0, run_s = 0, kmax = 0;
+  for (int i = 0; i < kSelWarps; ++i) { run_m += red3[i][0]; run_s += red3[i][1]; kmax = max(kmax, red3[i][2]); }
+
   for (int n0 = 0; n0 < g.N; n0 += blockDim.x) {
     const int n = n0 + threadIdx.x;
     const int w = b * g.N + n;
     const bool in = n < g.N;
-    const int kept = in ? (a.sel.win_rank[w] >= 0) : 0;
-    const int K = in ? a.sel.win_K[w] : 0;
+    const int kept = in ? (sel.win_rank[w] >= 0) : 0;
+    const int K = in ? sel.win_K[w] : 0;
+    if (in) kbuf[n] = K;
+    kmax = max(kmax, K);
     int em, es, tm, ts;
     block_excl_scan2(kept, K, em, es, tm, ts, ws);
     if (in) {
-      a.sel.win_row0[w] = run_s + es;
+      sel.win_row0[w] = run_s + es;
       if (kept) {
-        a.sel.win_rank[w] = run_m + em;
-        a.sel.sel_win[run_m + em] = w;
+        sel.win_rank[w] = run_m + em;
+        sel.sel_win[run_m + em] = w;
       }
+      sel.tiles[2 * w] = 0;
+      sel.tiles[2 * w + 1] = 0;
     }
     run_m += tm; run_s += ts;
     __syncthreads();
   }
-  __syncthreads();
-  for (int n = wid; n < g.N; n += nwarp) {
-    const int w = b * g.N + n;
-    const size_t q0 = (size_t)w * g.T;
-    const int K = a.sel.win_K[w];
-    const int row0 = a.sel.win_row0[w];
-    int run = 0;
-    for (int t0 = 0; t0 < g.T; t0 += 32) {
-      const int t = t0 + lane;
-      const bool keep = K > 0 && t < g.T && a.sel.tok_keep[q0 + t] != 0;
-      const unsigned bal = __ballot_sync(kFull, keep);
-      const int pre = __popc(bal & ((1u << lane) - 1u));
-      if (t < g.T) a.sel.tok_row[q0 + t] = keep ? row0 + run + pre : -1;
-      if (keep) a.sel.row_tok[row0 + run + pre] = (int)(q0 + t);
-      run += __popc(bal);
+  if (b == g.B - 1) {
+    kmax = warp_max_i(kmax);
+    __syncthreads();
+    if (lane == 0) red3[wid][2] = kmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int k = 0;
+      for (int i = 0; i < kSelWarps; ++i) k = max(k, red3[i][2]);
+      sel.counts[0] = run_m; sel.counts[1] = run_s; sel.counts[2] = k; sel.counts[3] = 0;
+      sel.win_row0[g.NW] = run_s;
     }
+  }
+  __syncthreads();
+  // greedy packing of consecutive windows of this frame into attention tiles of <= 128 rows:
+  // tiles[2w] = rows of the tile led by window w (0: not a leader), tiles[2w+1] = end window (exclusive)
+  if (threadIdx.x == 0) {
+    int start = 0, rows = 0;
+    for (int n = 0; n < g.N; ++n) {
+      const int K = kbuf[n];
+      if (rows + K > 128) {
+        sel.tiles[2 * (b * g.N + start)] = rows;
+        sel.tiles[2 * (b * g.N + start) + 1] = b * g.N + n;
+        start = n; rows = 0;
+      }
+      rows += K;
+    }
+    if (rows > 0) {
+      sel.tiles[2 * (b * g.N + start)] = rows;
+      sel.tiles[2 * (b * g.N + start) + 1] = b * g.N + g.N;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelectParams p) {
+  const int flavor = pick_flavor(p, blockIdx.z);
+  const sast_selection& sel = pick_sel(p, blockIdx.z);
+  const Geom g = make_geom(p.a.g, flavor);
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * kSelWarps + (threadIdx.x >> 5);
+  if (w >= g.NW) return;
+  const int b = w / g.N, n = w - b * g.N;
+  const size_t q0 = (size_t)w * g.T;
+  const int K = sel.win_K[w];
+  const int row0 = sel.win_row0[w];
+  int run = 0;
+  for (int t0 = 0; t0 < g.T; t0 += 32) {
+    const int t = t0 + lane;
+    const bool keep = K > 0 && t < g.T && sel.tok_keep[q0 + t] != 0;
+    const unsigned bal = __ballot_sync(kFull, keep);
+    const int pre = __popc(bal & ((1u << lane) - 1u));
+    if (t < g.T) sel.tok_row[q0 + t] = keep ? row0 + run + pre : -1;
+    if (keep) {
+      sel.row_tok[row0 + run + pre] = (int)(q0 + t);
+      sel.row_pix[row0 + run + pre] = b * g.H * g.W + frame_pixel(n, t, g.H, g.W, g.p0, g.p1, flavor);
+    }
+    run += __popc(bal);
   }
 }
 
@@ -220,18 +279,19 @@ __global__ void __launch_bounds__(kSelThreads) select_index_kernel(sast_select_a
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" size_t sast_selection_bytes(int32_t B, int32_t NW, int32_t P) {
+  (void)B;
   size_t n = 0;
   n += align_up(8 * 4, 16);                     // counts
-  n += 3 * align_up((size_t)NW * 4, 16);        // win_K, win_rank, sel_win
+  n += 4 * align_up((size_t)NW * 4, 16);        // win_K, win_rank, sel_win, win_logit
   n += align_up(((size_t)NW + 1) * 4, 16);      // win_row0
-  n += 2 * align_up((size_t)P * 4, 16);         // tok_row, row_tok
-  n += align_up((size_t)B * 16, 16);            // frame_tot
+  n += 3 * align_up((size_t)P * 4, 16);         // tok_row, row_tok, row_pix
   n += align_up((size_t)P, 16);                 // tok_keep
-  n += align_up((size_t)NW * 16, 16);           // tiles
+  n += align_up((size_t)NW * 8, 16);            // tiles
   return n;
 }
 
 extern "C" int sast_selection_bind(void* pool, int32_t B, int32_t NW, int32_t P, sast_selection* out) {
+  (void)B;
   SAST_CHECK_PTR(pool); SAST_CHECK_PTR(out);
   if ((reinterpret_cast<uintptr_t>(pool) & 15) != 0) return SAST_E_SHAPE;
   char* p = (char*)pool;
@@ -240,35 +300,58 @@ extern "C" int sast_selection_bind(void* pool, int32_t B, int32_t NW, int32_t P,
   out->win_K = (int32_t*)take((size_t)NW * 4);
   out->win_rank = (int32_t*)take((size_t)NW * 4);
   out->sel_win = (int32_t*)take((size_t)NW * 4);
+  out->win_logit = (float*)take((size_t)NW * 4);
   out->win_row0 = (int32_t*)take(((size_t)NW + 1) * 4);
   out->tok_row = (int32_t*)take((size_t)P * 4);
   out->row_tok = (int32_t*)take((size_t)P * 4);
-  out->frame_tot = (int32_t*)take((size_t)B * 16);
+  out->row_pix = (int32_t*)take((size_t)P * 4);
   out->tok_keep = (uint8_t*)take((size_t)P);
-  out->tiles = (int32_t*)take((size_t)NW * 16);
+  out->tiles = (int32_t*)take((size_t)NW * 8);
   return SAST_OK;
 }
 
-extern "C" int sast_select(const sast_select_args* a, void* stream) {
+static int check_sel(const sast_selection& s) {
+  SAST_CHECK_PTR(s.counts); SAST_CHECK_PTR(s.win_K); SAST_CHECK_PTR(s.win_rank); SAST_CHECK_PTR(s.win_row0);
+  SAST_CHECK_PTR(s.sel_win); SAST_CHECK_PTR(s.tok_row); SAST_CHECK_PTR(s.row_tok); SAST_CHECK_PTR(s.row_pix);
+  SAST_CHECK_PTR(s.win_logit); SAST_CHECK_PTR(s.tok_keep); SAST_CHECK_PTR(s.tiles);
+  return SAST_OK;
+}
+
+extern "C" int sast_select2(const sast_select_args* a, int32_t flavor_b, const sast_selection* sel_b, void* stream) {
   SAST_CHECK_PTR(a);
-  if (a->flavor != SAST_WINDOW && a->flavor != SAST_GRID && a->flavor != SAST_FLAT) return SAST_E_UNSUPPORTED;
-  int rc = sast::check_geom(a->g, a->flavor);
-  if (rc) return rc;
+  const int nf = sel_b ? 2 : 1;
+  for (int z = 0; z < nf; ++z) {
+    const int fl = z == 0 ? a->flavor : flavor_b;
+    if (fl != SAST_WINDOW && fl != SAST_GRID && fl != SAST_FLAT) return SAST_E_UNSUPPORTED;
+    int rc = sast::check_geom(a->g, fl);
+    if (rc) return rc;
+    rc = check_sel(z == 0 ? a->sel : *sel_b);
+    if (rc) return rc;
+  }
   if (a->mode == SAST_SEL_SCORES) { SAST_CHECK_PTR(a->tok_score); }
   else if (a->mode == SAST_SEL_PROBS) { SAST_CHECK_PTR(a->win_prob); SAST_CHECK_PTR(a->tok_prob); }
   else if (a->mode == SAST_SEL_FLAGS) { SAST_CHECK_PTR(a->win_flag); SAST_CHECK_PTR(a->tok_flag); }
   else return SAST_E_UNSUPPORTED;
-  const sast_selection& s = a->sel;
-  SAST_CHECK_PTR(s.counts); SAST_CHECK_PTR(s.win_K); SAST_CHECK_PTR(s.win_rank); SAST_CHECK_PTR(s.win_row0);
-  SAST_CHECK_PTR(s.sel_win); SAST_CHECK_PTR(s.tok_row); SAST_CHECK_PTR(s.row_tok); SAST_CHECK_PTR(s.frame_tot);
-  SAST_CHECK_PTR(s.tok_keep);
   const sast::Geom g = sast::make_geom(a->g, a->flavor);
-  const size_t smem = (size_t)g.N * 8;
+  const size_t smem = (size_t)g.N * 4;
   if (smem > 40 * 1024) return SAST_E_UNSUPPORTED;
+  sast::SelectParams p;
+  p.a = *a;
+  p.sel_b = sel_b ? *sel_b : a->sel;
+  p.flavor_b = sel_b ? flavor_b : a->flavor;
   cudaStream_t st = (cudaStream_t)stream;
-  sast::select_flags_kernel<<<g.B, sast::kSelThreads, smem, st>>>(*a);
+  const unsigned wblocks = (unsigned)((g.NW + sast::kSelWarps - 1) / sast::kSelWarps);
+  if (a->mode == SAST_SEL_SCORES) {
+    sast::win_logit_kernel<<<dim3(wblocks, 1, nf), sast::kSelThreads, 0, st>>>(p);
+    SAST_LAUNCH_CHECK();
+  }
+  sast::select_flags_kernel<<<dim3((g.N + sast::kSelWarps - 1) / sast::kSelWarps, g.B, nf), sast::kSelThreads, 0, st>>>(p);
   SAST_LAUNCH_CHECK();
-  sast::select_index_kernel<<<g.B, sast::kSelThreads, 0, st>>>(*a);
+  sast::select_scan_kernel<<<dim3(g.B, 1, nf), sast::kSelThreads, smem, st>>>(p);
+  SAST_LAUNCH_CHECK();
+  sast::select_tokens_kernel<<<dim3(wblocks, 1, nf), sast::kSelThreads, 0, st>>>(p);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }
+
+extern "C" int sast_select(const sast_select_args* a, void* stream) { return sast_select2(a, 0, nullptr, stream); }

@@ -78,7 +78,7 @@ def score_fwd(x: Tensor, pos: Tensor, r: Tensor, ctrl_w: Tensor, score_w: Tensor
     r = _f32c(r, "r")
     xw = torch.empty_like(x)
     tok = torch.empty(B, H, W, device=x.device, dtype=torch.float32)
-    scratch = torch.empty(2 * B * Cc, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(2 * B * Cc + ((Cc + 63) // 64) * B * H * W, device=x.device, dtype=torch.float32)
     a = L.ScoreArgs(_geom(B, H, W, Cc, 1, 1), x.data_ptr(), pos.data_ptr(), pstride, r.data_ptr(), r.shape[1],
                     _f32c(ctrl_w, "ctrl_w").data_ptr(), _f32c(score_w, "score_w").data_ptr(),
                     _f32c(score_b, "score_b").data_ptr(), float(amp), xw.data_ptr(), tok.data_ptr(),
@@ -115,9 +115,12 @@ def _(x, pos):
 # --------------------------------------------------------------------------------------------
 # a5/a6  selection
 # --------------------------------------------------------------------------------------------
+def _pool_words(B, NW, P) -> int:
+    return (L.lib().sast_selection_bytes(B, NW, P) + 3) // 4
+
+
 def _pool_alloc(B, NW, P, device) -> Tensor:
-    nbytes = L.lib().sast_selection_bytes(B, NW, P)
-    return torch.empty((nbytes + 3) // 4, device=device, dtype=torch.int32)
+    return torch.empty(_pool_words(B, NW, P), device=device, dtype=torch.int32)
 
 
 def _bind(pool: Tensor, B, NW, P) -> L.Selection:
@@ -153,8 +156,31 @@ def select(tok_score: Tensor, p0: int, p1: int, flavor: int, thr_win: float, thr
 @select.register_fake
 def _(tok_score, p0, p1, flavor, thr_win, thr_tok):
     B, H, W = tok_score.shape
-    n = (8 + 4 * (B * H * W // (p0 * p1)) * 3 + 2 * B * H * W + 64) * 2
-    return tok_score.new_empty(n, dtype=torch.int32)
+    return tok_score.new_empty(_pool_words(B, B * (H * W // (p0 * p1)), B * H * W), dtype=torch.int32)
+
+
+@torch.library.custom_op("sast::select_pair", mutates_args=())
+def select_pair(tok_score: Tensor, p0: int, p1: int, thr_win: float, thr_tok: float) -> Tuple[Tensor, Tensor]:
+    """Window-flavour and grid-flavour selections of one score map in the same launches
+    (what a first SAST block needs, SAST.py:120-123 and :138-147)."""
+    tok_score = _f32c(tok_score, "tok_score")
+    B, H, W = tok_score.shape
+    T = p0 * p1
+    NW, P = B * (H * W // T), B * H * W
+    dev = tok_score.device
+    pool_a, pool_b = _pool_alloc(B, NW, P, dev), _pool_alloc(B, NW, P, dev)
+    sel_a, sel_b = _bind(pool_a, B, NW, P), _bind(pool_b, B, NW, P)
+    a = L.SelectArgs(_geom(B, H, W, 32, p0, p1), L.WINDOW, L.SEL_SCORES, tok_score.data_ptr(), 0, 0, 0, 0,
+                     float(thr_win), float(thr_tok), 0, 0, sel_a)
+    L.check(L.lib().sast_select2(C.byref(a), L.GRID, C.byref(sel_b), L.stream_ptr(dev)), "sast_select2")
+    return pool_a, pool_b
+
+
+@select_pair.register_fake
+def _(tok_score, p0, p1, thr_win, thr_tok):
+    B, H, W = tok_score.shape
+    n = _pool_words(B, B * (H * W // (p0 * p1)), B * H * W)
+    return tok_score.new_empty(n, dtype=torch.int32), tok_score.new_empty(n, dtype=torch.int32)
 
 
 def select_with_probs(tok_score: Tensor, p0, p1, flavor, thr_win, thr_tok):

@@ -336,8 +336,9 @@ class SAST_block(nn.Module):
             xw, tok = ops.score_fwd(x, pos, r, self.to_controls.weight, self.to_scores.weight, self.to_scores.bias,
                                     float(self.amp_value))
             thr_w, thr_t = ops.thresholds(N, T, self.bounce_value)
-            sel1 = ops.Selection(ops.select(tok, p0, p1, L.WINDOW, thr_w, thr_t), B, H, W, p0, p1)
-            sel2 = ops.Selection(ops.select(tok, p0, p1, L.GRID, thr_w, thr_t), B, H, W, p0, p1)
+            pool1, pool2 = ops.select_pair(tok, p0, p1, thr_w, thr_t)
+            sel1 = ops.Selection(pool1, B, H, W, p0, p1)
+            sel2 = ops.Selection(pool2, B, H, W, p0, p1)
             sel1.tok_score, sel2.tok_score = tok, tok
         else:
             xw = ops.add_pos(x, pos)

@@ -122,3 +122,39 @@ def _backbone_check(g, m, net, precision):
         assert frac_bad < (1e-3 if precision == L.FP32 else 2e-2), (st, frac_bad, diff.max().item())
         s_ref, a_ref = g.arrays[f"sum1_s{st}"]
         assert abs(h.double().abs().sum().item() - a_ref) / a_ref < (1e-4 if precision == L.FP32 else 5e-3)
+
+
+@pytest.mark.parametrize("C,part,B,H,W,amp,r_scale", [
+    (64, (6, 10), 2, 96, 160, 2e-3, 0.02),     # 1 Mpx stage-1 map, partial selection: ragged tiles
+    (64, (6, 10), 2, 96, 160, 2e-4, 1.0),      # dense scene: every token selected, 2 windows per tile
+    (128, (8, 10), 3, 32, 40, 5e-3, 0.02),     # Gen1 stage-2 map, T = 80
+    (256, (6, 10), 2, 24, 40, 2e-3, 0.02),
+    (512, (6, 10), 2, 12, 20, 2e-3, 0.02),
+    (96, (4, 5), 2, 16, 20, 2e-3, 0.02),       # "large" model width: 3 heads, K/N tails in the GEMMs
+])
+def test_block_bf16_against_fp32_path(C, part, B, H, W, amp, r_scale):
+    """The tcgen05 path (bf16 operands, fp32 accumulate) against the CUDA-core fp32 path of the
+    same library at full map sizes: identical selections, outputs within the bf16 budget."""
+    from sast_b200.config import attention_config
+    from sast_b200.backbone import PositionEmbeddingSine
+    from oracle.golden_common import make_params, with_aliases
+    blk = sast_b200.SAST_block(C, attention_config(part, AMP=amp), first_block=True)
+    shapes = {k: tuple(v.shape) for k, v in blk.state_dict().items() if ".sub_layers." not in k}
+    blk.load_state_dict(with_aliases(make_params(shapes, seed=C), blk.state_dict().keys()))
+    blk = blk.to(DEV).eval()
+    gen = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(B, H, W, C, generator=gen) * torch.linspace(0.3, 1.7, W).view(1, 1, W, 1)).to(DEV)
+    r = (torch.rand(B, 20, generator=gen) * r_scale).to(DEV)
+    pos = PositionEmbeddingSine(C // 2, normalize=True, input_size=(1, H, W))
+    outs = {}
+    for prec in (L.FP32, L.BF16):
+        blk.win_attn.precision = blk.grid_attn.precision = prec
+        with torch.no_grad():
+            y, cnt, lists = blk(x, pos, r, None)
+        outs[prec] = (y, int(cnt), [(l.tok_row >= 0).clone() for l in lists])
+    assert outs[L.FP32][1] == outs[L.BF16][1] > 0
+    for a, b in zip(outs[L.FP32][2], outs[L.BF16][2]):
+        assert torch.equal(a, b)
+    assert torch.isfinite(outs[L.BF16][0]).all()
+    err = (outs[L.FP32][0] - outs[L.BF16][0]).abs().max().item()
+    assert err < 6e-2, err

@@ -34,14 +34,14 @@ def test_struct_sizes_match_header():
     lib = L.lib()   # _load() already raises on a mismatch; spell it out here
     for which, cls in enumerate((L.Geom, L.Selection, L.ScoreArgs, L.SelectArgs, L.LayerWeights, L.LayerArgs)):
         assert lib.sast_struct_size(which) == ctypes.sizeof(cls), cls.__name__
-    assert ctypes.sizeof(L.Geom) == 24 and ctypes.sizeof(L.Selection) == 80
+    assert ctypes.sizeof(L.Geom) == 24 and ctypes.sizeof(L.Selection) == 88
 
 
 def test_selection_pool_layout():
     lib = L.lib()
     B, NW, P = 3, 48, 48 * 60
     n = lib.sast_selection_bytes(B, NW, P)
-    assert n >= 8 * 4 + 4 * NW * 4 + 2 * P * 4 + P
+    assert n >= 8 * 4 + 5 * NW * 4 + 3 * P * 4 + P + NW * 8
     s = L.Selection()
     base = 1 << 20
     assert lib.sast_selection_bind(base, B, NW, P, ctypes.byref(s)) == 0
