@@ -86,10 +86,26 @@ class ConvDownsampling_Cf2Cl(nn.Module):
                               bias=False, padding_mode='replicate')
         self.norm = nn.LayerNorm(dim_out, eps=1e-5, elementwise_affine=norm_affine)
 
+    def _weight_cl(self) -> Tensor:
+        """Conv weight in channels-last memory format (what the NHWC cuDNN kernels want), cached."""
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_wkey", None) != key:
+            self._wcl = w.detach().contiguous(memory_format=torch.channels_last)
+            self._wkey = key
+        return self._wcl if not (w.requires_grad and torch.is_grad_enabled()) else w
+
     def forward(self, x: Tensor) -> Tensor:
-        y = self.conv(x.contiguous(memory_format=torch.channels_last))
-        y = y.permute(0, 2, 3, 1)                      # NHWC view of the channels-last result
-        return self.norm(y if y.is_contiguous() else y.contiguous())
+        """x: NCHW (the stem takes the raw uint8 / int32 / float histogram; later stages take the
+        previous stage's h, NCHW-logical over channels-last memory).  Returns NHWC fp32."""
+        pad = self.conv.padding[0] if isinstance(self.conv.padding, tuple) else int(self.conv.padding)
+        if x.is_contiguous() and not (x.shape[1] == 1 or x.shape[2:] == (1, 1)):
+            xp = ops.pad_input(x, pad) if x.shape[1] % 4 == 0 else ops.pad_nhwc(x.float().permute(0, 2, 3, 1), pad)
+        else:
+            xp = ops.pad_nhwc(x.permute(0, 2, 3, 1), pad)
+        y = F.conv2d(xp.permute(0, 3, 1, 2), self._weight_cl(), None, stride=self.conv.stride)   # NHWC in, NHWC out
+        y = y.permute(0, 2, 3, 1)
+        return ops.layernorm(y, self.norm.weight, self.norm.bias, self.norm.eps)
 
     @staticmethod
     def output_is_normed():
@@ -118,7 +134,40 @@ class DWSConvLSTM2d(nn.Module):
         self.conv_only_hidden = dws_conv_only_hidden
         self.cell_update_dropout = nn.Dropout(p=cell_update_dropout)
 
+    def _weights(self, C: int):
+        """(W_x [4C,C,1,1], W_full [4C,2C,1,1]) channels-last, cached: with a zero initial state only the
+        x-half of the 1x1 conv contributes (half the GEMM, no concat)."""
+        w = self.conv1x1.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_wkey", None) != key:
+            wd = w.detach()
+            self._wx = wd[:, :C].contiguous(memory_format=torch.channels_last)
+            self._wfull = wd.contiguous(memory_format=torch.channels_last)
+            self._wkey = key
+        return self._wx, self._wfull
+
     def forward(self, x: Tensor, h_and_c_previous: LstmState = None) -> Tuple[Tensor, Tensor]:
+        """x: [N,C,H,W] (any memory format; channels-last makes every step copy-free).  Returns
+        (h, c) as NCHW-logical tensors over channels-last memory."""
+        if isinstance(self.conv3x3_dws, nn.Identity) and not (torch.is_grad_enabled() and self.conv1x1.weight.requires_grad) \
+                and not self.training:
+            C = self.dim
+            wx, wfull = self._weights(C)
+            x = x.contiguous(memory_format=torch.channels_last)
+            if h_and_c_previous is None:
+                mix = F.conv2d(x, wx, self.conv1x1.bias)
+                c_prev = None
+            else:
+                h_tm1, c_tm1 = h_and_c_previous
+                mix = F.conv2d(torch.cat((x, h_tm1.contiguous(memory_format=torch.channels_last)), dim=1), wfull,
+                               self.conv1x1.bias)
+                c_prev = c_tm1.permute(0, 2, 3, 1)
+            h, c = ops.lstm_gates(mix.permute(0, 2, 3, 1), c_prev)          # NHWC
+            return h.permute(0, 3, 1, 2), c.permute(0, 3, 1, 2)
+        return self._forward_reference(x, h_and_c_previous)
+
+    def _forward_reference(self, x: Tensor, h_and_c_previous: LstmState = None) -> Tuple[Tensor, Tensor]:
+        """Op-by-op form (depth-wise conv variants, training with autograd)."""
         if h_and_c_previous is None:
             h_and_c_previous = (torch.zeros_like(x), torch.zeros_like(x))
         h_tm1, c_tm1 = h_and_c_previous
@@ -260,8 +309,7 @@ class RNNDetector(BaseDetector):
         states: List[Tuple[Tensor, Tensor]] = []
         output: Dict[int, Tensor] = {}
         r = non_zero_ratio(x)
-        x = x.float()
-        P = []
+        P = []            # (the stem casts its own input: no separate x.float() pass, ref sast_rnn.py:153)
         for stage_idx, stage in enumerate(self.stages):
             x, state, p = stage(x, prev_states[stage_idx], token_mask if stage_idx == 0 else None, r[:, stage_idx])
             states.append(state)

@@ -8,6 +8,8 @@
 // padding (SAST.py:223-226) has no counterpart: the only mask is "same window".
 //
 // CTA = 128 threads, thread t <-> tile row t <-> TMEM lane t.  Thread 0 issues TMA and MMA.
+// 128 TMEM columns and 41 KB of shared memory per CTA -> 4 CTAs per SM hide each other's
+// load -> MMA -> softmax -> MMA latency chain.
 //   Q,K,V tiles [128 x 32] bf16: TMA boxes out of the qkv buffer ([rows, 3C], head-major
 //   [h][q,k,v][32]) in SWIZZLE_64B; Q,K are K-major operands, V is the MN-major B operand of PV.
 //   P [128 x 128] bf16 is written by the softmax threads in the SWIZZLE_128B K-major layout.
@@ -16,7 +18,7 @@
 
 namespace sast {
 
-constexpr uint32_t AT_TMEM_COLS = 256;     // S: columns [0,128), O: columns [128,160)
+constexpr uint32_t AT_TMEM_COLS = 128;     // S: columns [0,128); O re-uses columns [0,32) once S has been consumed
 constexpr int AT_TILE = 8192;              // one 128 x 32 bf16 operand tile
 
 struct AttnSmem {
@@ -60,11 +62,11 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   const int t = threadIdx.x, warp = t >> 5;
 
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = base;
-  uint8_t* sK = base + AT_TILE;
-  uint8_t* sV = base + 2 * AT_TILE;
-  uint8_t* sP = base + 4 * AT_TILE;                        // 32 KB, 1024-aligned
-  AttnSmem* sm = reinterpret_cast<AttnSmem*>(base + 8 * AT_TILE);
+  uint8_t* sQ = base;                                      // Q, K are dead once S = Q K^T has completed:
+  uint8_t* sK = base + AT_TILE;                            // P (32 KB) is written over them
+  uint8_t* sP = base;
+  uint8_t* sV = base + 4 * AT_TILE;
+  AttnSmem* sm = reinterpret_cast<AttnSmem*>(base + 5 * AT_TILE);
 
   if (t == 0) {
     ptx::tma_prefetch_desc(&map_qkv);
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_s = sm->tmem_base;
-  const uint32_t tmem_o = tmem_s + 128;
+  const uint32_t tmem_o = tmem_s;
   const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
 
   // key range of this row: the compacted rows of its own window
@@ -287,7 +289,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   int rc = make_tmap_bf16_box(&mq, qkv, max_rows, 3 * C, 3 * C, 32, 128, 64);
   if (rc) return rc;
   static bool attr_done = false;
-  const size_t smem = 1024 + 8 * AT_TILE + sizeof(AttnSmem);
+  const size_t smem = 1024 + 5 * AT_TILE + sizeof(AttnSmem);
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -8,7 +8,8 @@
 //   warp 0   TMA producer   (one lane; ring of kStages {A 128x64, W BNx64} bf16 tiles)
 //   warp 1   TMEM allocator + MMA issuer (one lane; tcgen05.mma M=128,N=BN,K=16, 4 per k-block)
 //   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns per warp (warp w owns TMEM lanes
-//            32*(w%4)..+31 = output rows), bias / LayerScale / residual / GLU / scatter in registers.
+//            32*(w%4)..+31 = output rows), transposed through shared memory so that bias /
+//            LayerScale / residual / GLU / scatter run with coalesced 128-byte row segments.
 // M (= number of selected tokens) is read from device memory; CTAs past it exit at once.
 // K tails (K % 64 != 0) rely on TMA zero fill and issue only the k-steps that hold data.
 #include "layer.cuh"
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   const uint32_t a_bytes = TC_BM * TC_BK * 2, w_bytes = (uint32_t)BN * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + w_bytes;
   TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)stages * stage_bytes);
+  float* stage_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm) + 128);   // 4 x [32][33] fp32 epilogue tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + TC_BK - 1) / TC_BK;
@@ -103,59 +105,56 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     }
   } else {
     // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+    // tcgen05.ld gives every lane 32 consecutive columns of ITS row; global memory wants the
+    // opposite (a warp instruction touching whole 128-byte row segments).  Each warp therefore
+    // transposes its 32x32 chunk through a padded shared-memory tile and does all global I/O
+    // (residual loads, fp32 / bf16 / scattered stores) with 8 lanes x 16 bytes per row.
     const int quarter = warp & 3;
-    const int row = m0 + quarter * 32 + lane;
+    float* stage = stage_all + (warp - 2) * (32 * 33);
+    const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
     ptx::mbar_wait(&sm->tmem_full, 0);
     ptx::tc_fence_after();
-    const bool row_ok = row < M;
-    long long pix = 0;
-    if (EPI == EPI_SCATTER && row_ok) pix = ep.row_pix[row];
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t raw[32];
       ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, raw);
       ptx::tmem_ld_wait();
-      if (!row_ok) continue;
-      const int n = n0 + c0;
-      float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-      if (bias) {
+      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
+      __syncwarp();
+      const int n = n0 + c0 + c4;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (bias) b4 = *reinterpret_cast<const float4*>(bias + n);
+      if ((EPI == EPI_RESID || EPI == EPI_SCATTER) && ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias + n + j);
-          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-        }
-      }
-      if (EPI == EPI_GLU) {
-        float o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
-        __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n / 2;
-        store_bf16x8(dst, o);
-        store_bf16x8(dst + 8, o + 8);
-      } else {
-        if (EPI == EPI_RESID || EPI == EPI_SCATTER) {
-          const float* rp = ep.resid + (size_t)row * ep.ldr + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n + j);
-            v[j] = r4.x + g4.x * v[j]; v[j + 1] = r4.y + g4.y * v[j + 1];
-            v[j + 2] = r4.z + g4.z * v[j + 2]; v[j + 3] = r4.w + g4.w * v[j + 3];
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + r_sub;
+        const int row = m0 + quarter * 32 + r;
+        if (row >= M) continue;
+        const float* sp = stage + r * 33 + c4;
+        float v0 = sp[0] + b4.x, v1 = sp[1] + b4.y, v2 = sp[2] + b4.z, v3 = sp[3] + b4.w;
+        if (EPI == EPI_GLU) {
+          const __nv_bfloat162 o = __floats2bfloat162_rn(v0 * gelu_erf(v1), v2 * gelu_erf(v3));
+          *reinterpret_cast<__nv_bfloat162*>(ep.out_bf16 + (size_t)row * ep.ldo + (n >> 1)) = o;
+        } else {
+          if (EPI == EPI_RESID || EPI == EPI_SCATTER) {
+            const float4 r4 = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n);
+            v0 = r4.x + g4.x * v0; v1 = r4.y + g4.y * v1; v2 = r4.z + g4.z * v2; v3 = r4.w + g4.w * v3;
+          }
+          if (ep.out_f32) {
+            float* dst = EPI == EPI_SCATTER ? ep.out_f32 + (long long)ep.row_pix[row] * ep.C + n
+                                            : ep.out_f32 + (size_t)row * ep.ldo + n;
+            *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
+          }
+          if (EPI != EPI_SCATTER && ep.out_bf16) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ldo + n) = pk;
           }
         }
-        if (ep.out_f32) {
-          float* dst = EPI == EPI_SCATTER ? ep.out_f32 + pix * ep.C + n : ep.out_f32 + (size_t)row * ep.ldo + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        if (EPI != EPI_SCATTER && ep.out_bf16) {
-          __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, v + j);
-        }
       }
+      __syncwarp();
     }
   }
   ptx::tc_fence_before();
@@ -210,7 +209,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* 
                      long long max_rows, int m_static, const EpiParams& ep, cudaStream_t st) {
   const int nkb = (K + TC_BK - 1) / TC_BK;
   const int stages = nkb < TC_MAX_STAGES ? nkb : TC_MAX_STAGES;
-  const size_t smem = 1024 + (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + sizeof(TcSmem);
+  const size_t smem = 1024 + (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 128 + 4 * 32 * 33 * sizeof(float);
   static bool attr_done = false;   // per-instantiation; the attribute is idempotent
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -201,11 +201,14 @@ def select_from_probs(win_prob: Tensor, tok_prob: Tensor, H: int, W: int, p0: in
                         win_prob=win_prob, tok_prob=tok_prob)[0]
 
 
-def select_from_flags(win_flag: Tensor, tok_flag: Tensor, B: int, H: int, W: int, p0: int, p1: int) -> Tensor:
+def select_from_flags(win_flag: Tensor, tok_flag: Tensor, B: int, H: int, W: int, p0: int, p1: int,
+                      flavor: int = L.FLAT) -> Tensor:
+    """Selection from explicit keep flags (partitioned order).  `flavor` fixes how compacted rows map
+    back to NHWC pixels (row_pix): WINDOW / GRID for a map, FLAT for an already partitioned tensor."""
     L.require_cuda(win_flag, "win_flag")
     win_flag = win_flag.to(torch.uint8).contiguous()
     tok_flag = tok_flag.to(torch.uint8).contiguous()
-    return _select_impl(L.SEL_FLAGS, B, H, W, p0, p1, L.FLAT, 0.0, 0.0, win_flag.device, win_flag=win_flag,
+    return _select_impl(L.SEL_FLAGS, B, H, W, p0, p1, flavor, 0.0, 0.0, win_flag.device, win_flag=win_flag,
                         tok_flag=tok_flag)[0]
 
 
@@ -290,7 +293,7 @@ class Selection:
 
 
 def selection_from_lists(index_window: Tensor, asy_index: Tensor, B: int, H: int, W: int, p0: int, p1: int,
-                         given: Optional[Sequence[Tensor]] = None) -> Selection:
+                         given: Optional[Sequence[Tensor]] = None, flavor: int = L.FLAT) -> Selection:
     """Build a device selection from reference-style index tensors (MS_WSA.forward called with
     explicit indices, SAST.py:199-201)."""
     T = p0 * p1
@@ -302,7 +305,7 @@ def selection_from_lists(index_window: Tensor, asy_index: Tensor, B: int, H: int
     if asy_index.numel():
         a = asy_index.long()
         tf[index_window.long()[a // T] * T + a % T] = 1
-    pool = select_from_flags(wf, tf, B, H, W, p0, p1)
+    pool = select_from_flags(wf, tf, B, H, W, p0, p1, flavor)
     return Selection(pool, B, H, W, p0, p1, given=given)
 
 
@@ -396,3 +399,91 @@ def gemm_bf16(A: Tensor, Wt: Tensor, bias: Optional[Tensor] = None, out_bf16: bo
     L.check(L.lib().sast_gemm_bf16(A.data_ptr(), Wt.data_ptr(), L.ptr(bias), D.data_ptr(), int(out_bf16), M, N, K,
                                    L.stream_ptr(A.device)), "sast_gemm_bf16")
     return D
+
+
+# --------------------------------------------------------------------------------------------
+# glue of the dense callers around the block (stem input, downsample padding, LayerNorm, LSTM gates)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("sast::pad_input", mutates_args=())
+def pad_input(x: Tensor, pad: int) -> Tensor:
+    """[B,Cin,H,W] NCHW (uint8 / int32 / float32) -> fp32 NHWC [B,H+2p,W+2p,Cin], replicate padding."""
+    L.require_cuda(x, "x")
+    if x.dtype == torch.uint8:
+        dt = L.U8
+    elif x.dtype == torch.int32:
+        dt = L.I32
+    elif x.dtype == torch.float32:
+        dt = L.F32
+    else:
+        x = x.to(torch.float32 if x.is_floating_point() else torch.int32)
+        dt = L.F32 if x.is_floating_point() else L.I32
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    out = torch.empty(B, H + 2 * pad, W + 2 * pad, Cin, device=x.device, dtype=torch.float32)
+    L.check(L.lib().sast_pad_input(x.data_ptr(), dt, B, Cin, H, W, pad, out.data_ptr(), L.stream_ptr(x.device)),
+            "sast_pad_input")
+    return out
+
+
+@pad_input.register_fake
+def _(x, pad):
+    B, Cin, H, W = x.shape
+    return x.new_empty(B, H + 2 * pad, W + 2 * pad, Cin, dtype=torch.float32)
+
+
+@torch.library.custom_op("sast::pad_nhwc", mutates_args=())
+def pad_nhwc(x: Tensor, pad: int) -> Tensor:
+    """fp32 [B,H,W,C] (any strides with contiguous channels) -> dense replicate-padded [B,H+2p,W+2p,C]."""
+    L.require_cuda(x, "x")
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.stride(3) != 1 or any(s % 4 for s in x.stride()[:3]):
+        x = x.contiguous()
+    B, H, W, Cc = x.shape
+    out = torch.empty(B, H + 2 * pad, W + 2 * pad, Cc, device=x.device, dtype=torch.float32)
+    L.check(L.lib().sast_pad_nhwc(x.data_ptr(), B, H, W, Cc, pad, x.stride(0), x.stride(1), x.stride(2),
+                                  out.data_ptr(), L.stream_ptr(x.device)), "sast_pad_nhwc")
+    return out
+
+
+@pad_nhwc.register_fake
+def _(x, pad):
+    B, H, W, Cc = x.shape
+    return x.new_empty(B, H + 2 * pad, W + 2 * pad, Cc, dtype=torch.float32)
+
+
+@torch.library.custom_op("sast::layernorm", mutates_args=())
+def layernorm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps: float) -> Tensor:
+    x = _f32c(x, "x")
+    Cc = x.shape[-1]
+    out = torch.empty_like(x)
+    L.check(L.lib().sast_layernorm(x.data_ptr(), L.ptr(None if weight is None else _f32c(weight, "weight")),
+                                   L.ptr(None if bias is None else _f32c(bias, "bias")), float(eps),
+                                   x.numel() // Cc, Cc, out.data_ptr(), L.stream_ptr(x.device)), "sast_layernorm")
+    return out
+
+
+@layernorm.register_fake
+def _(x, weight, bias, eps):
+    return torch.empty_like(x, dtype=torch.float32)
+
+
+@torch.library.custom_op("sast::lstm_gates", mutates_args=())
+def lstm_gates(mix: Tensor, c_prev: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """mix [..., 4C] channels-last, c_prev [..., C] or None -> (h, c) [..., C]."""
+    mix = _f32c(mix, "mix")
+    Cc = mix.shape[-1] // 4
+    shape = mix.shape[:-1] + (Cc,)
+    if c_prev is not None:
+        c_prev = _f32c(c_prev, "c_prev")
+    h = torch.empty(shape, device=mix.device, dtype=torch.float32)
+    c = torch.empty(shape, device=mix.device, dtype=torch.float32)
+    L.check(L.lib().sast_lstm_gates(mix.data_ptr(), L.ptr(c_prev), mix.numel() // (4 * Cc), Cc, h.data_ptr(),
+                                    c.data_ptr(), L.stream_ptr(mix.device)), "sast_lstm_gates")
+    return h, c
+
+
+@lstm_gates.register_fake
+def _(mix, c_prev):
+    shape = mix.shape[:-1] + (mix.shape[-1] // 4,)
+    return mix.new_empty(shape, dtype=torch.float32), mix.new_empty(shape, dtype=torch.float32)

@@ -317,11 +317,11 @@ class SAST_block(nn.Module):
             return pos_emb.table(x)
         return pos_emb(x) if callable(pos_emb) else pos_emb
 
-    def _as_selection(self, lst, B, H, W) -> ops.Selection:
+    def _as_selection(self, lst, B, H, W, flavor) -> ops.Selection:
         if isinstance(lst, ops.Selection):
             return lst
         iw, it, pad, asy, K = lst
-        return ops.selection_from_lists(iw, asy, B, H, W, *self.partition_size, given=lst)
+        return ops.selection_from_lists(iw, asy, B, H, W, *self.partition_size, given=lst, flavor=flavor)
 
     def _partition_attn(self, x: Tensor, pos_emb, r: Tensor, index_list):
         B, H, W, C = x.shape
@@ -342,8 +342,8 @@ class SAST_block(nn.Module):
             sel1.tok_score, sel2.tok_score = tok, tok
         else:
             xw = ops.add_pos(x, pos)
-            sel1 = self._as_selection(index_list[0], B, H, W)
-            sel2 = self._as_selection(index_list[1], B, H, W)
+            sel1 = self._as_selection(index_list[0], B, H, W, L.WINDOW)
+            sel2 = self._as_selection(index_list[1], B, H, W, L.GRID)
         x1 = self.win_attn.run(xw, sel1, L.WINDOW, self.enable_CB)
         x2 = self.grid_attn.run(x1, sel2, L.GRID, self.enable_CB)
         count = LazyCount(sel1.counts[1] // B + sel2.counts[1] // B)
