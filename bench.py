@@ -191,7 +191,7 @@ def run_ours(args, workload):
         def fwd(x):
             with torch.no_grad():
                 f, s, p = net(x, None)
-            return f, s, torch.stack([q._t for q in p])
+            return f, s, torch.stack([t.reshape(()) for q in p for t, _ in q.terms])
         fwd(dev_in[0])
         launches_per_step = lib.sast_launch_count() - launches0
         runner = None
@@ -224,7 +224,8 @@ def run_ours(args, workload):
     barrier()
 
     # ---- end to end: pinned host uint8 -> device, forward, counts back to the host, every step ----
-    counts_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+    n_counts = 8
+    counts_host = torch.zeros(n_counts, dtype=torch.int64).pin_memory()
     x_stage = torch.empty_like(dev_in[0])
 
     def step_e2e(i):
@@ -244,7 +245,8 @@ def run_ours(args, workload):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_res, t_e2e = tt.tolist()
     frames = B * world * args.steps
-    counts = [int(c) for c in counts_host.tolist()]
+    raw = counts_host.tolist()      # selected tokens per SAST layer (2 per stage), whole batch
+    counts = [int(raw[2 * i]) // B + int(raw[2 * i + 1]) // B for i in range(4)]
 
     if rank == 0:
         from roofline import roofline_block            # measured live, same process

@@ -199,11 +199,11 @@ int sast_scatter(const sast_geom* g, int32_t flavor, const float* rows, const sa
  * Memory-bound glue of the dense callers on either side of the block.
  * sast_pad_input : [B,Cin,H,W] NCHW of `dtype` (SAST_U8/I32/F32) -> fp32 NHWC [B,H+2p,W+2p,Cin]
  *                  with replicate padding (ref: sast_rnn.py:153 x.float() + ops.py:77-89 conv
- *                  padding_mode='replicate').  Cin % 4 == 0.
+ *                  padding_mode='replicate').
  * sast_pad_nhwc  : fp32 NHWC map with element strides (stride_b, stride_y, stride_x; channels
  *                  contiguous) -> dense replicate-padded NHWC.
  * sast_layernorm : LayerNorm over the last dim of [P,C] fp32 (ref: ops.py:85,90); weight/bias may be NULL.
- * sast_lstm_gates: mix [P,4C] (1x1-conv output, channels [f,i,o | g]), c_prev [P,C] or NULL (zero state)
+ * sast_lstm_gates: mix [P,4C] (1x1-conv output, channels [f,i,o | g]) + bias [4C] (may be NULL), c_prev [P,C] or NULL (zero state)
  *                  -> h [P,C], c [P,C]   (ref: models/layers/rnn.py:58-69).
  */
 int sast_pad_input(const void* x, int32_t dtype, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t pad,
@@ -212,8 +212,8 @@ int sast_pad_nhwc(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, in
                   int64_t stride_y, int64_t stride_x, float* out, void* stream);
 int sast_layernorm(const float* x, const float* weight, const float* bias, float eps, int64_t P, int32_t C,
                    float* out, void* stream);
-int sast_lstm_gates(const float* mix, const float* c_prev, int64_t P, int32_t C, float* h_out, float* c_out,
-                    void* stream);
+int sast_lstm_gates(const float* mix, const float* bias, const float* c_prev, int64_t P, int32_t C, float* h_out,
+                    float* c_out, void* stream);
 
 /* D[M,N] = A[M,K] W[N,K]^T (+bias): bf16 in, fp32 accumulate on tcgen05, fp32 or bf16 out.
  * Exposed for unit tests of the tensor-core path. */

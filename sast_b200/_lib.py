@@ -87,7 +87,7 @@ def _load():
         "sast_pad_input": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
         "sast_pad_nhwc": (C.c_int, [vp, i32, i32, i32, i32, i32, i64, i64, i64, vp, vp]),
         "sast_layernorm": (C.c_int, [vp, vp, vp, f32, i64, i32, vp, vp]),
-        "sast_lstm_gates": (C.c_int, [vp, vp, i64, i32, vp, vp, vp]),
+        "sast_lstm_gates": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch

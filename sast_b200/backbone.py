@@ -100,7 +100,7 @@ class ConvDownsampling_Cf2Cl(nn.Module):
         previous stage's h, NCHW-logical over channels-last memory).  Returns NHWC fp32."""
         pad = self.conv.padding[0] if isinstance(self.conv.padding, tuple) else int(self.conv.padding)
         if x.is_contiguous() and not (x.shape[1] == 1 or x.shape[2:] == (1, 1)):
-            xp = ops.pad_input(x, pad) if x.shape[1] % 4 == 0 else ops.pad_nhwc(x.float().permute(0, 2, 3, 1), pad)
+            xp = ops.pad_input(x, pad)
         else:
             xp = ops.pad_nhwc(x.permute(0, 2, 3, 1), pad)
         y = F.conv2d(xp.permute(0, 3, 1, 2), self._weight_cl(), None, stride=self.conv.stride)   # NHWC in, NHWC out
@@ -155,14 +155,13 @@ class DWSConvLSTM2d(nn.Module):
             wx, wfull = self._weights(C)
             x = x.contiguous(memory_format=torch.channels_last)
             if h_and_c_previous is None:
-                mix = F.conv2d(x, wx, self.conv1x1.bias)
+                mix = F.conv2d(x, wx, None)
                 c_prev = None
             else:
                 h_tm1, c_tm1 = h_and_c_previous
-                mix = F.conv2d(torch.cat((x, h_tm1.contiguous(memory_format=torch.channels_last)), dim=1), wfull,
-                               self.conv1x1.bias)
+                mix = F.conv2d(torch.cat((x, h_tm1.contiguous(memory_format=torch.channels_last)), dim=1), wfull, None)
                 c_prev = c_tm1.permute(0, 2, 3, 1)
-            h, c = ops.lstm_gates(mix.permute(0, 2, 3, 1), c_prev)          # NHWC
+            h, c = ops.lstm_gates(mix.permute(0, 2, 3, 1), self.conv1x1.bias, c_prev)          # NHWC; bias folded in
             return h.permute(0, 3, 1, 2), c.permute(0, 3, 1, 2)
         return self._forward_reference(x, h_and_c_previous)
 

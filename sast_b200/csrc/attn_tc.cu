@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     ptx::mbar_init(&sm->bar_o, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 0) ptx::tmem_alloc<AT_TMEM_COLS>(&sm->tmem_base);
+  if (warp == 0) ptx::tmem_alloc(&sm->tmem_base, AT_TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     __syncthreads();          // everyone is done with S, O and the smem tiles before the next head reuses them
     ptx::tc_fence_after();
   }
-  if (warp == 0) ptx::tmem_dealloc<AT_TMEM_COLS>(tmem_s);
+  if (warp == 0) ptx::tmem_dealloc(tmem_s, AT_TMEM_COLS);
 }
 
 // ---- CUDA-core variant (debug / A-B knob SAST_B200_ATTN=simt): one thread per query row ----

@@ -18,7 +18,6 @@
 namespace sast {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192, TC_MAX_STAGES = 4;
-constexpr uint32_t TC_TMEM_COLS = 128;   // >= max BN, power of two
 
 struct TcSmem {            // lives after the operand ring (which needs 1024-byte alignment)
   uint64_t full[TC_MAX_STAGES];
@@ -64,7 +63,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     ptx::mbar_init(&sm->tmem_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<TC_TMEM_COLS>(&sm->tmem_base);
+  const uint32_t tmem_cols = BN < 32 ? 32u : (uint32_t)BN;      // BN is 32, 64 or 128: as many CTAs per SM as TMEM allows
+  if (warp == 1) ptx::tmem_alloc(&sm->tmem_base, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -105,47 +105,40 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     }
   } else {
     // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
-    // tcgen05.ld gives every lane 32 consecutive columns of ITS row; global memory wants the
-    // opposite (a warp instruction touching whole 128-byte row segments).  Each warp therefore
-    // transposes its 32x32 chunk through a padded shared-memory tile and does all global I/O
-    // (residual loads, fp32 / bf16 / scattered stores) with 8 lanes x 16 bytes per row.
     const int quarter = warp & 3;
-    float* stage = stage_all + (warp - 2) * (32 * 33);
-    const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
     ptx::mbar_wait(&sm->tmem_full, 0);
     ptx::tc_fence_after();
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t raw[32];
-      ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, raw);
-      ptx::tmem_ld_wait();
+    if constexpr (EPI == EPI_STORE || EPI == EPI_RESID) {
+      // tcgen05.ld gives every lane 32 consecutive columns of ITS row; wide row outputs want the
+      // opposite (a warp instruction touching whole 128-byte row segments).  Each warp transposes
+      // its 32x32 chunk through a padded shared-memory tile and does the global I/O (residual
+      // loads, fp32 / bf16 stores) with 8 lanes x 16 bytes per row.
+      float* stage = stage_all + (warp - 2) * (32 * 33);
+      const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, raw);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
-      __syncwarp();
-      const int n = n0 + c0 + c4;
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (bias) b4 = *reinterpret_cast<const float4*>(bias + n);
-      if ((EPI == EPI_RESID || EPI == EPI_SCATTER) && ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n);
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
+        __syncwarp();
+        const int n = n0 + c0 + c4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (bias) b4 = *reinterpret_cast<const float4*>(bias + n);
+        if (EPI == EPI_RESID && ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n);
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + r_sub;
-        const int row = m0 + quarter * 32 + r;
-        if (row >= M) continue;
-        const float* sp = stage + r * 33 + c4;
-        float v0 = sp[0] + b4.x, v1 = sp[1] + b4.y, v2 = sp[2] + b4.z, v3 = sp[3] + b4.w;
-        if (EPI == EPI_GLU) {
-          const __nv_bfloat162 o = __floats2bfloat162_rn(v0 * gelu_erf(v1), v2 * gelu_erf(v3));
-          *reinterpret_cast<__nv_bfloat162*>(ep.out_bf16 + (size_t)row * ep.ldo + (n >> 1)) = o;
-        } else {
-          if (EPI == EPI_RESID || EPI == EPI_SCATTER) {
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + r_sub;
+          const int row = m0 + quarter * 32 + r;
+          if (row >= M) continue;
+          const float* sp = stage + r * 33 + c4;
+          float v0 = sp[0] + b4.x, v1 = sp[1] + b4.y, v2 = sp[2] + b4.z, v3 = sp[3] + b4.w;
+          if (EPI == EPI_RESID) {
             const float4 r4 = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n);
             v0 = r4.x + g4.x * v0; v1 = r4.y + g4.y * v1; v2 = r4.z + g4.z * v2; v3 = r4.w + g4.w * v3;
           }
-          if (ep.out_f32) {
-            float* dst = EPI == EPI_SCATTER ? ep.out_f32 + (long long)ep.row_pix[row] * ep.C + n
-                                            : ep.out_f32 + (size_t)row * ep.ldo + n;
-            *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
-          }
-          if (EPI != EPI_SCATTER && ep.out_bf16) {
+          if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + n) = make_float4(v0, v1, v2, v3);
+          if (ep.out_bf16) {
             const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
             uint2 pk;
             pk.x = *reinterpret_cast<const uint32_t*>(&lo);
@@ -153,15 +146,61 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
             *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ldo + n) = pk;
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
+    } else {
+      // GLU (narrow bf16 rows) and SCATTER (rows land on scattered pixels): every lane finishes its own row
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < M;
+      long long pix = 0;
+      if (EPI == EPI_SCATTER && row_ok) pix = ep.row_pix[row];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, raw);
+        const int n = n0 + c0;
+        float4 r4[8];
+        if (EPI == EPI_SCATTER && row_ok) {      // residual loads in flight while the TMEM load completes
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n + 4 * j);
+        }
+        ptx::tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + n + j);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+        if (EPI == EPI_GLU) {
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+          __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n / 2;
+          store_bf16x8(dst, o);
+          store_bf16x8(dst + 8, o + 8);
+        } else {
+          float* dst = ep.out_f32 + pix * ep.C + n;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n + 4 * j);
+            *reinterpret_cast<float4*>(dst + 4 * j) =
+                make_float4(r4[j].x + g4.x * v[4 * j], r4[j].y + g4.y * v[4 * j + 1], r4[j].z + g4.z * v[4 * j + 2],
+                            r4[j].w + g4.w * v[4 * j + 3]);
+          }
+        }
+      }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<TC_TMEM_COLS>(tmem_d);
+    ptx::tmem_dealloc(tmem_d, tmem_cols);
   }
 }
 
@@ -209,7 +248,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* 
                      long long max_rows, int m_static, const EpiParams& ep, cudaStream_t st) {
   const int nkb = (K + TC_BK - 1) / TC_BK;
   const int stages = nkb < TC_MAX_STAGES ? nkb : TC_MAX_STAGES;
-  const size_t smem = 1024 + (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 128 + 4 * 32 * 33 * sizeof(float);
+  const bool staged = EPI == EPI_STORE || EPI == EPI_RESID;
+  const size_t smem = 1024 + (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 128 + (staged ? 4 * 32 * 33 * sizeof(float) : 0);
   static bool attr_done = false;   // per-instantiation; the attribute is idempotent
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

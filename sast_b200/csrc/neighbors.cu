@@ -11,26 +11,31 @@
 
 namespace sast {
 
+// CTA = one padded output row segment of 64 pixels: the Cin input planes are read with coalesced
+// row loads into shared memory ([Cin][64]), then written out pixel-major (Cin contiguous floats per
+// pixel = dense 16-byte stores across the warp).
 template <typename T>
 __global__ void __launch_bounds__(256) pad_input_kernel(const T* __restrict__ x, int B, int Cin, int H, int W, int pad,
                                                         float* __restrict__ out) {
-  // one thread per output pixel column of 4 px: reads Cin planes (coalesced along W), writes Cin-contiguous NHWC
+  extern __shared__ float tile[];                 // [Cin][65]
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
-  const long long total = (long long)B * Ho * Wo;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int xo = (int)(i % Wo);
-    const int yo = (int)((i / Wo) % Ho);
-    const int b = (int)(i / ((long long)Wo * Ho));
-    const int xs = min(max(xo - pad, 0), W - 1), ys = min(max(yo - pad, 0), H - 1);
-    const T* src = x + ((size_t)b * Cin * H + ys) * W + xs;
-    float* dst = out + i * Cin;
-    for (int c = 0; c < Cin; c += 4) {
-      float v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = (c + k < Cin) ? (float)src[(size_t)(c + k) * H * W] : 0.f;
-      if (c + 3 < Cin) *reinterpret_cast<float4*>(dst + c) = make_float4(v[0], v[1], v[2], v[3]);
-      else for (int k = 0; c + k < Cin; ++k) dst[c + k] = v[k];
-    }
+  const int segs = (Wo + 63) / 64;
+  const int seg = blockIdx.x % segs;
+  const int yo = (blockIdx.x / segs) % Ho;
+  const int b = blockIdx.x / (segs * Ho);
+  const int ys = min(max(yo - pad, 0), H - 1);
+  const int x0 = seg * 64;
+  for (int i = threadIdx.x; i < Cin * 64; i += blockDim.x) {
+    const int c = i >> 6, dx = i & 63;
+    const int xs = min(max(x0 + dx - pad, 0), W - 1);
+    tile[c * 65 + dx] = (float)x[((size_t)(b * Cin + c) * H + ys) * W + xs];
+  }
+  __syncthreads();
+  const int npx = min(64, Wo - x0);
+  float* dst = out + ((size_t)(b * Ho + yo) * Wo + x0) * Cin;
+  for (int i = threadIdx.x; i < npx * Cin; i += blockDim.x) {
+    const int dx = i / Cin, c = i - dx * Cin;
+    dst[i] = tile[c * 65 + dx];
   }
 }
 
@@ -110,19 +115,27 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // mix [P,4C] = conv1x1([x, h_prev]) (+bias): channels [0,3C) -> sigmoid -> (forget, input, output); [3C,4C) -> tanh -> g
-__global__ void __launch_bounds__(256) lstm_gates_kernel(const float* __restrict__ mix, const float* __restrict__ c_prev,
-                                                         long long P, int C, float* __restrict__ h_out,
-                                                         float* __restrict__ c_out) {
+__global__ void __launch_bounds__(256) lstm_gates_kernel(const float* __restrict__ mix, const float* __restrict__ bias,
+                                                         const float* __restrict__ c_prev, long long P, int C,
+                                                         float* __restrict__ h_out, float* __restrict__ c_out) {
   const int c4n = C / 4;
   const long long total = P * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i / c4n;
     const int c = (int)(i % c4n) * 4;
     const float* m = mix + p * 4 * C + c;
-    const float4 f4 = *reinterpret_cast<const float4*>(m);
-    const float4 i4 = *reinterpret_cast<const float4*>(m + C);
-    const float4 o4 = *reinterpret_cast<const float4*>(m + 2 * C);
-    const float4 g4 = *reinterpret_cast<const float4*>(m + 3 * C);
+    float4 f4 = *reinterpret_cast<const float4*>(m);
+    float4 i4 = *reinterpret_cast<const float4*>(m + C);
+    float4 o4 = *reinterpret_cast<const float4*>(m + 2 * C);
+    float4 g4 = *reinterpret_cast<const float4*>(m + 3 * C);
+    if (bias) {   // the 1x1 conv's bias, folded in here instead of a separate pass over mix
+      const float4 bf = *reinterpret_cast<const float4*>(bias + c), bi = *reinterpret_cast<const float4*>(bias + C + c);
+      const float4 bo = *reinterpret_cast<const float4*>(bias + 2 * C + c), bg = *reinterpret_cast<const float4*>(bias + 3 * C + c);
+      f4.x += bf.x; f4.y += bf.y; f4.z += bf.z; f4.w += bf.w;
+      i4.x += bi.x; i4.y += bi.y; i4.z += bi.z; i4.w += bi.w;
+      o4.x += bo.x; o4.y += bo.y; o4.z += bo.z; o4.w += bo.w;
+      g4.x += bg.x; g4.y += bg.y; g4.z += bg.z; g4.w += bg.w;
+    }
     float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c_prev) c0 = *reinterpret_cast<const float4*>(c_prev + p * C + c);
     const float f[4] = {f4.x, f4.y, f4.z, f4.w}, ii[4] = {i4.x, i4.y, i4.z, i4.w}, o[4] = {o4.x, o4.y, o4.z, o4.w},
@@ -151,14 +164,14 @@ extern "C" int sast_pad_input(const void* x, int32_t dtype, int32_t B, int32_t C
   using namespace sast;
   SAST_CHECK_PTR(x); SAST_CHECK_PTR(out);
   if (B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || pad < 0) return SAST_E_SHAPE;
-  if (Cin % 4 != 0) return SAST_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad);
-  const unsigned grid = grid_for(total, 256);
+  const unsigned grid = (unsigned)((long long)B * (H + 2 * pad) * ((W + 2 * pad + 63) / 64));
+  const size_t smem = (size_t)Cin * 65 * sizeof(float);
+  if (smem > 48 * 1024) return SAST_E_UNSUPPORTED;
   switch (dtype) {
-    case SAST_U8: pad_input_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)x, B, Cin, H, W, pad, out); break;
-    case SAST_I32: pad_input_kernel<int32_t><<<grid, 256, 0, st>>>((const int32_t*)x, B, Cin, H, W, pad, out); break;
-    case SAST_F32: pad_input_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, Cin, H, W, pad, out); break;
+    case SAST_U8: pad_input_kernel<uint8_t><<<grid, 256, smem, st>>>((const uint8_t*)x, B, Cin, H, W, pad, out); break;
+    case SAST_I32: pad_input_kernel<int32_t><<<grid, 256, smem, st>>>((const int32_t*)x, B, Cin, H, W, pad, out); break;
+    case SAST_F32: pad_input_kernel<float><<<grid, 256, smem, st>>>((const float*)x, B, Cin, H, W, pad, out); break;
     default: return SAST_E_UNSUPPORTED;
   }
   SAST_LAUNCH_CHECK();
@@ -200,12 +213,12 @@ extern "C" int sast_layernorm(const float* x, const float* weight, const float* 
   return SAST_OK;
 }
 
-extern "C" int sast_lstm_gates(const float* mix, const float* c_prev, int64_t P, int32_t C, float* h_out, float* c_out,
-                               void* stream) {
+extern "C" int sast_lstm_gates(const float* mix, const float* bias, const float* c_prev, int64_t P, int32_t C, float* h_out,
+                               float* c_out, void* stream) {
   using namespace sast;
   SAST_CHECK_PTR(mix); SAST_CHECK_PTR(h_out); SAST_CHECK_PTR(c_out);
   if (P <= 0 || C <= 0 || C % 4 != 0) return SAST_E_SHAPE;
-  lstm_gates_kernel<<<grid_for(P * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(mix, c_prev, P, C, h_out, c_out);
+  lstm_gates_kernel<<<grid_for(P * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(mix, bias, c_prev, P, C, h_out, c_out);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

@@ -469,8 +469,8 @@ def _(x, weight, bias, eps):
 
 
 @torch.library.custom_op("sast::lstm_gates", mutates_args=())
-def lstm_gates(mix: Tensor, c_prev: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
-    """mix [..., 4C] channels-last, c_prev [..., C] or None -> (h, c) [..., C]."""
+def lstm_gates(mix: Tensor, bias: Optional[Tensor], c_prev: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """mix [..., 4C] channels-last (+ bias [4C]), c_prev [..., C] or None -> (h, c) [..., C]."""
     mix = _f32c(mix, "mix")
     Cc = mix.shape[-1] // 4
     shape = mix.shape[:-1] + (Cc,)
@@ -478,12 +478,13 @@ def lstm_gates(mix: Tensor, c_prev: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
         c_prev = _f32c(c_prev, "c_prev")
     h = torch.empty(shape, device=mix.device, dtype=torch.float32)
     c = torch.empty(shape, device=mix.device, dtype=torch.float32)
-    L.check(L.lib().sast_lstm_gates(mix.data_ptr(), L.ptr(c_prev), mix.numel() // (4 * Cc), Cc, h.data_ptr(),
+    L.check(L.lib().sast_lstm_gates(mix.data_ptr(), L.ptr(None if bias is None else _f32c(bias, "bias")), L.ptr(c_prev),
+                                    mix.numel() // (4 * Cc), Cc, h.data_ptr(),
                                     c.data_ptr(), L.stream_ptr(mix.device)), "sast_lstm_gates")
     return h, c
 
 
 @lstm_gates.register_fake
-def _(mix, c_prev):
+def _(mix, bias, c_prev):
     shape = mix.shape[:-1] + (mix.shape[-1] // 4,)
     return mix.new_empty(shape, dtype=torch.float32), mix.new_empty(shape, dtype=torch.float32)

@@ -40,8 +40,9 @@ class GraphedBackbone:
                 for (hs, cs), (h, c) in zip(self.states, states):
                     hs.copy_(h)
                     cs.copy_(c)
-            self.counts = torch.stack([p._t.reshape(()) if hasattr(p, "_t") else torch.as_tensor(p, device=self.x.device)
-                                       for p in P])
+            # raw selected-token totals of every SAST layer (static buffers of the graph); see counts()
+            self._terms = [p.terms for p in P]
+            self.raw_counts = torch.stack([t.reshape(()) for terms in self._terms for t, _ in terms])
         self.feats = feats
         self.new_states = states
 
@@ -57,4 +58,13 @@ class GraphedBackbone:
         if x is not None and x.data_ptr() != self.x.data_ptr():
             self.x.copy_(x, non_blocking=True)
         self.graph.replay()
-        return self.feats, self.new_states, self.counts
+        return self.feats, self.new_states, self.raw_counts
+
+    def counts(self, raw: Optional[Tensor] = None) -> List[int]:
+        """Per-stage selected-token counts (the reference's P list) from a raw_counts tensor (syncs)."""
+        vals = (self.raw_counts if raw is None else raw).tolist()
+        out, i = [], 0
+        for terms in self._terms:
+            out.append(sum(int(vals[i + j]) // d for j, (_, d) in enumerate(terms)))
+            i += len(terms)
+        return out

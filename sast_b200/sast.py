@@ -119,13 +119,18 @@ class LazyCount:
     The reference returns ``len(asy_index) // B`` (SAST.py:136,159), which costs a host sync
     per layer.  Callers only ever add these up and divide (modules/detection.py:158,196-199)."""
 
-    __slots__ = ("_t",)
+    __slots__ = ("terms",)
 
-    def __init__(self, t: Tensor):
-        self._t = t
+    def __init__(self, *terms):
+        """terms: (0-dim device int tensor, divisor) pairs; value = sum(t // divisor)."""
+        self.terms = tuple(t if isinstance(t, tuple) else (t, 1) for t in terms)
 
     def __int__(self):
-        return int(self._t.item())
+        if len(self.terms) == 1:
+            vals = [int(self.terms[0][0].item())]
+        else:
+            vals = torch.stack([t.reshape(()) for t, _ in self.terms]).tolist()     # one sync for all terms
+        return sum(int(v) // d for v, (_, d) in zip(vals, self.terms))
 
     __index__ = __int__
 
@@ -134,7 +139,7 @@ class LazyCount:
 
     def __add__(self, other):
         if isinstance(other, LazyCount):
-            return LazyCount(self._t + other._t)
+            return LazyCount(*(self.terms + other.terms))
         if isinstance(other, int) and other == 0:
             return self
         return int(self) + other
@@ -346,7 +351,7 @@ class SAST_block(nn.Module):
             sel2 = self._as_selection(index_list[1], B, H, W, L.GRID)
         x1 = self.win_attn.run(xw, sel1, L.WINDOW, self.enable_CB)
         x2 = self.grid_attn.run(x1, sel2, L.GRID, self.enable_CB)
-        count = LazyCount(sel1.counts[1] // B + sel2.counts[1] // B)
+        count = LazyCount((sel1.counts[1], B), (sel2.counts[1], B))
         return x2, count, [sel1, sel2]
 
     def forward(self, x: Tensor, pos_emb, r: Tensor, index_list):

@@ -121,7 +121,7 @@ def test_thresholds_are_fp32_cast():
 
 
 def test_lazy_count_behaves_like_int():
-    a, b = sast_b200.LazyCount(torch.tensor(7)), sast_b200.LazyCount(torch.tensor(5))
+    a, b = sast_b200.LazyCount(torch.tensor(7)), sast_b200.LazyCount((torch.tensor(11), 2))
     assert int(a) == 7 and a == 7 and a > b and a // 2 == 3 and a / 2 == 3.5 and a * 2 == 14
     P = 0
     P += a
