@@ -4,10 +4,11 @@
 // the canonical TN shape, so both operands are TMA-loaded as SWIZZLE_128B tiles and fed to
 // tcgen05.mma straight from shared memory; the fp32 accumulator lives in TMEM.
 //
-// CTA = one 128 x BN output tile, 6 warps:
-//   warp 0   TMA producer   (one lane; ring of kStages {A 128x64, W BNx64} bf16 tiles)
-//   warp 1   TMEM allocator + MMA issuer (one lane; tcgen05.mma M=128,N=BN,K=16, 4 per k-block)
-//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns per warp (warp w owns TMEM lanes
+// Persistent CTAs (one per SM), each walking 128 x BN output tiles, 10 warps:
+//   warp 0   TMA producer   (one lane; ring of 4 {A 128x64, W BNx64} bf16 stages, runs ahead across tiles)
+//   warp 1   TMEM allocator + MMA issuer (one lane; tcgen05.mma M=128,N=BN,K=16, 4 per k-block; two
+//            accumulators so the next tile is multiplied while the previous one is drained)
+//   warps 2-9 epilogue (two groups of 4, one per accumulator): tcgen05.ld 32 lanes x 32 columns per warp (warp w owns TMEM lanes
 //            32*(w%4)..+31 = output rows), transposed through shared memory so that bias /
 //            LayerScale / residual / GLU / scatter run with coalesced 128-byte row segments.
 // M (= number of selected tokens) is read from device memory; CTAs past it exit at once.
@@ -17,12 +18,15 @@
 
 namespace sast {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192, TC_MAX_STAGES = 4;
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_EPI_WARPS = 8;                       // two groups of 4 (one per TMEM accumulator)
+constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct TcSmem {            // lives after the operand ring (which needs 1024-byte alignment)
-  uint64_t full[TC_MAX_STAGES];
-  uint64_t empty[TC_MAX_STAGES];
-  uint64_t tmem_full;
+  uint64_t full[TC_STAGES];
+  uint64_t empty[TC_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
 
@@ -36,22 +40,26 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
   *reinterpret_cast<uint4*>(dst) = pk;
 }
 
+// Persistent: every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest, so CTAs that
+// run side by side share the A tile in L2).  The TMA ring runs ahead across tile boundaries, the MMA
+// warp ping-pongs between two TMEM accumulators, and the two epilogue groups (4 warps each, one per
+// accumulator) drain tile i while tile i+1 is being loaded and multiplied.
 template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                             const __grid_constant__ CUtensorMap map_w,
-                                                             const float* __restrict__ bias, int N, int K, int BN, int stages,
-                                                             const int* __restrict__ counts, int m_static, EpiParams ep) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_w,
+                                                                const float* __restrict__ bias, int N, int K, int BN,
+                                                                const int* __restrict__ counts, int m_static, EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int M = counts ? counts[1] : m_static;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
-  if (m0 >= M) return;
+  const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = N / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  if ((int)blockIdx.x >= total_tiles) return;
 
-  // carve shared memory: ring first (1024-aligned), bookkeeping after
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = TC_BM * TC_BK * 2, w_bytes = (uint32_t)BN * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + w_bytes;
-  TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)stages * stage_bytes);
-  float* stage_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm) + 128);   // 4 x [32][33] fp32 epilogue tiles
+  TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)TC_STAGES * stage_bytes);
+  float* stage_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm) + 128);   // 8 x [32][33] fp32 epilogue tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + TC_BK - 1) / TC_BK;
@@ -59,148 +67,176 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&map_a);
     ptx::tma_prefetch_desc(&map_w);
-    for (int s = 0; s < stages; ++s) { ptx::mbar_init(&sm->full[s], 1); ptx::mbar_init(&sm->empty[s], 1); }
-    ptx::mbar_init(&sm->tmem_full, 1);
+    for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&sm->full[s], 1); ptx::mbar_init(&sm->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&sm->tmem_full[a], 1); ptx::mbar_init(&sm->tmem_empty[a], 4); }
     ptx::fence_barrier_init();
   }
-  const uint32_t tmem_cols = BN < 32 ? 32u : (uint32_t)BN;      // BN is 32, 64 or 128: as many CTAs per SM as TMEM allows
+  const uint32_t tmem_cols = BN <= 16 ? 32u : (uint32_t)(2 * BN);   // two accumulators; BN in {32,64,128}
   if (warp == 1) ptx::tmem_alloc(&sm->tmem_base, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_d = sm->tmem_base;
+  const uint32_t tmem_base = sm->tmem_base;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t round = (uint32_t)(kb / stages);
-        ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
-        uint8_t* sa = base + (size_t)s * stage_bytes;
-        ptx::mbar_arrive_expect_tx(&sm->full[s], stage_bytes);
-        ptx::tma_load_2d(sa, &map_a, &sm->full[s], kb * TC_BK, m0);
-        ptx::tma_load_2d(sa + a_bytes, &map_w, &sm->full[s], kb * TC_BK, n0);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % TC_STAGES, round = it / TC_STAGES;
+          ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
+          uint8_t* sa = base + (size_t)s * stage_bytes;
+          ptx::mbar_arrive_expect_tx(&sm->full[s], stage_bytes);
+          ptx::tma_load_2d(sa, &map_a, &sm->full[s], kb * TC_BK, m0);
+          ptx::tma_load_2d(sa + a_bytes, &map_w, &sm->full[s], kb * TC_BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, (uint32_t)BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t round = (uint32_t)(kb / stages);
-        ptx::mbar_wait(&sm->full[s], round & 1);
+      uint32_t it = 0, ti = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        const uint32_t acc = ti & 1, use = ti >> 1;
+        ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);       // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
-        const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
-        const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
-        const int krem = K - kb * TC_BK;
-        const int ksteps = krem >= TC_BK ? 4 : (krem + 15) / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
-          ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % TC_STAGES, round = it / TC_STAGES;
+          ptx::mbar_wait(&sm->full[s], round & 1);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
+          const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
+          const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
+          const int krem = K - kb * TC_BK;
+          const int ksteps = krem >= TC_BK ? 4 : (krem + 15) / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+            ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          ptx::umma_commit(&sm->empty[s]);          // frees the smem slot when these MMAs retire
         }
-        ptx::umma_commit(&sm->empty[s]);          // frees the smem slot when these MMAs retire
+        ptx::umma_commit(&sm->tmem_full[acc]);      // accumulator complete
       }
-      ptx::umma_commit(&sm->tmem_full);           // accumulator complete
     }
   } else {
-    // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+    // ---------------- epilogue: group g = (warp-2)/4 drains accumulator g; TMEM lane quarter = warp % 4 ----------------
+    const int group = (warp - 2) >> 2;
     const int quarter = warp & 3;
-    ptx::mbar_wait(&sm->tmem_full, 0);
-    ptx::tc_fence_after();
-    if constexpr (EPI == EPI_STORE || EPI == EPI_RESID) {
-      // tcgen05.ld gives every lane 32 consecutive columns of ITS row; wide row outputs want the
-      // opposite (a warp instruction touching whole 128-byte row segments).  Each warp transposes
-      // its 32x32 chunk through a padded shared-memory tile and does the global I/O (residual
-      // loads, fp32 / bf16 stores) with 8 lanes x 16 bytes per row.
-      float* stage = stage_all + (warp - 2) * (32 * 33);
-      const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, raw);
-        ptx::tmem_ld_wait();
+    float* stage = stage_all + (warp - 2) * (32 * 33);
+    const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
+    uint32_t ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      if ((int)(ti & 1) != group) continue;
+      const uint32_t use = ti >> 1;
+      const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+      const uint32_t tmem_d = tmem_base + (uint32_t)group * (uint32_t)BN + ((uint32_t)(quarter * 32) << 16);
+      ptx::mbar_wait(&sm->tmem_full[group], use & 1);
+      ptx::tc_fence_after();
+      if constexpr (EPI == EPI_STORE || EPI == EPI_RESID) {
+        // tcgen05.ld gives every lane 32 consecutive columns of ITS row; wide row outputs want the
+        // opposite (a warp instruction touching whole 128-byte row segments).  Each warp transposes
+        // its 32x32 chunk through a padded shared-memory tile and does the global I/O (residual
+        // loads, fp32 / bf16 stores) with 8 lanes x 16 bytes per row.
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
+          const int n = n0 + c0 + c4;
+          float4 r4[8];
+          if (EPI == EPI_RESID) {                  // residual rows in flight while the TMEM load completes
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
-        __syncwarp();
-        const int n = n0 + c0 + c4;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (bias) b4 = *reinterpret_cast<const float4*>(bias + n);
-        if (EPI == EPI_RESID && ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n);
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + r_sub;
-          const int row = m0 + quarter * 32 + r;
-          if (row >= M) continue;
-          const float* sp = stage + r * 33 + c4;
-          float v0 = sp[0] + b4.x, v1 = sp[1] + b4.y, v2 = sp[2] + b4.z, v3 = sp[3] + b4.w;
-          if (EPI == EPI_RESID) {
-            const float4 r4 = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n);
-            v0 = r4.x + g4.x * v0; v1 = r4.y + g4.y * v1; v2 = r4.z + g4.z * v2; v3 = r4.w + g4.w * v3;
+            for (int it = 0; it < 8; ++it) {
+              const int row = m0 + quarter * 32 + it * 4 + r_sub;
+              r4[it] = row < M ? *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
-          if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + n) = make_float4(v0, v1, v2, v3);
-          if (ep.out_bf16) {
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ldo + n) = pk;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (bias) b4 = *reinterpret_cast<const float4*>(bias + n);
+          if (EPI == EPI_RESID && ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r_sub;
+            const int row = m0 + quarter * 32 + r;
+            if (row >= M) continue;
+            const float* sp = stage + r * 33 + c4;
+            float v0 = sp[0] + b4.x, v1 = sp[1] + b4.y, v2 = sp[2] + b4.z, v3 = sp[3] + b4.w;
+            if (EPI == EPI_RESID) {
+              v0 = r4[it].x + g4.x * v0; v1 = r4[it].y + g4.y * v1; v2 = r4[it].z + g4.z * v2; v3 = r4[it].w + g4.w * v3;
+            }
+            if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + n) = make_float4(v0, v1, v2, v3);
+            if (ep.out_bf16) {
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ldo + n) = pk;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // GLU (narrow bf16 rows) and SCATTER (rows land on scattered pixels): every lane finishes its own row
+        const int row = m0 + quarter * 32 + lane;
+        const bool row_ok = row < M;
+        long long pix = 0;
+        if (EPI == EPI_SCATTER && row_ok) pix = ep.row_pix[row];
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
+          const int n = n0 + c0;
+          float4 r4[8];
+          if (EPI == EPI_SCATTER && row_ok) {      // residual loads in flight while the TMEM load completes
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n + 4 * j);
+          }
+          ptx::tmem_ld_wait();
+          if (!row_ok) continue;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias + n + j);
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (EPI == EPI_GLU) {
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+            __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n / 2;
+            store_bf16x8(dst, o);
+            store_bf16x8(dst + 8, o + 8);
+          } else {
+            float* dst = ep.out_f32 + pix * ep.C + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n + 4 * j);
+              *reinterpret_cast<float4*>(dst + 4 * j) =
+                  make_float4(r4[j].x + g4.x * v[4 * j], r4[j].y + g4.y * v[4 * j + 1], r4[j].z + g4.z * v[4 * j + 2],
+                              r4[j].w + g4.w * v[4 * j + 3]);
+            }
           }
         }
-        __syncwarp();
       }
-    } else {
-      // GLU (narrow bf16 rows) and SCATTER (rows land on scattered pixels): every lane finishes its own row
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < M;
-      long long pix = 0;
-      if (EPI == EPI_SCATTER && row_ok) pix = ep.row_pix[row];
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, raw);
-        const int n = n0 + c0;
-        float4 r4[8];
-        if (EPI == EPI_SCATTER && row_ok) {      // residual loads in flight while the TMEM load completes
-#pragma unroll
-          for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n + 4 * j);
-        }
-        ptx::tmem_ld_wait();
-        if (!row_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias + n + j);
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        }
-        if (EPI == EPI_GLU) {
-          float o[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
-          __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n / 2;
-          store_bf16x8(dst, o);
-          store_bf16x8(dst + 8, o + 8);
-        } else {
-          float* dst = ep.out_f32 + pix * ep.C + n;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (ep.gamma) g4 = *reinterpret_cast<const float4*>(ep.gamma + n + 4 * j);
-            *reinterpret_cast<float4*>(dst + 4 * j) =
-                make_float4(r4[j].x + g4.x * v[4 * j], r4[j].y + g4.y * v[4 * j + 1], r4[j].z + g4.z * v[4 * j + 2],
-                            r4[j].w + g4.w * v[4 * j + 3]);
-          }
-        }
-      }
+      // this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm->tmem_empty[group]);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_d, tmem_cols);
+    ptx::tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -243,21 +279,30 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, long long rows, int cols,
   return make_tmap_bf16_box(m, ptr, rows, cols, ld, TC_BK, box_rows, 128);
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int EPI>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* bias, int N, int K, int BN, const int* counts,
                      long long max_rows, int m_static, const EpiParams& ep, cudaStream_t st) {
-  const int nkb = (K + TC_BK - 1) / TC_BK;
-  const int stages = nkb < TC_MAX_STAGES ? nkb : TC_MAX_STAGES;
-  const bool staged = EPI == EPI_STORE || EPI == EPI_RESID;
-  const size_t smem = 1024 + (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 128 + (staged ? 4 * 32 * 33 * sizeof(float) : 0);
+  const size_t smem = 1024 + (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 128 +
+                      TC_EPI_WARPS * 32 * 33 * sizeof(float);
   static bool attr_done = false;   // per-instantiation; the attribute is idempotent
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  const dim3 grid((unsigned)((max_rows + TC_BM - 1) / TC_BM), (unsigned)(N / BN));
-  gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(ma, mw, bias, N, K, BN, stages, counts, m_static, ep);
+  const long long tiles = ((max_rows + TC_BM - 1) / TC_BM) * (N / BN);       // worst case; the kernel clips to counts[1]
+  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+  gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(ma, mw, bias, N, K, BN, counts, m_static, ep);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

@@ -411,11 +411,14 @@ static int launch_gather_ln_t(const sast_layer_args& a, const Geom& g, const Lay
 }
 
 static int launch_gather_ln(const sast_layer_args& a, const Geom& g, const LayerWorkspace& ws, cudaStream_t st) {
+  // few lanes per token (each holding up to 4 float4): short shuffle reductions, and the per-token index
+  // arithmetic (token -> pixel) is amortised over 8-16 tokens per warp
   const int C = g.C;
-  if (C <= 32) return launch_gather_ln_t<8, 1, 4>(a, g, ws, st);
-  if (C <= 64) return launch_gather_ln_t<16, 1, 4>(a, g, ws, st);
-  if (C <= 128) return launch_gather_ln_t<32, 1, 4>(a, g, ws, st);
-  if (C <= 256) return launch_gather_ln_t<32, 2, 4>(a, g, ws, st);
+  if (C <= 32) return launch_gather_ln_t<2, 4, 2>(a, g, ws, st);
+  if (C <= 64) return launch_gather_ln_t<4, 4, 2>(a, g, ws, st);
+  if (C <= 96) return launch_gather_ln_t<8, 3, 2>(a, g, ws, st);
+  if (C <= 128) return launch_gather_ln_t<8, 4, 2>(a, g, ws, st);
+  if (C <= 256) return launch_gather_ln_t<16, 4, 2>(a, g, ws, st);
   if (C <= 512) return launch_gather_ln_t<32, 4, 2>(a, g, ws, st);
   if (C <= 1024) return launch_gather_ln_t<32, 8, 1>(a, g, ws, st);
   return SAST_E_UNSUPPORTED;

@@ -146,3 +146,30 @@ def test_config_objects():
     assert c.stage.attention.get("norm_eps", 1e-5) == 1e-5 and c.stage.lstm.dws_conv is False
     with pytest.raises(AssertionError):
         backbone_config((240, 304))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference checkout only exists in the build container")
+def test_dropin_shadows_reference_modules():
+    """With sast_b200/dropin ahead of the reference on sys.path, the reference's own detector
+    (models/detection/yolox_extension/models/detector.py, unedited) builds OUR backbone."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r, '/root/reference']\n"
+        "from omegaconf import DictConfig\n"
+        "from models.detection.yolox_extension.models.detector import YoloXDetector\n"
+        "from sast_b200.config import backbone_config\n"
+        "cfg = DictConfig(dict(backbone=dict(backbone_config((384, 640))), fpn=dict(name='PAFPN', depth=0.67, in_stages=[2,3,4],"
+        " depthwise=False, act='silu', compile=dict(enable=False, args=dict())), head=dict(name='YoloX', depthwise=False, act='silu',"
+        " num_classes=3, compile=dict(enable=False, args=dict()))))\n"
+        "det = YoloXDetector(cfg)\n"
+        "import models.layers.SAST.SAST as S, models.layers.rnn as R\n"
+        "print(type(det.backbone).__module__, S.SAST_block.__module__, R.DWSConvLSTM2d.__module__, type(det.fpn).__module__)\n"
+    ) % (ROOT, os.path.join(ROOT, "sast_b200", "dropin"), os.path.join(ROOT, "oracle", "_shim"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("sast_b200.backbone")]
+    assert line, out.stdout[-500:]
+    mods = line[0].split()
+    assert mods[0] == "sast_b200.backbone" and mods[1] == "sast_b200.sast" and mods[2] == "sast_b200.backbone"
+    assert mods[3].startswith("models.detection.yolox_extension")
