@@ -11,31 +11,43 @@
 
 namespace sast {
 
-// CTA = one padded output row segment of 64 pixels: the Cin input planes are read with coalesced
-// row loads into shared memory ([Cin][64]), then written out pixel-major (Cin contiguous floats per
-// pixel = dense 16-byte stores across the warp).
+// CTA = one padded output row segment of PX pixels: the Cin input planes are read with coalesced
+// row loads into shared memory ([Cin][PX] in the input dtype), then written out pixel-major
+// (Cin contiguous floats per pixel: dense 16-byte stores across the warp).
+constexpr int PAD_PX = 256;
 template <typename T>
 __global__ void __launch_bounds__(256) pad_input_kernel(const T* __restrict__ x, int B, int Cin, int H, int W, int pad,
                                                         float* __restrict__ out) {
-  extern __shared__ float tile[];                 // [Cin][65]
+  extern __shared__ __align__(16) uint8_t tile_raw[];
+  T* tile = reinterpret_cast<T*>(tile_raw);            // [Cin][PAD_PX + 4]
+  constexpr int LD = PAD_PX + 4;
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
-  const int segs = (Wo + 63) / 64;
+  const int segs = (Wo + PAD_PX - 1) / PAD_PX;
   const int seg = blockIdx.x % segs;
   const int yo = (blockIdx.x / segs) % Ho;
   const int b = blockIdx.x / (segs * Ho);
   const int ys = min(max(yo - pad, 0), H - 1);
-  const int x0 = seg * 64;
-  for (int i = threadIdx.x; i < Cin * 64; i += blockDim.x) {
-    const int c = i >> 6, dx = i & 63;
-    const int xs = min(max(x0 + dx - pad, 0), W - 1);
-    tile[c * 65 + dx] = (float)x[((size_t)(b * Cin + c) * H + ys) * W + xs];
+  const int x0 = seg * PAD_PX;
+  const int npx = min(PAD_PX, Wo - x0);
+  for (int c = 0; c < Cin; ++c) {
+    const T* src = x + ((size_t)(b * Cin + c) * H + ys) * W;
+    for (int dx = threadIdx.x; dx < npx; dx += blockDim.x) tile[c * LD + dx] = src[min(max(x0 + dx - pad, 0), W - 1)];
   }
   __syncthreads();
-  const int npx = min(64, Wo - x0);
   float* dst = out + ((size_t)(b * Ho + yo) * Wo + x0) * Cin;
-  for (int i = threadIdx.x; i < npx * Cin; i += blockDim.x) {
-    const int dx = i / Cin, c = i - dx * Cin;
-    dst[i] = tile[c * 65 + dx];
+  if (Cin % 4 == 0) {
+    const int c4n = Cin / 4;
+    for (int i = threadIdx.x; i < npx * c4n; i += blockDim.x) {
+      const int dx = i / c4n, c = (i - dx * c4n) * 4;
+      *reinterpret_cast<float4*>(dst + (size_t)dx * Cin + c) =
+          make_float4((float)tile[c * LD + dx], (float)tile[(c + 1) * LD + dx], (float)tile[(c + 2) * LD + dx],
+                      (float)tile[(c + 3) * LD + dx]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < npx * Cin; i += blockDim.x) {
+      const int dx = i / Cin, c = i - dx * Cin;
+      dst[i] = (float)tile[c * LD + dx];
+    }
   }
 }
 
@@ -165,8 +177,9 @@ extern "C" int sast_pad_input(const void* x, int32_t dtype, int32_t B, int32_t C
   SAST_CHECK_PTR(x); SAST_CHECK_PTR(out);
   if (B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || pad < 0) return SAST_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = (unsigned)((long long)B * (H + 2 * pad) * ((W + 2 * pad + 63) / 64));
-  const size_t smem = (size_t)Cin * 65 * sizeof(float);
+  const unsigned grid = (unsigned)((long long)B * (H + 2 * pad) * ((W + 2 * pad + PAD_PX - 1) / PAD_PX));
+  const size_t esz = dtype == SAST_U8 ? 1 : 4;
+  const size_t smem = (size_t)Cin * (PAD_PX + 4) * esz;
   if (smem > 48 * 1024) return SAST_E_UNSUPPORTED;
   switch (dtype) {
     case SAST_U8: pad_input_kernel<uint8_t><<<grid, 256, smem, st>>>((const uint8_t*)x, B, Cin, H, W, pad, out); break;

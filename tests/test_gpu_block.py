@@ -108,7 +108,7 @@ def _backbone_check(g, m, net, precision):
     got_p = [int(v) for v in p0] + [int(v) for v in p1]
     # selected-token counts: exact in fp32 up to threshold flips (<= 0.1 %), looser for bf16 whose
     # rounding feeds the next stage's scores
-    rel = 1e-3 if precision == L.FP32 else 2e-2
+    rel = 1e-3 if precision == L.FP32 else 5e-2
     for a, b in zip(got_p, ref_p):
         assert abs(a - b) <= max(3, rel * b), (got_p, ref_p)
     tol = 5e-4 if precision == L.FP32 else 8e-2
