@@ -96,12 +96,14 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // below the bf16 output rounding) -- one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner instead of erff.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * exp2f(-z * z * 1.44269504088896340736f);    // erf(|x|/sqrt2)
+  float ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z * 1.44269504088896340736f));
+  const float e = 1.0f - p * t * ex;                                          // erf(|x|/sqrt2)
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                                                                 const float* __restrict__ bias, int N, int K, int BN,
                                                                 const int* __restrict__ counts, int m_static, EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ float stage_smem[(EPI == EPI_STORE || EPI == EPI_RESID) ? TC_EPI_WARPS : 1][32 * 33];   // epilogue transpose tiles
   const int M = counts ? counts[1] : m_static;
   const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = N / BN;
   const int total_tiles = m_tiles * n_tiles;
@@ -130,10 +131,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t tmem_d = tmem_base + (uint32_t)group * (uint32_t)BN + ((uint32_t)(quarter * 32) << 16);
       ptx::mbar_wait(&sm->tmem_full[group], use & 1);
       ptx::tc_fence_after();
-      {
-        // Every lane finishes its own row: 32 accumulator columns per tcgen05.ld, bias / LayerScale /
-        // residual / GLU in registers, 16-byte stores into the row (full 32-byte sectors, no transpose:
-        // the instruction count, not coalescing, is what bounds this epilogue).
+      if constexpr (EPI == EPI_STORE || EPI == EPI_RESID) {
+        // tcgen05.ld gives every lane 32 consecutive columns of ITS row; wide row outputs want the
+        // opposite (a warp instruction touching whole 128-byte row segments).  Each warp transposes
+        // its 32x32 chunk through a padded shared-memory tile and does the global I/O (residual
+        // loads, fp32 / bf16 stores) with 8 lanes x 16 bytes per row.
+        float* stage = &stage_smem[warp - 2][0];
+        const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
+          const int n = n0 + c0 + c4;
+          float4 r4[8];
+          if (EPI == EPI_RESID) {                  // residual rows in flight while the TMEM load completes
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = m0 + quarter * 32 + it * 4 + r_sub;
+              r4[it] = row < M ? *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+          if (EPI == EPI_RESID && ep.gamma) g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r_sub;
+            const int row = m0 + quarter * 32 + r;
+            if (row >= M) continue;
+            const float* sp = stage + r * 33 + c4;
+            float v0 = sp[0] + b4.x, v1 = sp[1] + b4.y, v2 = sp[2] + b4.z, v3 = sp[3] + b4.w;
+            if (EPI == EPI_RESID) {
+              v0 = r4[it].x + g4.x * v0; v1 = r4[it].y + g4.y * v1; v2 = r4[it].z + g4.z * v2; v3 = r4[it].w + g4.w * v3;
+            }
+            if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + n) = make_float4(v0, v1, v2, v3);
+            if (ep.out_bf16) {
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ldo + n) = pk;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // GLU (narrow bf16 rows) and SCATTER (rows land on scattered pixels): every lane finishes its own row
         const int row = m0 + quarter * 32 + lane;
         const bool row_ok = row < M;
         long long pix = 0;
@@ -143,7 +189,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
           const int n = n0 + c0;
           float4 r4[8];
-          if ((EPI == EPI_SCATTER || EPI == EPI_RESID) && row_ok) {      // residual loads fly while the TMEM load completes
+          if (EPI == EPI_SCATTER && row_ok) {      // residual loads in flight while the TMEM load completes
 #pragma unroll
             for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n + 4 * j);
           }
@@ -167,24 +213,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             store_bf16x8(dst, o);
             store_bf16x8(dst + 8, o + 8);
           } else {
-            if (EPI == EPI_SCATTER || EPI == EPI_RESID) {
+            float* dst = ep.out_f32 + pix * ep.C + n;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (ep.gamma) g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4 * j));
-                v[4 * j] = r4[j].x + g4.x * v[4 * j]; v[4 * j + 1] = r4[j].y + g4.y * v[4 * j + 1];
-                v[4 * j + 2] = r4[j].z + g4.z * v[4 * j + 2]; v[4 * j + 3] = r4[j].w + g4.w * v[4 * j + 3];
-              }
-            }
-            if (ep.out_f32) {
-              float* dst = EPI == EPI_SCATTER ? ep.out_f32 + pix * ep.C + n : ep.out_f32 + (size_t)row * ep.ldo + n;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (EPI != EPI_SCATTER && ep.out_bf16) {
-              __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j, v + j);
+            for (int j = 0; j < 8; ++j) {
+              float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (ep.gamma) g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4 * j));
+              *reinterpret_cast<float4*>(dst + 4 * j) =
+                  make_float4(r4[j].x + g4.x * v[4 * j], r4[j].y + g4.y * v[4 * j + 1], r4[j].z + g4.z * v[4 * j + 2],
+                              r4[j].w + g4.w * v[4 * j + 3]);
             }
           }
         }

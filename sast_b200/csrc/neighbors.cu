@@ -17,7 +17,7 @@ namespace sast {
 constexpr int PAD_PX = 256;
 template <typename T>
 __global__ void __launch_bounds__(256) pad_input_kernel(const T* __restrict__ x, int B, int Cin, int H, int W, int pad,
-                                                        float* __restrict__ out) {
+                                                        int cgroup, float* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t tile_raw[];
   T* tile = reinterpret_cast<T*>(tile_raw);            // [Cin][PAD_PX + 4]
   constexpr int LD = PAD_PX + 4;
@@ -29,25 +29,29 @@ __global__ void __launch_bounds__(256) pad_input_kernel(const T* __restrict__ x,
   const int ys = min(max(yo - pad, 0), H - 1);
   const int x0 = seg * PAD_PX;
   const int npx = min(PAD_PX, Wo - x0);
-  for (int c = 0; c < Cin; ++c) {
-    const T* src = x + ((size_t)(b * Cin + c) * H + ys) * W;
-    for (int dx = threadIdx.x; dx < npx; dx += blockDim.x) tile[c * LD + dx] = src[min(max(x0 + dx - pad, 0), W - 1)];
-  }
-  __syncthreads();
   float* dst = out + ((size_t)(b * Ho + yo) * Wo + x0) * Cin;
-  if (Cin % 4 == 0) {
-    const int c4n = Cin / 4;
-    for (int i = threadIdx.x; i < npx * c4n; i += blockDim.x) {
-      const int dx = i / c4n, c = (i - dx * c4n) * 4;
-      *reinterpret_cast<float4*>(dst + (size_t)dx * Cin + c) =
-          make_float4((float)tile[c * LD + dx], (float)tile[(c + 1) * LD + dx], (float)tile[(c + 2) * LD + dx],
-                      (float)tile[(c + 3) * LD + dx]);
+  for (int cg0 = 0; cg0 < Cin; cg0 += cgroup) {            // channel groups sized to the shared-memory tile
+    const int cg = min(cgroup, Cin - cg0);
+    for (int i = threadIdx.x; i < cg * PAD_PX; i += blockDim.x) {
+      const int c = i / PAD_PX, dx = i - c * PAD_PX;
+      if (dx < npx) tile[c * LD + dx] = x[((size_t)(b * Cin + cg0 + c) * H + ys) * W + min(max(x0 + dx - pad, 0), W - 1)];
     }
-  } else {
-    for (int i = threadIdx.x; i < npx * Cin; i += blockDim.x) {
-      const int dx = i / Cin, c = i - dx * Cin;
-      dst[i] = (float)tile[c * LD + dx];
+    __syncthreads();
+    if (cg % 4 == 0 && Cin % 4 == 0) {
+      const int c4n = cg / 4;
+      for (int i = threadIdx.x; i < npx * c4n; i += blockDim.x) {
+        const int dx = i / c4n, c = (i - dx * c4n) * 4;
+        *reinterpret_cast<float4*>(dst + (size_t)dx * Cin + cg0 + c) =
+            make_float4((float)tile[c * LD + dx], (float)tile[(c + 1) * LD + dx], (float)tile[(c + 2) * LD + dx],
+                        (float)tile[(c + 3) * LD + dx]);
+      }
+    } else {
+      for (int i = threadIdx.x; i < npx * cg; i += blockDim.x) {
+        const int dx = i / cg, c = i - dx * cg;
+        dst[(size_t)dx * Cin + cg0 + c] = (float)tile[c * LD + dx];
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -179,12 +183,13 @@ extern "C" int sast_pad_input(const void* x, int32_t dtype, int32_t B, int32_t C
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((long long)B * (H + 2 * pad) * ((W + 2 * pad + PAD_PX - 1) / PAD_PX));
   const size_t esz = dtype == SAST_U8 ? 1 : 4;
-  const size_t smem = (size_t)Cin * (PAD_PX + 4) * esz;
-  if (smem > 48 * 1024) return SAST_E_UNSUPPORTED;
+  int cgroup = (int)((40 * 1024) / ((PAD_PX + 4) * esz));
+  if (cgroup >= Cin) cgroup = Cin; else cgroup &= ~3;
+  const size_t smem = (size_t)cgroup * (PAD_PX + 4) * esz;
   switch (dtype) {
-    case SAST_U8: pad_input_kernel<uint8_t><<<grid, 256, smem, st>>>((const uint8_t*)x, B, Cin, H, W, pad, out); break;
-    case SAST_I32: pad_input_kernel<int32_t><<<grid, 256, smem, st>>>((const int32_t*)x, B, Cin, H, W, pad, out); break;
-    case SAST_F32: pad_input_kernel<float><<<grid, 256, smem, st>>>((const float*)x, B, Cin, H, W, pad, out); break;
+    case SAST_U8: pad_input_kernel<uint8_t><<<grid, 256, smem, st>>>((const uint8_t*)x, B, Cin, H, W, pad, cgroup, out); break;
+    case SAST_I32: pad_input_kernel<int32_t><<<grid, 256, smem, st>>>((const int32_t*)x, B, Cin, H, W, pad, cgroup, out); break;
+    case SAST_F32: pad_input_kernel<float><<<grid, 256, smem, st>>>((const float*)x, B, Cin, H, W, pad, cgroup, out); break;
     default: return SAST_E_UNSUPPORTED;
   }
   SAST_LAUNCH_CHECK();
