@@ -114,8 +114,12 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     ptx::tc_fence_after();
 
     // ---- softmax over this row's window (two passes over TMEM: max, then exp / sum / P) ----
+    // A warp only visits the 32-column chunks that some of its rows need (block-diagonal mask: with
+    // two 60-token windows per tile most warps skip a third of the columns); skipped chunks of P are zero.
+    const int wlo = __reduce_min_sync(kFull, t < rows ? lo : 128) & ~31;
+    const int whi = __reduce_max_sync(kFull, t < rows ? hi : 0);
     float mx = -INFINITY;
-    for (int c0 = 0; c0 < rows16; c0 += 32) {
+    for (int c0 = wlo; c0 < whi; c0 += 32) {
       uint32_t raw[32];
       ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
       ptx::tmem_ld_wait();
@@ -126,19 +130,23 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
       }
     }
     float sum = 0.f;
+    const float mxs = mx * sc;
     const int r8 = t & 7;
     uint8_t* prow = sP + (t >> 3) * 1024 + r8 * 128;
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = 0; c0 < rows16; c0 += 32) {
       uint32_t pk[16];
-      if (c0 < rows16) {
+      if (c0 >= wlo && c0 < whi) {
         uint32_t raw[32];
         ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const int col = c0 + j;
-          const float p0 = (col >= lo && col < hi) ? exp2f((__uint_as_float(raw[j]) - mx) * sc) : 0.f;
-          const float p1 = (col + 1 >= lo && col + 1 < hi) ? exp2f((__uint_as_float(raw[j + 1]) - mx) * sc) : 0.f;
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[j]), sc, -mxs)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs)));
+          p0 = (col >= lo && col < hi) ? p0 : 0.f;
+          p1 = (col + 1 >= lo && col + 1 < hi) ? p1 : 0.f;
           const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
           // the row sum uses the bf16-rounded probabilities the PV product will see
           const float2 f2 = __bfloat1622float2(b2);

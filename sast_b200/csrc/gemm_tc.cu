@@ -294,7 +294,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* 
   const size_t smem = 1024 + (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 128;
   static bool attr_done = false;   // per-instantiation; the attribute is idempotent
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);   // + <= 34 KB static
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }

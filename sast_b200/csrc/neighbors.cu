@@ -32,9 +32,21 @@ __global__ void __launch_bounds__(256) pad_input_kernel(const T* __restrict__ x,
   float* dst = out + ((size_t)(b * Ho + yo) * Wo + x0) * Cin;
   for (int cg0 = 0; cg0 < Cin; cg0 += cgroup) {            // channel groups sized to the shared-memory tile
     const int cg = min(cgroup, Cin - cg0);
-    for (int i = threadIdx.x; i < cg * PAD_PX; i += blockDim.x) {
-      const int c = i / PAD_PX, dx = i - c * PAD_PX;
-      if (dx < npx) tile[c * LD + dx] = x[((size_t)(b * Cin + cg0 + c) * H + ys) * W + min(max(x0 + dx - pad, 0), W - 1)];
+    // PAD_PX == blockDim.x: thread t owns pixel column t of every plane; loads are issued four planes at a
+    // time before any of them is consumed (one byte load in flight per thread is pure latency)
+    const int dx = threadIdx.x;
+    const int xs = min(max(x0 + dx - pad, 0), W - 1);
+    const T* src = x + ((size_t)(b * Cin + cg0) * H + ys) * W + xs;
+    const size_t plane = (size_t)H * W;
+    int c = 0;
+    for (; c + 4 <= cg; c += 4) {
+      const T v0 = src[(size_t)c * plane], v1 = src[(size_t)(c + 1) * plane], v2 = src[(size_t)(c + 2) * plane],
+              v3 = src[(size_t)(c + 3) * plane];
+      if (dx < npx) { tile[c * LD + dx] = v0; tile[(c + 1) * LD + dx] = v1; tile[(c + 2) * LD + dx] = v2; tile[(c + 3) * LD + dx] = v3; }
+    }
+    for (; c < cg; ++c) {
+      const T v0 = src[(size_t)c * plane];
+      if (dx < npx) tile[c * LD + dx] = v0;
     }
     __syncthreads();
     if (cg % 4 == 0 && Cin % 4 == 0) {

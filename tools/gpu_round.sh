@@ -8,7 +8,9 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2>&1
 echo "bench exit $?" >> gpurun_out/bench.log
+if [ "$1" != "quick" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 echo "ncu exit $?" >> gpurun_out/ncu_bench.log
+fi
 tail -5 gpurun_out/pytest.log; tail -3 gpurun_out/smoke.log; tail -2 gpurun_out/bench.log
