@@ -117,7 +117,9 @@ typedef struct sast_score_args {
   float amp;
   float* xw;               /* out [B,H,W,C]; must not alias x */
   float* tok_score;        /* out [B,H,W] */
-  float* ctrl_scratch;     /* scratch floats: 2*B*C (sigmoid(ctrl), amp/ctrl) + ceil(C/64)*B*H*W (partial scores) */
+  float* ctrl_scratch;     /* scratch floats: 2*B*C (sigmoid(ctrl), amp/ctrl) + (C/32)*B*H*W (partial scores) */
+  const float* score_w_hi; /* optional: to_scores.weight split for the 3xTF32 tensor-core path: */
+  const float* score_w_lo; /*   w_hi = tf32(w), w_lo = tf32(w - w_hi), both [C,C] fp32. NULL -> fp32 FMA kernel */
 } sast_score_args;
 int sast_score_fwd(const sast_score_args* a, void* stream);
 

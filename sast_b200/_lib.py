@@ -38,7 +38,7 @@ class ScoreArgs(C.Structure):
     _fields_ = [("g", Geom), ("x", C.c_void_p), ("pos", C.c_void_p), ("pos_batch_stride", C.c_int64),
                 ("r", C.c_void_p), ("n_bins", C.c_int32), ("ctrl_w", C.c_void_p), ("score_w", C.c_void_p),
                 ("score_b", C.c_void_p), ("amp", C.c_float), ("xw", C.c_void_p), ("tok_score", C.c_void_p),
-                ("ctrl_scratch", C.c_void_p)]
+                ("ctrl_scratch", C.c_void_p), ("score_w_hi", C.c_void_p), ("score_w_lo", C.c_void_p)]
 
 
 class SelectArgs(C.Structure):

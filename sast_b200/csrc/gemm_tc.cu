@@ -274,6 +274,20 @@ int make_tmap_bf16_box(CUtensorMap* m, const void* ptr, long long rows, int cols
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
+// 2-D fp32 row-major [rows, cols]; box = box_cols (<= 32: 128-byte swizzle span) x box_rows
+int make_tmap_f32_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return (int)cudaErrorNotSupported;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
 int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_rows) {
   return make_tmap_bf16_box(m, ptr, rows, cols, ld, TC_BK, box_rows, 128);
 }

@@ -131,6 +131,8 @@ __global__ void add_pos_kernel(const float4* __restrict__ x, const float4* __res
   }
 }
 
+int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv, float* l1_part, int* n_slices, cudaStream_t st);
+
 }  // namespace sast
 
 extern "C" int sast_score_fwd(const sast_score_args* a, void* stream) {
@@ -156,9 +158,22 @@ extern "C" int sast_score_fwd(const sast_score_args* a, void* stream) {
   float* inv = a->ctrl_scratch + (size_t)g.B * g.C;
   sast::controls_kernel<<<g.B, 128, 0, st>>>(a->r, a->ctrl_w, a->n_bins, g.C, a->amp, sig, inv);
   SAST_LAUNCH_CHECK();
-  const int ny = (g.C + sast::BN - 1) / sast::BN;
+  float* part_buf = a->ctrl_scratch + 2 * (size_t)g.B * g.C;
+  int ny;
+  if (a->score_w_hi && a->score_w_lo) {      // 3xTF32 on tcgen05
+    const int bn = g.C % 128 == 0 ? 128 : (g.C % 64 == 0 ? 64 : 32);
+    float* part = g.C / bn == 1 ? a->tok_score : part_buf;
+    int rc = sast::launch_score_tc(a, sig, inv, part, &ny, st);
+    if (rc) return rc;
+    if (ny > 1) {
+      sast::score_reduce_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(part, ny, P, a->tok_score);
+      SAST_LAUNCH_CHECK();
+    }
+    return SAST_OK;
+  }
+  ny = (g.C + sast::BN - 1) / sast::BN;
   const dim3 grid((unsigned)((P + sast::BM - 1) / sast::BM), ny);
-  float* part = ny == 1 ? a->tok_score : a->ctrl_scratch + 2 * (size_t)g.B * g.C;
+  float* part = ny == 1 ? a->tok_score : part_buf;
   sast::score_kernel<<<grid, 256, 0, st>>>(a->x, a->pos, a->pos_batch_stride, a->score_w, a->score_b, sig, inv, HW, g.C, P,
                                            a->xw, part);
   SAST_LAUNCH_CHECK();

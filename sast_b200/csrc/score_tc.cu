@@ -1,0 +1,263 @@
+// a4 on the tensor cores: scoring GEMM  s = relu((x + pos) Ws^T + b)  as 3xTF32 tcgen05.mma.
+//
+// Selection thresholds a softmax of sum_c |amp/ctrl_c * s_c| (SURVEY.md "hard part 1"): a bf16 GEMM
+// flips ~1e-3 of the tokens, so the product is kept fp32-accurate by error compensation:
+//     a = a_hi + a_lo,  w = w_hi + w_lo   (each half rounded to TF32, 1+10-bit significand)
+//     a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi          (dropped term ~2^-22 |a||w|)
+// Three kind::tf32 MMAs per 8-wide k-step, fp32 accumulation in TMEM.
+//
+// Persistent CTAs, 9 warps:
+//   warps 0-3  loaders: x + pos formed on the fly (coalesced float4 rows), split into hi/lo and written
+//              to shared memory in the SWIZZLE_128B K-major operand layout; lane 0 also TMA-loads the
+//              pre-split weight tiles (W_hi, W_lo: [C,C] fp32, K-major like nn.Linear.weight)
+//   warps 4-7  epilogue: TMEM -> shared-memory transpose -> coalesced rows: STP-weighted map
+//              xw = sigmoid(ctrl) sigmoid(s) x0 and the per-token L1  sum_c |amp/ctrl_c s_c|
+//   warp 8     TMEM allocator + MMA issuer; two accumulators (tile i drains while tile i+1 multiplies)
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sast {
+
+constexpr int SC_BM = 128, SC_BK = 32, SC_STAGES = 2;
+constexpr int SC_THREADS = 9 * 32;
+
+struct ScSmem {
+  uint64_t full[SC_STAGES];
+  uint64_t empty[SC_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);   // D=F32, A=B=TF32, K-major
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap map_whi,
+                                                                 const __grid_constant__ CUtensorMap map_wlo,
+                                                                 const float* __restrict__ x, const float* __restrict__ pos,
+                                                                 long long pos_bstride, const float* __restrict__ bs,
+                                                                 const float* __restrict__ sig, const float* __restrict__ inv,
+                                                                 int HW, int C, int BN, long long P, float* __restrict__ xw,
+                                                                 float* __restrict__ l1_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ float stage_smem[4][32 * 33];
+  const int m_tiles = (int)((P + SC_BM - 1) / SC_BM), n_tiles = C / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = SC_BM * SC_BK * 4;                     // 16 KB per half
+  const uint32_t w_bytes = (uint32_t)BN * SC_BK * 4;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;         // A_hi, A_lo, W_hi, W_lo
+  ScSmem* sm = reinterpret_cast<ScSmem*>(base + (size_t)SC_STAGES * stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = C / SC_BK;
+
+  if (threadIdx.x == 0) {
+    ptx::tma_prefetch_desc(&map_whi);
+    ptx::tma_prefetch_desc(&map_wlo);
+    for (int s = 0; s < SC_STAGES; ++s) { ptx::mbar_init(&sm->full[s], 129); ptx::mbar_init(&sm->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&sm->tmem_full[a], 1); ptx::mbar_init(&sm->tmem_empty[a], 4); }
+    ptx::fence_barrier_init();
+  }
+  const uint32_t tmem_cols = (uint32_t)(2 * BN) < 32u ? 32u : (uint32_t)(2 * BN);
+  if (warp == 8) ptx::tmem_alloc(&sm->tmem_base, tmem_cols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = sm->tmem_base;
+
+  if (warp < 4) {
+    // ---------------- loaders ----------------
+    const int t = threadIdx.x;                 // 0..127
+    const int chunk = t & 7;                   // 16-byte chunk of the 128-byte k-block row
+    const int rbase = t >> 3;                  // rows rbase, rbase+16, ... (8 rows per thread)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const long long m0 = (long long)(tile / n_tiles) * SC_BM;
+      const int n0 = (tile % n_tiles) * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % SC_STAGES, round = it / SC_STAGES;
+        ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
+        uint8_t* st = base + (size_t)s * stage_bytes;
+        if (t == 0) {
+          ptx::mbar_arrive_expect_tx(&sm->full[s], 2 * w_bytes);
+          ptx::tma_load_2d(st + 2 * a_bytes, &map_whi, &sm->full[s], kb * SC_BK, n0);
+          ptx::tma_load_2d(st + 2 * a_bytes + w_bytes, &map_wlo, &sm->full[s], kb * SC_BK, n0);
+        }
+        float4 xv[8], pv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const long long tok = m0 + rbase + 16 * j;
+          if (tok < P) {
+            xv[j] = *reinterpret_cast<const float4*>(x + tok * C + kb * SC_BK + chunk * 4);
+            pv[j] = *reinterpret_cast<const float4*>(pos + (tok / HW) * pos_bstride + (tok % HW) * (long long)C + kb * SC_BK + chunk * 4);
+          } else {
+            xv[j] = make_float4(0.f, 0.f, 0.f, 0.f); pv[j] = xv[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = rbase + 16 * j;
+          const float a0 = xv[j].x + pv[j].x, a1 = xv[j].y + pv[j].y, a2 = xv[j].z + pv[j].z, a3 = xv[j].w + pv[j].w;
+          const float h0 = to_tf32(a0), h1 = to_tf32(a1), h2 = to_tf32(a2), h3 = to_tf32(a3);
+          const uint32_t off = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128 + (uint32_t)((chunk ^ (r & 7)) * 16);
+          *reinterpret_cast<float4*>(st + off) = make_float4(h0, h1, h2, h3);
+          *reinterpret_cast<float4*>(st + a_bytes + off) = make_float4(to_tf32(a0 - h0), to_tf32(a1 - h1), to_tf32(a2 - h2), to_tf32(a3 - h3));
+        }
+        ptx::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
+        ptx::mbar_arrive(&sm->full[s]);
+      }
+    }
+  } else if (warp == 8) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(SC_BM, (uint32_t)BN);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t acc = ti & 1, use = ti >> 1;
+        ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % SC_STAGES, round = it / SC_STAGES;
+          ptx::mbar_wait(&sm->full[s], round & 1);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
+          const uint64_t dah = ptx::umma_desc_sw128_kmajor(sa), dal = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
+          const uint64_t dwh = ptx::umma_desc_sw128_kmajor(sa + 2 * a_bytes), dwl = ptx::umma_desc_sw128_kmajor(sa + 2 * a_bytes + w_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {          // 8 tf32 = 32 bytes per k-step: +2 in the >>4 address field
+            const uint64_t o = (uint64_t)(k * 2);
+            umma_tf32_ss(tmem_d, dal + o, dwh + o, idesc, (kb | k) ? 1u : 0u);    // small terms first
+            umma_tf32_ss(tmem_d, dah + o, dwl + o, idesc, 1u);
+            umma_tf32_ss(tmem_d, dah + o, dwh + o, idesc, 1u);
+          }
+          ptx::umma_commit(&sm->empty[s]);
+        }
+        ptx::umma_commit(&sm->tmem_full[acc]);
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 4..7, TMEM lane quarter = warp % 4) ----------------
+    const int quarter = warp & 3;
+    float* stage = &stage_smem[quarter][0];
+    const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t acc = ti & 1, use = ti >> 1;
+      const long long m0 = (long long)(tile / n_tiles) * SC_BM;
+      const int n_tile = tile % n_tiles, n0 = n_tile * BN;
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN + ((uint32_t)(quarter * 32) << 16);
+      ptx::mbar_wait(&sm->tmem_full[acc], use & 1);
+      ptx::tc_fence_after();
+      float l1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) l1[i] = 0.f;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
+        const int n = n0 + c0 + c4;
+        float4 xv[8], pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {           // x0 rows for the weighted map, in flight while TMEM loads
+          const long long tok = m0 + quarter * 32 + i * 4 + r_sub;
+          if (tok < P) {
+            xv[i] = *reinterpret_cast<const float4*>(x + tok * C + n);
+            pv[i] = *reinterpret_cast<const float4*>(pos + (tok / HW) * pos_bstride + (tok % HW) * (long long)C + n);
+          }
+        }
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bs + n));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + r_sub;
+          const long long tok = m0 + quarter * 32 + r;
+          if (tok >= P) continue;
+          const int b = (int)(tok / HW);
+          const float4 sg = __ldg(reinterpret_cast<const float4*>(sig + (size_t)b * C + n));
+          const float4 iv = __ldg(reinterpret_cast<const float4*>(inv + (size_t)b * C + n));
+          const float* sp = stage + r * 33 + c4;
+          const float s0 = fmaxf(sp[0] + b4.x, 0.f), s1 = fmaxf(sp[1] + b4.y, 0.f), s2 = fmaxf(sp[2] + b4.z, 0.f),
+                      s3 = fmaxf(sp[3] + b4.w, 0.f);
+          float4 o;
+          o.x = (sg.x * __fdividef(1.0f, 1.0f + __expf(-s0))) * (xv[i].x + pv[i].x);
+          o.y = (sg.y * __fdividef(1.0f, 1.0f + __expf(-s1))) * (xv[i].y + pv[i].y);
+          o.z = (sg.z * __fdividef(1.0f, 1.0f + __expf(-s2))) * (xv[i].z + pv[i].z);
+          o.w = (sg.w * __fdividef(1.0f, 1.0f + __expf(-s3))) * (xv[i].w + pv[i].w);
+          *reinterpret_cast<float4*>(xw + tok * C + n) = o;
+          l1[i] += (fabsf(iv.x * s0) + fabsf(iv.y * s1)) + (fabsf(iv.z * s2) + fabsf(iv.w * s3));
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm->tmem_empty[acc]);
+      // per-token L1 over this tile's BN channels: reduce the 8 lanes that share a row
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = l1[i];
+        v += __shfl_xor_sync(kFull, v, 1);
+        v += __shfl_xor_sync(kFull, v, 2);
+        v += __shfl_xor_sync(kFull, v, 4);
+        const long long tok = m0 + quarter * 32 + i * 4 + r_sub;
+        if ((lane & 7) == 0 && tok < P) l1_out[(long long)n_tile * P + tok] = v;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+int make_tmap_f32_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows);
+
+// returns the number of channel slices (partials) written to l1_part, or <0 / >0 on error (negated for CUDA errors)
+int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv, float* l1_part, int* n_slices, cudaStream_t st) {
+  const sast_geom& g = a->g;
+  const long long P = (long long)g.B * g.H * g.W;
+  const int C = g.C;
+  const int BN = C % 128 == 0 ? 128 : (C % 64 == 0 ? 64 : 32);
+  CUtensorMap mh, ml;
+  int rc = make_tmap_f32_box(&mh, a->score_w_hi, C, C, C, SC_BK, BN);
+  if (rc) return rc;
+  rc = make_tmap_f32_box(&ml, a->score_w_lo, C, C, C, SC_BK, BN);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)SC_STAGES * (2 * SC_BM * SC_BK * 4 + 2 * (size_t)BN * SC_BK * 4) + sizeof(ScSmem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long tiles = ((P + SC_BM - 1) / SC_BM) * (C / BN);
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  score_tc_kernel<<<grid, SC_THREADS, smem, st>>>(mh, ml, a->x, a->pos, a->pos_batch_stride, a->score_b, sig, inv, g.H * g.W, C, BN, P,
+                                                  a->xw, l1_part);
+  SAST_LAUNCH_CHECK();
+  *n_slices = C / BN;
+  return SAST_OK;
+}
+
+}  // namespace sast

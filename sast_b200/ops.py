@@ -67,7 +67,9 @@ def _(x):
 # --------------------------------------------------------------------------------------------
 @torch.library.custom_op("sast::score_fwd", mutates_args=())
 def score_fwd(x: Tensor, pos: Tensor, r: Tensor, ctrl_w: Tensor, score_w: Tensor, score_b: Tensor,
-              amp: float) -> Tuple[Tensor, Tensor]:
+              amp: float, score_w_hi: Optional[Tensor] = None, score_w_lo: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """score_w_hi / score_w_lo (see :func:`split_tf32`) select the 3xTF32 tensor-core kernel; without them the
+    fp32 CUDA-core kernel runs."""
     x = _f32c(x, "x")
     B, H, W, Cc = x.shape
     pos = _f32c(pos, "pos")
@@ -78,17 +80,28 @@ def score_fwd(x: Tensor, pos: Tensor, r: Tensor, ctrl_w: Tensor, score_w: Tensor
     r = _f32c(r, "r")
     xw = torch.empty_like(x)
     tok = torch.empty(B, H, W, device=x.device, dtype=torch.float32)
-    scratch = torch.empty(2 * B * Cc + ((Cc + 63) // 64) * B * H * W, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(2 * B * Cc + (Cc // 32) * B * H * W, device=x.device, dtype=torch.float32)
     a = L.ScoreArgs(_geom(B, H, W, Cc, 1, 1), x.data_ptr(), pos.data_ptr(), pstride, r.data_ptr(), r.shape[1],
                     _f32c(ctrl_w, "ctrl_w").data_ptr(), _f32c(score_w, "score_w").data_ptr(),
                     _f32c(score_b, "score_b").data_ptr(), float(amp), xw.data_ptr(), tok.data_ptr(),
-                    scratch.data_ptr())
+                    scratch.data_ptr(), L.ptr(score_w_hi), L.ptr(score_w_lo))
     L.check(L.lib().sast_score_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_score_fwd")
     return xw, tok
 
 
+def split_tf32(w: Tensor) -> Tuple[Tensor, Tensor]:
+    """w = hi + lo (+ ~2^-22 |w|) with both halves representable in TF32 (round to nearest, ties away,
+    like cvt.rna.tf32.f32): the weight operands of the 3xTF32 scoring GEMM."""
+    def rna(t):
+        bits = t.contiguous().view(torch.int32)
+        return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    w = w.detach().float().contiguous()
+    hi = rna(w)
+    return hi, rna(w - hi)
+
+
 @score_fwd.register_fake
-def _(x, pos, r, ctrl_w, score_w, score_b, amp):
+def _(x, pos, r, ctrl_w, score_w, score_b, amp, score_w_hi=None, score_w_lo=None):
     return torch.empty_like(x, dtype=torch.float32), x.new_empty(x.shape[:3], dtype=torch.float32)
 
 
@@ -102,7 +115,7 @@ def add_pos(x: Tensor, pos: Tensor) -> Tensor:
     pstride = 0 if pos.dim() == 3 else H * W * Cc
     out = torch.empty_like(x)
     a = L.ScoreArgs(_geom(B, H, W, Cc, 1, 1), x.data_ptr(), pos.data_ptr(), pstride, 0, 0, 0, 0, 0, 0.0,
-                    out.data_ptr(), 0, 0)
+                    out.data_ptr(), 0, 0, 0, 0)
     L.check(L.lib().sast_score_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_score_fwd(add_pos)")
     return out
 

@@ -315,6 +315,18 @@ class SAST_block(nn.Module):
         self.first_block = first_block
         self.B, self.N, self.dim = None, None, dim
 
+    def _score_split(self):
+        """TF32 hi/lo halves of to_scores.weight for the tensor-core scoring kernel (cached); (None, None)
+        selects the fp32 CUDA-core kernel (precision FP32 = validation grade)."""
+        if self.win_attn.precision == L.FP32:
+            return None, None
+        w = self.to_scores.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_split_key", None) != key:
+            self._split = ops.split_tf32(w)
+            self._split_key = key
+        return self._split
+
     @staticmethod
     def _position(pos_emb, x: Tensor) -> Tensor:
         """[H,W,C] table when the callable can provide one (no B-fold repeat), else its output."""
@@ -338,8 +350,9 @@ class SAST_block(nn.Module):
         self.B, self.N = B, N
         pos = self._position(pos_emb, x)
         if self.first_block:
+            w_hi, w_lo = self._score_split()
             xw, tok = ops.score_fwd(x, pos, r, self.to_controls.weight, self.to_scores.weight, self.to_scores.bias,
-                                    float(self.amp_value))
+                                    float(self.amp_value), w_hi, w_lo)
             thr_w, thr_t = ops.thresholds(N, T, self.bounce_value)
             pool1, pool2 = ops.select_pair(tok, p0, p1, thr_w, thr_t)
             sel1 = ops.Selection(pool1, B, H, W, p0, p1)

@@ -49,6 +49,13 @@ def test_score_fwd(B, H, W, C):
                             p["to_scores.weight"].to(DEV), p["to_scores.bias"].to(DEV), amp)
     assert (xw.cpu() - xw_ref).abs().max() < 2e-5
     assert ((tok.cpu() - tok_ref).abs() / tok_ref.abs().clamp_min(1e-12)).max() < 2e-5
+    # 3xTF32 tensor-core kernel (what the bf16 precision mode runs): same bars
+    w_hi, w_lo = ops.split_tf32(p["to_scores.weight"].to(DEV))
+    assert (w_hi + w_lo - p["to_scores.weight"].to(DEV)).abs().max() < 1e-6
+    xw3, tok3 = ops.score_fwd(x.to(DEV), pos.to(DEV), r.to(DEV), p["to_controls.weight"].to(DEV),
+                              p["to_scores.weight"].to(DEV), p["to_scores.bias"].to(DEV), amp, w_hi, w_lo)
+    assert (xw3.cpu() - xw_ref).abs().max() < 2e-5
+    assert ((tok3.cpu() - tok_ref).abs() / tok_ref.abs().clamp_min(1e-12)).max() < 2e-5
     # batched pos (reference-style repeated tensor) gives the same result
     xw2, tok2 = ops.score_fwd(x.to(DEV), pos[None].repeat(B, 1, 1, 1).to(DEV), r.to(DEV), p["to_controls.weight"].to(DEV),
                               p["to_scores.weight"].to(DEV), p["to_scores.bias"].to(DEV), amp)
@@ -71,3 +78,32 @@ def test_gemm_tcgen05(M, N, K):
     Db = ops.gemm_bf16(A.to(DEV), Wt.to(DEV), None, out_bf16=True)
     ref_b = (A.float() @ Wt.float().t())
     assert (Db.float().cpu() - ref_b).abs().max() < 4e-2
+
+
+@pytest.mark.parametrize("tensor_core", [False, True], ids=["fp32-fma", "tf32x3-tcgen05"])
+def test_score_to_selection_flip_rate(tensor_core):
+    """Tier B end to end at the 1 Mpx stage-1 map size: scoring GEMM -> per-token score -> softmax ->
+    threshold on the GPU against the reference pipeline on the CPU.  A flip needs a probability within
+    rounding distance of the threshold: <= 1e-4 of the tokens."""
+    B, H, W, C, part = 2, 96, 160, 64, (6, 10)
+    T, N = 60, 96 * 160 // 60
+    shapes = {"to_scores.weight": (C, C), "to_scores.bias": (C,), "to_controls.weight": (C, 20)}
+    p = make_params(shapes, seed=5)
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(B, H, W, C, generator=gen) * torch.linspace(0.3, 1.7, W).view(1, 1, W, 1)
+    r = torch.rand(B, 20, generator=gen) * 0.02
+    pos = O.position_table(H, W, C)
+    amp = 2e-3
+    _, scores = O.scoring(x, pos, r, p, part, amp)                      # [B,N,T,C] window-partitioned
+    lists = O.select_layer(scores, T, 1e-3)
+    ref = torch.zeros(B * N * T, dtype=torch.bool)
+    ref[lists[0][lists[3] // T] * T + lists[3] % T] = True
+    hi_lo = ops.split_tf32(p["to_scores.weight"].to(DEV)) if tensor_core else (None, None)
+    _, tok = ops.score_fwd(x.to(DEV), pos.to(DEV), r.to(DEV), p["to_controls.weight"].to(DEV),
+                           p["to_scores.weight"].to(DEV), p["to_scores.bias"].to(DEV), amp, *hi_lo)
+    thr_w, thr_t = ops.thresholds(N, T, 1e-3)
+    sel = ops.Selection(ops.select(tok, 6, 10, L.WINDOW, thr_w, thr_t), B, H, W, 6, 10)
+    got = (sel.tok_row >= 0).cpu()
+    flips = int((got != ref).sum())
+    assert 0.2 < ref.float().mean() < 0.9           # a genuinely partial selection
+    assert flips <= 1e-4 * ref.numel() + 1, f"{flips} flips of {ref.numel()}"
