@@ -347,14 +347,14 @@ __global__ void __launch_bounds__(256) rows_copy_kernel(float* __restrict__ map,
 
 template <bool GATHER>
 static int launch_rows_copy(float* map, float* rows, const sast_selection* sel, int C, cudaStream_t st) {
-  // few lanes per row, each with up to 4 x 16 bytes, 4 rows per lane group: 16-64 independent 16-byte
-  // requests in flight per lane keep HBM busy (the kernel is pure data movement)
+  // a row is read by consecutive lanes (whole 128-byte lines per request), 4 rows per lane group in flight
+  // (measured: wider per-lane strips -- 4 lanes x 64 B per row -- lose ~7 % of bandwidth to partial lines)
   const dim3 grid(148 * 8), block(256);
-  if (C <= 32) rows_copy_kernel<GATHER, 2, 4><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 64) rows_copy_kernel<GATHER, 4, 4><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 96) rows_copy_kernel<GATHER, 8, 3><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 128) rows_copy_kernel<GATHER, 8, 4><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 256) rows_copy_kernel<GATHER, 16, 4><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  if (C <= 32) rows_copy_kernel<GATHER, 8, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 64) rows_copy_kernel<GATHER, 16, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 96) rows_copy_kernel<GATHER, 32, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 128) rows_copy_kernel<GATHER, 32, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 256) rows_copy_kernel<GATHER, 32, 2><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
   else if (C <= 512) rows_copy_kernel<GATHER, 32, 4><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
   else if (C <= 1024) rows_copy_kernel<GATHER, 32, 8><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
   else return SAST_E_UNSUPPORTED;

@@ -6,26 +6,30 @@
 //     a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi          (dropped term ~2^-22 |a||w|)
 // Three kind::tf32 MMAs per 8-wide k-step, fp32 accumulation in TMEM.
 //
-// Persistent CTAs, 9 warps:
+// Persistent CTAs, 13 warps:
 //   warps 0-3  loaders: x + pos formed on the fly (coalesced float4 rows), split into hi/lo and written
 //              to shared memory in the SWIZZLE_128B K-major operand layout; lane 0 also TMA-loads the
 //              pre-split weight tiles (W_hi, W_lo: [C,C] fp32, K-major like nn.Linear.weight)
-//   warps 4-7  epilogue: TMEM -> shared-memory transpose -> coalesced rows: STP-weighted map
-//              xw = sigmoid(ctrl) sigmoid(s) x0 and the per-token L1  sum_c |amp/ctrl_c s_c|
-//   warp 8     TMEM allocator + MMA issuer; two accumulators (tile i drains while tile i+1 multiplies)
+//   warps 4-11 epilogue, two groups of 4 (one TMEM accumulator each, tiles round-robin): TMEM ->
+//              shared-memory transpose -> coalesced rows: STP-weighted map xw = sigmoid(ctrl) sigmoid(s) x0
+//              and the per-token L1  sum_c |amp/ctrl_c s_c|.  The epilogue is the long pole (a sigmoid and
+//              ~20 flops per output), hence 8 of the 13 warps.
+//   warp 12    TMEM allocator + MMA issuer
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace sast {
 
 constexpr int SC_BM = 128, SC_BK = 32, SC_STAGES = 2;
-constexpr int SC_THREADS = 9 * 32;
+constexpr int SC_GROUPS = 2;                     // epilogue groups = TMEM accumulators
+constexpr int SC_MMA_WARP = 4 + 4 * SC_GROUPS;
+constexpr int SC_THREADS = (SC_MMA_WARP + 1) * 32;
 
 struct ScSmem {
   uint64_t full[SC_STAGES];
   uint64_t empty[SC_STAGES];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[SC_GROUPS];
+  uint64_t tmem_empty[SC_GROUPS];
   uint32_t tmem_base;
 };
 
@@ -53,15 +57,16 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
                                                                  const float* __restrict__ sig, const float* __restrict__ inv,
                                                                  int HW, int C, int BN, long long P, float* __restrict__ xw,
                                                                  float* __restrict__ l1_out) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ float stage_smem[4][32 * 33];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];     // ring | ScSmem | epilogue transpose tiles
   const int m_tiles = (int)((P + SC_BM - 1) / SC_BM), n_tiles = C / BN;
   const int total_tiles = m_tiles * n_tiles;
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem_raw;                                       // 1024-byte aligned (checked below)
   const uint32_t a_bytes = SC_BM * SC_BK * 4;                     // 16 KB per half
   const uint32_t w_bytes = (uint32_t)BN * SC_BK * 4;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;         // A_hi, A_lo, W_hi, W_lo
-  ScSmem* sm = reinterpret_cast<ScSmem*>(base + (size_t)SC_STAGES * stage_bytes);
+  ScSmem* sm = reinterpret_cast<ScSmem*>(smem_raw + (size_t)SC_STAGES * stage_bytes);
+  float* stage_all = reinterpret_cast<float*>(smem_raw + (size_t)SC_STAGES * stage_bytes + 256);
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = C / SC_BK;
 
@@ -69,11 +74,12 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
     ptx::tma_prefetch_desc(&map_whi);
     ptx::tma_prefetch_desc(&map_wlo);
     for (int s = 0; s < SC_STAGES; ++s) { ptx::mbar_init(&sm->full[s], 129); ptx::mbar_init(&sm->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&sm->tmem_full[a], 1); ptx::mbar_init(&sm->tmem_empty[a], 4); }
+    for (int a = 0; a < SC_GROUPS; ++a) { ptx::mbar_init(&sm->tmem_full[a], 1); ptx::mbar_init(&sm->tmem_empty[a], 4); }
     ptx::fence_barrier_init();
   }
-  const uint32_t tmem_cols = (uint32_t)(2 * BN) < 32u ? 32u : (uint32_t)(2 * BN);
-  if (warp == 8) ptx::tmem_alloc(&sm->tmem_base, tmem_cols);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(SC_GROUPS * BN)) tmem_cols <<= 1;
+  if (warp == SC_MMA_WARP) ptx::tmem_alloc(&sm->tmem_base, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -86,27 +92,35 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
     const int rbase = t >> 3;                  // rows rbase, rbase+16, ... (8 rows per thread)
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const long long m0 = (long long)(tile / n_tiles) * SC_BM;
+      const int m0 = (tile / n_tiles) * SC_BM;
       const int n0 = (tile % n_tiles) * BN;
+      int xo[8], po[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int tok = m0 + rbase + 16 * j;
+        const bool ok = tok < (int)P;
+        const int b = ok ? tok / HW : 0;
+        xo[j] = ok ? tok * C + chunk * 4 : -1;
+        po[j] = (int)(b * pos_bstride) + (ok ? tok - b * HW : 0) * C + chunk * 4;
+      }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t s = it % SC_STAGES, round = it / SC_STAGES;
+        float4 xv[8], pv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {         // global loads first: they do not depend on the ring slot
+          if (xo[j] >= 0) {
+            xv[j] = *reinterpret_cast<const float4*>(x + xo[j] + kb * SC_BK);
+            pv[j] = *reinterpret_cast<const float4*>(pos + po[j] + kb * SC_BK);
+          } else {
+            xv[j] = make_float4(0.f, 0.f, 0.f, 0.f); pv[j] = xv[j];
+          }
+        }
         ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
         uint8_t* st = base + (size_t)s * stage_bytes;
         if (t == 0) {
           ptx::mbar_arrive_expect_tx(&sm->full[s], 2 * w_bytes);
           ptx::tma_load_2d(st + 2 * a_bytes, &map_whi, &sm->full[s], kb * SC_BK, n0);
           ptx::tma_load_2d(st + 2 * a_bytes + w_bytes, &map_wlo, &sm->full[s], kb * SC_BK, n0);
-        }
-        float4 xv[8], pv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const long long tok = m0 + rbase + 16 * j;
-          if (tok < P) {
-            xv[j] = *reinterpret_cast<const float4*>(x + tok * C + kb * SC_BK + chunk * 4);
-            pv[j] = *reinterpret_cast<const float4*>(pos + (tok / HW) * pos_bstride + (tok % HW) * (long long)C + kb * SC_BK + chunk * 4);
-          } else {
-            xv[j] = make_float4(0.f, 0.f, 0.f, 0.f); pv[j] = xv[j];
-          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -121,13 +135,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
         ptx::mbar_arrive(&sm->full[s]);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == SC_MMA_WARP) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(SC_BM, (uint32_t)BN);
       uint32_t it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t acc = ti & 1, use = ti >> 1;
+        const uint32_t acc = ti % SC_GROUPS, use = ti / SC_GROUPS;
         ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
@@ -151,17 +165,30 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
       }
     }
   } else {
-    // ---------------- epilogue (warps 4..7, TMEM lane quarter = warp % 4) ----------------
+    // ---------------- epilogue (warps 4..15: group = (warp-4)/4, TMEM lane quarter = warp % 4) ----------------
+    const int group = (warp - 4) >> 2;
     const int quarter = warp & 3;
-    float* stage = &stage_smem[quarter][0];
+    float* stage = stage_all + (warp - 4) * (32 * 33);
     const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-      const uint32_t acc = ti & 1, use = ti >> 1;
-      const long long m0 = (long long)(tile / n_tiles) * SC_BM;
+      if ((int)(ti % SC_GROUPS) != group) continue;
+      const uint32_t use = ti / SC_GROUPS;
+      const int m0 = (tile / n_tiles) * SC_BM;
       const int n_tile = tile % n_tiles, n0 = n_tile * BN;
-      const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN + ((uint32_t)(quarter * 32) << 16);
-      ptx::mbar_wait(&sm->tmem_full[acc], use & 1);
+      const uint32_t tmem_d = tmem_base + (uint32_t)group * (uint32_t)BN + ((uint32_t)(quarter * 32) << 16);
+      // per-row element offsets of this lane's 8 rows (hoisted out of the column loop; < 2^31, checked on the host)
+      int xo[8], po[8], co[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int tok = m0 + quarter * 32 + i * 4 + r_sub;
+        const bool ok = tok < (int)P;
+        const int b = ok ? tok / HW : 0;
+        xo[i] = ok ? tok * C + c4 : -1;
+        po[i] = (int)(b * pos_bstride) + (ok ? tok - b * HW : 0) * C + c4;
+        co[i] = b * C + c4;
+      }
+      ptx::mbar_wait(&sm->tmem_full[group], use & 1);
       ptx::tc_fence_after();
       float l1[8];
 #pragma unroll
@@ -169,45 +196,39 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t raw[32];
         ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
-        const int n = n0 + c0 + c4;
-        float4 xv[8], pv[8];
+        const int nc = n0 + c0;
+        float4 xv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {           // x0 rows for the weighted map, in flight while TMEM loads
-          const long long tok = m0 + quarter * 32 + i * 4 + r_sub;
-          if (tok < P) {
-            xv[i] = *reinterpret_cast<const float4*>(x + tok * C + n);
-            pv[i] = *reinterpret_cast<const float4*>(pos + (tok / HW) * pos_bstride + (tok % HW) * (long long)C + n);
-          }
-        }
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bs + n));
+        for (int i = 0; i < 8; ++i)             // x rows for the weighted map, in flight while TMEM loads
+          if (xo[i] >= 0) xv[i] = *reinterpret_cast<const float4*>(x + xo[i] + nc);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bs + nc + c4));
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          if (xo[i] < 0) continue;
           const int r = i * 4 + r_sub;
-          const long long tok = m0 + quarter * 32 + r;
-          if (tok >= P) continue;
-          const int b = (int)(tok / HW);
-          const float4 sg = __ldg(reinterpret_cast<const float4*>(sig + (size_t)b * C + n));
-          const float4 iv = __ldg(reinterpret_cast<const float4*>(inv + (size_t)b * C + n));
+          const float4 sg = __ldg(reinterpret_cast<const float4*>(sig + co[i] + nc));
+          const float4 iv = __ldg(reinterpret_cast<const float4*>(inv + co[i] + nc));
+          const float4 pv = __ldg(reinterpret_cast<const float4*>(pos + po[i] + nc));      // small table, cache resident
           const float* sp = stage + r * 33 + c4;
           const float s0 = fmaxf(sp[0] + b4.x, 0.f), s1 = fmaxf(sp[1] + b4.y, 0.f), s2 = fmaxf(sp[2] + b4.z, 0.f),
                       s3 = fmaxf(sp[3] + b4.w, 0.f);
           float4 o;
-          o.x = (sg.x * __fdividef(1.0f, 1.0f + __expf(-s0))) * (xv[i].x + pv[i].x);
-          o.y = (sg.y * __fdividef(1.0f, 1.0f + __expf(-s1))) * (xv[i].y + pv[i].y);
-          o.z = (sg.z * __fdividef(1.0f, 1.0f + __expf(-s2))) * (xv[i].z + pv[i].z);
-          o.w = (sg.w * __fdividef(1.0f, 1.0f + __expf(-s3))) * (xv[i].w + pv[i].w);
-          *reinterpret_cast<float4*>(xw + tok * C + n) = o;
+          o.x = (sg.x * __fdividef(1.0f, 1.0f + __expf(-s0))) * (xv[i].x + pv.x);
+          o.y = (sg.y * __fdividef(1.0f, 1.0f + __expf(-s1))) * (xv[i].y + pv.y);
+          o.z = (sg.z * __fdividef(1.0f, 1.0f + __expf(-s2))) * (xv[i].z + pv.z);
+          o.w = (sg.w * __fdividef(1.0f, 1.0f + __expf(-s3))) * (xv[i].w + pv.w);
+          *reinterpret_cast<float4*>(xw + xo[i] + nc) = o;
           l1[i] += (fabsf(iv.x * s0) + fabsf(iv.y * s1)) + (fabsf(iv.z * s2) + fabsf(iv.w * s3));
         }
         __syncwarp();
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&sm->tmem_empty[acc]);
+      if (lane == 0) ptx::mbar_arrive(&sm->tmem_empty[group]);
       // per-token L1 over this tile's BN channels: reduce the 8 lanes that share a row
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -215,14 +236,14 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
         v += __shfl_xor_sync(kFull, v, 1);
         v += __shfl_xor_sync(kFull, v, 2);
         v += __shfl_xor_sync(kFull, v, 4);
-        const long long tok = m0 + quarter * 32 + i * 4 + r_sub;
-        if ((lane & 7) == 0 && tok < P) l1_out[(long long)n_tile * P + tok] = v;
+        const int tok = m0 + quarter * 32 + i * 4 + r_sub;
+        if ((lane & 7) == 0 && tok < (int)P) l1_out[(long long)n_tile * P + tok] = v;
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == SC_MMA_WARP) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -241,10 +262,12 @@ int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv
   if (rc) return rc;
   rc = make_tmap_f32_box(&ml, a->score_w_lo, C, C, C, SC_BK, BN);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)SC_STAGES * (2 * SC_BM * SC_BK * 4 + 2 * (size_t)BN * SC_BK * 4) + sizeof(ScSmem);
+  if (P * C >= (1ll << 31)) return SAST_E_UNSUPPORTED;        // 32-bit element offsets inside the kernel
+  const size_t smem = (size_t)SC_STAGES * (2 * SC_BM * SC_BK * 4 + 2 * (size_t)BN * SC_BK * 4) + 256 +
+                      (size_t)4 * SC_GROUPS * 32 * 33 * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
