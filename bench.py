@@ -92,7 +92,7 @@ def build_net(workload, precision, device):
     net = net.to(device).eval()
     prec = L.FP32 if precision == "fp32" else L.BF16
     for m in net.modules():
-        if isinstance(m, sast_b200.MS_WSA):
+        if isinstance(m, (sast_b200.MS_WSA, sast_b200.DWSConvLSTM2d)):
             m.precision = prec
     return net
 

@@ -217,6 +217,16 @@ int sast_layernorm(const float* x, const float* weight, const float* bias, float
 int sast_lstm_gates(const float* mix, const float* bias, const float* c_prev, int64_t P, int32_t C, float* h_out,
                     float* c_out, void* stream);
 
+/*
+ * Conv-LSTM cell as one kernel (ref: models/layers/rnn.py:36-69 with dws_conv False): the 1x1 conv of
+ * [x | h_prev] as a TF32 tcgen05 GEMM straight from the fp32 NHWC maps, gates in the epilogue.
+ * x, h_prev, c_prev, h_out, c_out: [P,C] fp32 (NHWC rows); h_prev/c_prev both NULL = zero state.
+ * w_packed [4C,K] fp32, K = C (zero state) or 2C, rows interleaved 4*c + {forget,input,output,cell};
+ * bias_packed [4C] in the same order (may be NULL).
+ */
+int sast_lstm_fwd(const float* x, const float* h_prev, const float* c_prev, const float* w_packed,
+                  const float* bias_packed, int64_t P, int32_t C, float* h_out, float* c_out, void* stream);
+
 /* D[M,N] = A[M,K] W[N,K]^T (+bias): bf16 in, fp32 accumulate on tcgen05, fp32 or bf16 out.
  * Exposed for unit tests of the tensor-core path. */
 int sast_gemm_bf16(const uint16_t* A, const uint16_t* W, const float* bias, void* D, int32_t d_is_bf16,

@@ -16,8 +16,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib as L
 from . import ops
-from .sast import SAST_block
+from .sast import SAST_block, default_precision
 
 Tensor = torch.Tensor
 LstmState = Optional[Tuple[Tensor, Tensor]]
@@ -133,35 +134,48 @@ class DWSConvLSTM2d(nn.Module):
         self.conv1x1 = nn.Conv2d(xh_dim, gates_dim, kernel_size=1)
         self.conv_only_hidden = dws_conv_only_hidden
         self.cell_update_dropout = nn.Dropout(p=cell_update_dropout)
+        self.precision = default_precision()     # BF16 (tensor-core mode): fused TF32 tcgen05 kernel; FP32: cuDNN conv + gate kernel
 
-    def _weights(self, C: int):
-        """(W_x [4C,C,1,1], W_full [4C,2C,1,1]) channels-last, cached: with a zero initial state only the
-        x-half of the 1x1 conv contributes (half the GEMM, no concat)."""
-        w = self.conv1x1.weight
-        key = (w.data_ptr(), w._version)
+    def _packed(self, C: int):
+        """1x1-conv weights for the fused kernel, cached: rows interleaved 4*c + {f,i,o,g} so that one
+        accumulator chunk holds all four gates of a channel; (W_x [4C,C] for a zero initial state -- only
+        the x-half of the conv contributes --, W_full [4C,2C], bias [4C])."""
+        w, b = self.conv1x1.weight, self.conv1x1.bias
+        key = (w.data_ptr(), w._version, None if b is None else b._version)
         if getattr(self, "_wkey", None) != key:
-            wd = w.detach()
-            self._wx = wd[:, :C].contiguous(memory_format=torch.channels_last)
-            self._wfull = wd.contiguous(memory_format=torch.channels_last)
+            w2 = w.detach().float().reshape(4, C, 2 * C).permute(1, 0, 2).reshape(4 * C, 2 * C)
+            self._wfull = w2.contiguous()
+            self._wx = w2[:, :C].contiguous()
+            self._bp = None if b is None else b.detach().float().reshape(4, C).t().reshape(-1).contiguous()
             self._wkey = key
-        return self._wx, self._wfull
+        return self._wx, self._wfull, self._bp
 
     def forward(self, x: Tensor, h_and_c_previous: LstmState = None) -> Tuple[Tensor, Tensor]:
         """x: [N,C,H,W] (any memory format; channels-last makes every step copy-free).  Returns
         (h, c) as NCHW-logical tensors over channels-last memory."""
-        if isinstance(self.conv3x3_dws, nn.Identity) and not (torch.is_grad_enabled() and self.conv1x1.weight.requires_grad) \
-                and not self.training:
+        fusable = isinstance(self.conv3x3_dws, nn.Identity) and not self.training and self.dim % 8 == 0 and \
+            not (torch.is_grad_enabled() and self.conv1x1.weight.requires_grad)
+        if fusable and self.precision == L.FP32:
+            # validation grade: the 1x1 conv through cuDNN/cuBLAS (fp32 when TF32 is disabled), gates fused
             C = self.dim
-            wx, wfull = self._weights(C)
+            w = self.conv1x1.weight
             x = x.contiguous(memory_format=torch.channels_last)
             if h_and_c_previous is None:
-                mix = F.conv2d(x, wx, None)
-                c_prev = None
+                mix, c_prev = F.conv2d(x, w[:, :C], None), None
             else:
                 h_tm1, c_tm1 = h_and_c_previous
-                mix = F.conv2d(torch.cat((x, h_tm1.contiguous(memory_format=torch.channels_last)), dim=1), wfull, None)
+                mix = F.conv2d(torch.cat((x, h_tm1.contiguous(memory_format=torch.channels_last)), dim=1), w, None)
                 c_prev = c_tm1.permute(0, 2, 3, 1)
-            h, c = ops.lstm_gates(mix.permute(0, 2, 3, 1), self.conv1x1.bias, c_prev)          # NHWC; bias folded in
+            h, c = ops.lstm_gates(mix.permute(0, 2, 3, 1), self.conv1x1.bias, c_prev)
+            return h.permute(0, 3, 1, 2), c.permute(0, 3, 1, 2)
+        if fusable:
+            wx, wfull, bp = self._packed(self.dim)
+            xl = x.permute(0, 2, 3, 1)                                   # NHWC view (no copy for channels-last x)
+            if h_and_c_previous is None:
+                h, c = ops.lstm_fwd(xl, None, None, wx, bp)
+            else:
+                h_tm1, c_tm1 = h_and_c_previous
+                h, c = ops.lstm_fwd(xl, h_tm1.permute(0, 2, 3, 1), c_tm1.permute(0, 2, 3, 1), wfull, bp)
             return h.permute(0, 3, 1, 2), c.permute(0, 3, 1, 2)
         return self._forward_reference(x, h_and_c_previous)
 

@@ -45,8 +45,9 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 // accumulator) drain tile i while tile i+1 is being loaded and multiplied.
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_a2, int k_split,
                                                                 const __grid_constant__ CUtensorMap map_w,
-                                                                const float* __restrict__ bias, int N, int K, int BN,
+                                                                const float* __restrict__ bias, int N, int K, int BN, int stages,
                                                                 const int* __restrict__ counts, int m_static, EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float stage_smem[(EPI == EPI_STORE || EPI == EPI_RESID) ? TC_EPI_WARPS : 1][32 * 33];   // epilogue transpose tiles
@@ -58,19 +59,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = TC_BM * TC_BK * 2, w_bytes = (uint32_t)BN * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + w_bytes;
-  TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)TC_STAGES * stage_bytes);
+  TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)stages * stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (K + TC_BK - 1) / TC_BK;
+  // operand element: bf16 (64 per 128-byte k-block row) or, for EPI_LSTM, fp32 read as TF32 (32 per row)
+  constexpr bool kTf32 = (EPI == EPI_LSTM);
+  constexpr int kBK = kTf32 ? 32 : TC_BK;
+  constexpr int kKStep = kTf32 ? 8 : 16;
+  const int nkb = (K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&map_a);
     ptx::tma_prefetch_desc(&map_w);
-    for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&sm->full[s], 1); ptx::mbar_init(&sm->empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { ptx::mbar_init(&sm->full[s], 1); ptx::mbar_init(&sm->empty[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&sm->tmem_full[a], 1); ptx::mbar_init(&sm->tmem_empty[a], 4); }
     ptx::fence_barrier_init();
   }
-  const uint32_t tmem_cols = BN <= 16 ? 32u : (uint32_t)(2 * BN);   // two accumulators; BN in {32,64,128}
+  uint32_t tmem_cols = 32;                                          // two accumulators of BN columns, power of two
+  while (tmem_cols < (uint32_t)(2 * BN)) tmem_cols <<= 1;
   if (warp == 1) ptx::tmem_alloc(&sm->tmem_base, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
@@ -83,18 +89,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % TC_STAGES, round = it / TC_STAGES;
+          const uint32_t s = it % (uint32_t)stages, round = it / (uint32_t)stages;
           ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
           uint8_t* sa = base + (size_t)s * stage_bytes;
           ptx::mbar_arrive_expect_tx(&sm->full[s], stage_bytes);
-          ptx::tma_load_2d(sa, &map_a, &sm->full[s], kb * TC_BK, m0);
-          ptx::tma_load_2d(sa + a_bytes, &map_w, &sm->full[s], kb * TC_BK, n0);
+          const int k0 = kb * kBK;
+          if (k0 < k_split) ptx::tma_load_2d(sa, &map_a, &sm->full[s], k0, m0);
+          else ptx::tma_load_2d(sa, &map_a2, &sm->full[s], k0 - k_split, m0);      // second A source ([x | h_prev])
+          ptx::tma_load_2d(sa + a_bytes, &map_w, &sm->full[s], k0, n0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(TC_BM, (uint32_t)BN);
+      const uint32_t idesc = kTf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)BN >> 3) << 17) | ((TC_BM >> 4) << 24))
+                                   : ptx::umma_idesc_bf16(TC_BM, (uint32_t)BN);
       uint32_t it = 0, ti = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1, use = ti >> 1;
@@ -102,17 +111,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % TC_STAGES, round = it / TC_STAGES;
+          const uint32_t s = it % (uint32_t)stages, round = it / (uint32_t)stages;
           ptx::mbar_wait(&sm->full[s], round & 1);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
           const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
           const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
-          const int krem = K - kb * TC_BK;
-          const int ksteps = krem >= TC_BK ? 4 : (krem + 15) / 16;
+          const int krem = K - kb * kBK;
+          const int ksteps = krem >= kBK ? 4 : (krem + kKStep - 1) / kKStep;
           for (int k = 0; k < ksteps; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
-            ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            // advance one k-step = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+            if (kTf32) ptx::umma_tf32_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            else ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           }
           ptx::umma_commit(&sm->empty[s]);          // frees the smem slot when these MMAs retire
         }
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           __syncwarp();
         }
       } else {
-        // GLU (narrow bf16 rows) and SCATTER (rows land on scattered pixels): every lane finishes its own row
+        // GLU / LSTM (narrow rows) and SCATTER (rows land on scattered pixels): every lane finishes its own row
         const int row = m0 + quarter * 32 + lane;
         const bool row_ok = row < M;
         long long pix = 0;
@@ -212,6 +222,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n / 2;
             store_bf16x8(dst, o);
             store_bf16x8(dst + 8, o + 8);
+          } else if (EPI == EPI_LSTM) {
+            // 32 columns = 8 channels x [forget, input, output, cell-input]   (models/layers/rnn.py:58-69)
+            const int ch = n / 4;
+            float cp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (ep.resid) {
+              const float4 c0v = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + ch);
+              const float4 c1v = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + ch + 4);
+              cp[0] = c0v.x; cp[1] = c0v.y; cp[2] = c0v.z; cp[3] = c0v.w; cp[4] = c1v.x; cp[5] = c1v.y; cp[6] = c1v.z; cp[7] = c1v.w;
+            }
+            float hn[8], cn[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float f = __fdividef(1.0f, 1.0f + __expf(-v[4 * j])), ig = __fdividef(1.0f, 1.0f + __expf(-v[4 * j + 1]));
+              const float og = __fdividef(1.0f, 1.0f + __expf(-v[4 * j + 2]));
+              const float g = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v[4 * j + 3]));        // tanh
+              cn[j] = f * cp[j] + ig * g;
+              hn[j] = og * (1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * cn[j])));
+            }
+            float* hd = ep.out_f32 + (size_t)row * ep.ldo + ch;
+            float* cd = ep.out2_f32 + (size_t)row * ep.ldo + ch;
+            *reinterpret_cast<float4*>(hd) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(hd + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            *reinterpret_cast<float4*>(cd) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            *reinterpret_cast<float4*>(cd + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
           } else {
             float* dst = ep.out_f32 + pix * ep.C + n;
 #pragma unroll
@@ -304,22 +338,30 @@ static int sm_count() {
 
 template <int EPI>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* bias, int N, int K, int BN, const int* counts,
-                     long long max_rows, int m_static, const EpiParams& ep, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)TC_STAGES * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 128;
+                     long long max_rows, int m_static, const EpiParams& ep, cudaStream_t st,
+                     const CUtensorMap* ma2 = nullptr, int k_split = 1 << 30) {
+  const int stages = BN > 128 ? 3 : TC_STAGES;                          // 3 x 48 KB or 4 x <=32 KB of operand ring
+  const size_t smem = 1024 + (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 128;
   static bool attr_done = false;   // per-instantiation; the attribute is idempotent
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);   // + <= 34 KB static
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);   // + <= 34 KB static
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
   const long long tiles = ((max_rows + TC_BM - 1) / TC_BM) * (N / BN);       // worst case; the kernel clips to counts[1]
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(ma, mw, bias, N, K, BN, counts, m_static, ep);
+  gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(ma, ma2 ? *ma2 : ma, k_split, mw, bias, N, K, BN, stages, counts, m_static, ep);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }
 
-static int pick_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : (N % 32 == 0 ? 32 : 0)); }
+// Widest N tile (multiple of 32, <= 256 so that two accumulators fit the 512 TMEM columns) that divides N:
+// every extra n-tile re-reads the A tile and pays the per-tile hand-shakes again.
+static int pick_bn(int N) {
+  for (int bn = 256; bn >= 32; bn -= 32)
+    if (N % bn == 0) return bn;
+  return 0;
+}
 
 int launch_gemm_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, int N, int K, const int* counts,
                    long long max_rows, int epi, const EpiParams& ep, cudaStream_t st) {
@@ -340,6 +382,30 @@ int launch_gemm_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, cons
 }
 
 }  // namespace sast
+
+// h, c = LSTM cell on the 1x1-conv of [x | h_prev]  (models/layers/rnn.py:36-69, dws_conv False) as ONE kernel:
+// TF32 tcgen05 GEMM straight from the fp32 NHWC maps + gate epilogue.  w_packed [4C, K] fp32 with rows interleaved
+// 4*c + {f,i,o,g} (K = C for a zero initial state, 2C otherwise), bias_packed [4C] likewise.
+extern "C" int sast_lstm_fwd(const float* x, const float* h_prev, const float* c_prev, const float* w_packed,
+                             const float* bias_packed, int64_t P, int32_t C, float* h_out, float* c_out, void* stream) {
+  using namespace sast;
+  SAST_CHECK_PTR(x); SAST_CHECK_PTR(w_packed); SAST_CHECK_PTR(h_out); SAST_CHECK_PTR(c_out);
+  if (P <= 0 || C <= 0 || C % 8 != 0 || P >= (1ll << 31)) return SAST_E_SHAPE;
+  if ((h_prev == nullptr) != (c_prev == nullptr)) return SAST_E_NULL;
+  const int K = h_prev ? 2 * C : C, N = 4 * C;
+  const int BN = pick_bn(N);
+  if (BN == 0) return SAST_E_SHAPE;
+  CUtensorMap ma, ma2, mw;
+  int rc = make_tmap_f32_box(&ma, x, P, C, C, 32, TC_BM);
+  if (rc) return rc;
+  if (h_prev) { rc = make_tmap_f32_box(&ma2, h_prev, P, C, C, 32, TC_BM); if (rc) return rc; }
+  rc = make_tmap_f32_box(&mw, w_packed, N, K, K, 32, BN);
+  if (rc) return rc;
+  EpiParams ep{};
+  ep.out_f32 = h_out; ep.out2_f32 = c_out; ep.ldo = C; ep.resid = c_prev; ep.ldr = C;
+  return launch_tc<EPI_LSTM>(ma, mw, bias_packed, N, K, BN, nullptr, P, (int)P, ep, (cudaStream_t)stream, h_prev ? &ma2 : nullptr,
+                             h_prev ? C : (1 << 30));
+}
 
 extern "C" int sast_gemm_bf16(const uint16_t* A, const uint16_t* W, const float* bias, void* D, int32_t d_is_bf16, int32_t M,
                               int32_t N, int32_t K, void* stream) {

@@ -10,11 +10,13 @@ enum Epi {
   EPI_STORE = 0,    // D = acc + bias                                   (QKV)
   EPI_RESID = 1,    // D = resid + gamma * (acc + bias)                 (proj + LayerScale + shortcut)
   EPI_GLU = 2,      // D[:, j] = (acc[2j]+b[2j]) * gelu(acc[2j+1]+b[2j+1])  (GLU, interleaved weight rows)
-  EPI_SCATTER = 3   // map[pixel(row)] = resid + gamma * (acc + bias)   (MLP out + LayerScale + residual + scatter-back)
+  EPI_SCATTER = 3,  // map[pixel(row)] = resid + gamma * (acc + bias)   (MLP out + LayerScale + residual + scatter-back)
+  EPI_LSTM = 4      // conv-LSTM gates: columns interleaved [f,i,o,g] per channel; TF32 operands straight from fp32
 };
 
 struct EpiParams {
-  float* out_f32;          // fp32 destination (rows or NHWC map)
+  float* out_f32;          // fp32 destination (rows or NHWC map); EPI_LSTM: h
+  float* out2_f32;         // EPI_LSTM: c
   __nv_bfloat16* out_bf16; // optional bf16 copy of the destination rows (operand of the next GEMM)
   int ldo;                 // leading dimension of the row destinations
   const float* resid;      // [rows, ldr] fp32

@@ -501,3 +501,22 @@ def lstm_gates(mix: Tensor, bias: Optional[Tensor], c_prev: Optional[Tensor]) ->
 def _(mix, bias, c_prev):
     shape = mix.shape[:-1] + (mix.shape[-1] // 4,)
     return mix.new_empty(shape, dtype=torch.float32), mix.new_empty(shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("sast::lstm_fwd", mutates_args=())
+def lstm_fwd(x: Tensor, h_prev: Optional[Tensor], c_prev: Optional[Tensor], w_packed: Tensor,
+             bias_packed: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """Fused conv-LSTM cell on NHWC fp32 maps [..., C]; see sast_lstm_fwd in include/sast_b200.h."""
+    x = _f32c(x, "x")
+    Cc = x.shape[-1]
+    if h_prev is not None:
+        h_prev, c_prev = _f32c(h_prev, "h_prev"), _f32c(c_prev, "c_prev")
+    h, c = torch.empty_like(x), torch.empty_like(x)
+    L.check(L.lib().sast_lstm_fwd(x.data_ptr(), L.ptr(h_prev), L.ptr(c_prev), w_packed.data_ptr(), L.ptr(bias_packed),
+                                  x.numel() // Cc, Cc, h.data_ptr(), c.data_ptr(), L.stream_ptr(x.device)), "sast_lstm_fwd")
+    return h, c
+
+
+@lstm_fwd.register_fake
+def _(x, h_prev, c_prev, w_packed, bias_packed):
+    return torch.empty_like(x, dtype=torch.float32), torch.empty_like(x, dtype=torch.float32)

@@ -38,7 +38,7 @@ def build_backbone(meta, precision):
 
 def set_precision(net, precision):
     for m in net.modules():
-        if isinstance(m, sast_b200.MS_WSA):
+        if isinstance(m, (sast_b200.MS_WSA, sast_b200.DWSConvLSTM2d)):
             m.precision = precision
 
 
