@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                                                                 const float* __restrict__ bias, int N, int K, int BN, int stages,
                                                                 const int* __restrict__ counts, int m_static, EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ float stage_smem[(EPI == EPI_STORE || EPI == EPI_RESID) ? TC_EPI_WARPS : 1][32 * 33];   // epilogue transpose tiles
+  __shared__ __align__(16) float stage_smem[TC_EPI_WARPS][32 * 32];   // epilogue transpose tiles (XOR-swizzled 16-byte groups)
   const int M = counts ? counts[1] : m_static;
   const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = N / BN;
   const int total_tiles = m_tiles * n_tiles;
@@ -141,122 +141,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t tmem_d = tmem_base + (uint32_t)group * (uint32_t)BN + ((uint32_t)(quarter * 32) << 16);
       ptx::mbar_wait(&sm->tmem_full[group], use & 1);
       ptx::tc_fence_after();
-      if constexpr (EPI == EPI_STORE || EPI == EPI_RESID) {
-        // tcgen05.ld gives every lane 32 consecutive columns of ITS row; wide row outputs want the
-        // opposite (a warp instruction touching whole 128-byte row segments).  Each warp transposes
-        // its 32x32 chunk through a padded shared-memory tile and does the global I/O (residual
-        // loads, fp32 / bf16 stores) with 8 lanes x 16 bytes per row.
+      {
+        // tcgen05.ld gives every lane 32 consecutive accumulator columns of ITS row; global memory wants the
+        // opposite (a warp instruction covering whole row segments).  Phase A: each lane drops its 32 values
+        // into a [32 rows x 128 B] shared-memory tile with 8 x STS.128, 16-byte groups XOR-swizzled by
+        // (row % 8) -- conflict free.  Phase B: lane = (row-in-group r_sub, 16-byte column group gq); per
+        // iteration a warp handles 4 full rows: LDS.128, epilogue math on 4 columns whose bias / gamma are
+        // lane constants, one 4..16-byte store per output -- every global access is a dense row segment.
         float* stage = &stage_smem[warp - 2][0];
-        const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
+        const int r_sub = lane >> 3, gq = lane & 7, c4 = gq * 4;
+        // rows of this lane in phase B (fixed per tile): r = it*4 + r_sub
+        long long pixo[8];
+        if (EPI == EPI_SCATTER) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int row = m0 + quarter * 32 + it * 4 + r_sub;
+            pixo[it] = row < M ? (long long)ep.row_pix[row] * ep.C : -1;
+          }
+        }
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t raw[32];
           ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
           const int n = n0 + c0 + c4;
           float4 r4[8];
-          if (EPI == EPI_RESID) {                  // residual rows in flight while the TMEM load completes
+          if (EPI == EPI_RESID || EPI == EPI_SCATTER) {    // residual rows in flight while the TMEM load completes
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = m0 + quarter * 32 + it * 4 + r_sub;
               r4[it] = row < M ? *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
+          float cprev[8];
+          if (EPI == EPI_LSTM) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = m0 + quarter * 32 + it * 4 + r_sub;
+              cprev[it] = (ep.resid && row < M) ? ep.resid[(size_t)row * ep.ldr + (n >> 2)] : 0.f;
+            }
+          }
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
           if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
-          if (EPI == EPI_RESID && ep.gamma) g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
+          if ((EPI == EPI_RESID || EPI == EPI_SCATTER) && ep.gamma) g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n));
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(stage + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_uint4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]);
           __syncwarp();
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + r_sub;
             const int row = m0 + quarter * 32 + r;
             if (row >= M) continue;
-            const float* sp = stage + r * 33 + c4;
-            float v0 = sp[0] + b4.x, v1 = sp[1] + b4.y, v2 = sp[2] + b4.z, v3 = sp[3] + b4.w;
-            if (EPI == EPI_RESID) {
-              v0 = r4[it].x + g4.x * v0; v1 = r4[it].y + g4.y * v1; v2 = r4[it].z + g4.z * v2; v3 = r4[it].w + g4.w * v3;
-            }
-            if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + n) = make_float4(v0, v1, v2, v3);
-            if (ep.out_bf16) {
-              const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
-              uint2 pk;
-              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ldo + n) = pk;
+            const float4 a4 = *reinterpret_cast<const float4*>(stage + r * 32 + ((gq ^ (r & 7)) << 2));
+            float v0 = a4.x + b4.x, v1 = a4.y + b4.y, v2 = a4.z + b4.z, v3 = a4.w + b4.w;
+            if (EPI == EPI_GLU) {            // columns interleaved value_j, gate_j
+              const __nv_bfloat162 o = __floats2bfloat162_rn(v0 * gelu_erf_fast(v1), v2 * gelu_erf_fast(v3));
+              *reinterpret_cast<__nv_bfloat162*>(ep.out_bf16 + (size_t)row * ep.ldo + (n >> 1)) = o;
+            } else if (EPI == EPI_LSTM) {    // columns interleaved forget, input, output, cell-input of one channel
+              const float f = __fdividef(1.0f, 1.0f + __expf(-v0)), ig = __fdividef(1.0f, 1.0f + __expf(-v1));
+              const float og = __fdividef(1.0f, 1.0f + __expf(-v2));
+              const float g = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v3));                 // tanh
+              const float cn = f * cprev[it] + ig * g;
+              ep.out2_f32[(size_t)row * ep.ldo + (n >> 2)] = cn;
+              ep.out_f32[(size_t)row * ep.ldo + (n >> 2)] = og * (1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * cn)));
+            } else {
+              if (EPI == EPI_RESID || EPI == EPI_SCATTER) {
+                v0 = r4[it].x + g4.x * v0; v1 = r4[it].y + g4.y * v1; v2 = r4[it].z + g4.z * v2; v3 = r4[it].w + g4.w * v3;
+              }
+              if (EPI == EPI_SCATTER) {
+                *reinterpret_cast<float4*>(ep.out_f32 + pixo[it] + n) = make_float4(v0, v1, v2, v3);
+              } else {
+                if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + n) = make_float4(v0, v1, v2, v3);
+                if (ep.out_bf16) {
+                  const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+                  uint2 pk;
+                  pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                  pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                  *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ldo + n) = pk;
+                }
+              }
             }
           }
           __syncwarp();
-        }
-      } else {
-        // GLU / LSTM (narrow rows) and SCATTER (rows land on scattered pixels): every lane finishes its own row
-        const int row = m0 + quarter * 32 + lane;
-        const bool row_ok = row < M;
-        long long pix = 0;
-        if (EPI == EPI_SCATTER && row_ok) pix = ep.row_pix[row];
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t raw[32];
-          ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
-          const int n = n0 + c0;
-          float4 r4[8];
-          if (EPI == EPI_SCATTER && row_ok) {      // residual loads in flight while the TMEM load completes
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n + 4 * j);
-          }
-          ptx::tmem_ld_wait();
-          if (!row_ok) continue;
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          }
-          if (EPI == EPI_GLU) {
-            float o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_erf_fast(v[2 * j + 1]);
-            __nv_bfloat16* dst = ep.out_bf16 + (size_t)row * ep.ldo + n / 2;
-            store_bf16x8(dst, o);
-            store_bf16x8(dst + 8, o + 8);
-          } else if (EPI == EPI_LSTM) {
-            // 32 columns = 8 channels x [forget, input, output, cell-input]   (models/layers/rnn.py:58-69)
-            const int ch = n / 4;
-            float cp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (ep.resid) {
-              const float4 c0v = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + ch);
-              const float4 c1v = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + ch + 4);
-              cp[0] = c0v.x; cp[1] = c0v.y; cp[2] = c0v.z; cp[3] = c0v.w; cp[4] = c1v.x; cp[5] = c1v.y; cp[6] = c1v.z; cp[7] = c1v.w;
-            }
-            float hn[8], cn[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float f = __fdividef(1.0f, 1.0f + __expf(-v[4 * j])), ig = __fdividef(1.0f, 1.0f + __expf(-v[4 * j + 1]));
-              const float og = __fdividef(1.0f, 1.0f + __expf(-v[4 * j + 2]));
-              const float g = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v[4 * j + 3]));        // tanh
-              cn[j] = f * cp[j] + ig * g;
-              hn[j] = og * (1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * cn[j])));
-            }
-            float* hd = ep.out_f32 + (size_t)row * ep.ldo + ch;
-            float* cd = ep.out2_f32 + (size_t)row * ep.ldo + ch;
-            *reinterpret_cast<float4*>(hd) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            *reinterpret_cast<float4*>(hd + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-            *reinterpret_cast<float4*>(cd) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            *reinterpret_cast<float4*>(cd + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-          } else {
-            float* dst = ep.out_f32 + pix * ep.C + n;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (ep.gamma) g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n + 4 * j));
-              *reinterpret_cast<float4*>(dst + 4 * j) =
-                  make_float4(r4[j].x + g4.x * v[4 * j], r4[j].y + g4.y * v[4 * j + 1], r4[j].z + g4.z * v[4 * j + 2],
-                              r4[j].w + g4.w * v[4 * j + 3]);
-            }
-          }
         }
       }
       // this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
@@ -357,15 +323,21 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* 
 
 // Widest N tile (multiple of 32, <= 256 so that two accumulators fit the 512 TMEM columns) that divides N:
 // every extra n-tile re-reads the A tile and pays the per-tile hand-shakes again.
-static int pick_bn(int N) {
-  for (int bn = 256; bn >= 32; bn -= 32)
-    if (N % bn == 0) return bn;
-  return 0;
+// ... unless that leaves SMs idle: with few row tiles (late stages, small batches) narrower tiles win.
+static int pick_bn(int N, long long m_tiles = 1 << 20) {
+  int best = 0;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    if (N % bn != 0) continue;
+    if (!best) best = bn;
+    if (m_tiles * (N / bn) >= sm_count()) return bn;     // widest tile that still fills the chip
+    best = bn;                                           // otherwise the narrowest divisor (most tiles)
+  }
+  return best;
 }
 
 int launch_gemm_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, int N, int K, const int* counts,
                    long long max_rows, int epi, const EpiParams& ep, cudaStream_t st) {
-  const int BN = pick_bn(N);
+  const int BN = pick_bn(N, (max_rows + TC_BM - 1) / TC_BM);
   if (BN == 0 || K % 8 != 0 || lda % 8 != 0) return SAST_E_SHAPE;
   CUtensorMap ma, mw;
   int rc = make_tmap_bf16_2d(&ma, A, max_rows, K, lda, TC_BM);
@@ -393,7 +365,7 @@ extern "C" int sast_lstm_fwd(const float* x, const float* h_prev, const float* c
   if (P <= 0 || C <= 0 || C % 8 != 0 || P >= (1ll << 31)) return SAST_E_SHAPE;
   if ((h_prev == nullptr) != (c_prev == nullptr)) return SAST_E_NULL;
   const int K = h_prev ? 2 * C : C, N = 4 * C;
-  const int BN = pick_bn(N);
+  const int BN = pick_bn(N, (P + TC_BM - 1) / TC_BM);
   if (BN == 0) return SAST_E_SHAPE;
   CUtensorMap ma, ma2, mw;
   int rc = make_tmap_f32_box(&ma, x, P, C, C, 32, TC_BM);
@@ -412,7 +384,7 @@ extern "C" int sast_gemm_bf16(const uint16_t* A, const uint16_t* W, const float*
   using namespace sast;
   SAST_CHECK_PTR(A); SAST_CHECK_PTR(W); SAST_CHECK_PTR(D);
   if (M <= 0 || N <= 0 || K <= 0) return SAST_E_SHAPE;
-  const int BN = pick_bn(N);
+  const int BN = pick_bn(N, (M + TC_BM - 1) / TC_BM);
   if (BN == 0 || K % 8 != 0) return SAST_E_SHAPE;
   CUtensorMap ma, mw;
   int rc = make_tmap_bf16_2d(&ma, A, M, K, K, TC_BM);
