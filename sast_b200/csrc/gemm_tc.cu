@@ -187,24 +187,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           for (int k = 0; k < 8; ++k)
             *reinterpret_cast<uint4*>(stage + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_uint4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]);
           __syncwarp();
+          // math for all 8 row-iterations is straight-line (independent chains interleave); only the stores are predicated
+          float4 a4[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + r_sub;
-            const int row = m0 + quarter * 32 + r;
-            if (row >= M) continue;
-            const float4 a4 = *reinterpret_cast<const float4*>(stage + r * 32 + ((gq ^ (r & 7)) << 2));
-            float v0 = a4.x + b4.x, v1 = a4.y + b4.y, v2 = a4.z + b4.z, v3 = a4.w + b4.w;
-            if (EPI == EPI_GLU) {            // columns interleaved value_j, gate_j
-              const __nv_bfloat162 o = __floats2bfloat162_rn(v0 * gelu_erf_fast(v1), v2 * gelu_erf_fast(v3));
-              *reinterpret_cast<__nv_bfloat162*>(ep.out_bf16 + (size_t)row * ep.ldo + (n >> 1)) = o;
-            } else if (EPI == EPI_LSTM) {    // columns interleaved forget, input, output, cell-input of one channel
-              const float f = __fdividef(1.0f, 1.0f + __expf(-v0)), ig = __fdividef(1.0f, 1.0f + __expf(-v1));
-              const float og = __fdividef(1.0f, 1.0f + __expf(-v2));
-              const float g = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v3));                 // tanh
-              const float cn = f * cprev[it] + ig * g;
-              ep.out2_f32[(size_t)row * ep.ldo + (n >> 2)] = cn;
-              ep.out_f32[(size_t)row * ep.ldo + (n >> 2)] = og * (1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * cn)));
-            } else {
+            a4[it] = *reinterpret_cast<const float4*>(stage + r * 32 + ((gq ^ (r & 7)) << 2));
+          }
+          if (EPI == EPI_GLU) {                // columns interleaved value_j, gate_j
+            __nv_bfloat162 o[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              o[it] = __floats2bfloat162_rn((a4[it].x + b4.x) * gelu_erf_fast(a4[it].y + b4.y), (a4[it].z + b4.z) * gelu_erf_fast(a4[it].w + b4.w));
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = m0 + quarter * 32 + it * 4 + r_sub;
+              if (row < M) *reinterpret_cast<__nv_bfloat162*>(ep.out_bf16 + (size_t)row * ep.ldo + (n >> 1)) = o[it];
+            }
+          } else if (EPI == EPI_LSTM) {        // columns interleaved forget, input, output, cell-input of one channel
+            float hn[8], cn[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const float f = __fdividef(1.0f, 1.0f + __expf(-(a4[it].x + b4.x))), ig = __fdividef(1.0f, 1.0f + __expf(-(a4[it].y + b4.y)));
+              const float og = __fdividef(1.0f, 1.0f + __expf(-(a4[it].z + b4.z)));
+              const float g = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * (a4[it].w + b4.w)));     // tanh
+              cn[it] = f * cprev[it] + ig * g;
+              hn[it] = og * (1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * cn[it])));
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = m0 + quarter * 32 + it * 4 + r_sub;
+              if (row < M) {
+                ep.out2_f32[(size_t)row * ep.ldo + (n >> 2)] = cn[it];
+                ep.out_f32[(size_t)row * ep.ldo + (n >> 2)] = hn[it];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = m0 + quarter * 32 + it * 4 + r_sub;
+              if (row >= M) continue;
+              float v0 = a4[it].x + b4.x, v1 = a4[it].y + b4.y, v2 = a4[it].z + b4.z, v3 = a4[it].w + b4.w;
               if (EPI == EPI_RESID || EPI == EPI_SCATTER) {
                 v0 = r4[it].x + g4.x * v0; v1 = r4[it].y + g4.y * v1; v2 = r4[it].z + g4.z * v2; v3 = r4[it].w + g4.w * v3;
               }
