@@ -236,6 +236,11 @@ int sast_gemm_bf16(const uint16_t* A, const uint16_t* W, const float* bias, void
  * loaded: a monotonically increasing statistics counter, the only process-wide state. */
 uint64_t sast_launch_count(void);
 
+/* D[M,N/2] (bf16) = value * gelu_erf(gate) of A W^T + bias, W rows interleaved value_j, gate_j: the layer's
+ * GLU GEMM (ops.py:135-137) standalone, for unit tests and the roofline measurement of bench.py. */
+int sast_gemm_bf16_glu(const uint16_t* A, const uint16_t* W, const float* bias, uint16_t* D, int32_t M, int32_t N,
+                       int32_t K, void* stream);
+
 /* Library / build info. */
 int sast_abi_version(void);
 /* sizeof of an ABI struct: 0 sast_geom, 1 sast_selection, 2 sast_score_args, 3 sast_select_args,

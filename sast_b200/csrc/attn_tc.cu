@@ -7,7 +7,7 @@
 // The compacted buffer holds selected tokens only, so the reference's -1e4 column mask for
 // padding (SAST.py:223-226) has no counterpart: the only mask is "same window".
 //
-// CTA = 128 threads, thread t <-> tile row t <-> TMEM lane t.  Thread 0 issues TMA and MMA.
+// CTA = 256 threads, two threads per tile row (= TMEM lane), each on half of the key columns.  Thread 0 issues TMA and MMA.
 // 128 TMEM columns and 41 KB of shared memory per CTA -> 4 CTAs per SM hide each other's
 // load -> MMA -> softmax -> MMA latency chain.
 //   Q,K,V tiles [128 x 32] bf16: TMA boxes out of the qkv buffer ([rows, 3C], head-major
@@ -50,16 +50,36 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32
   return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 256 threads: warps w and w+4 own TMEM lanes 32*(w%4)..+31 (= tile rows); the low warp of a pair works on key
+// columns [0,64), the high warp on [64,128) -- two threads per row halve the softmax latency chain and double
+// the warps the SM can interleave.
+__global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                            __nv_bfloat16* __restrict__ att, int C, int heads_per_cta,
                                                            const int* __restrict__ tiles, const int* __restrict__ win_row0,
                                                            const int* __restrict__ row_tok, int T) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ float pmax[2][128], psum[2][128];
   const int w = blockIdx.x;
   const int rows = tiles[2 * w];
   if (rows == 0) return;                                   // not a tile leader
   const int row0 = win_row0[w];
-  const int t = threadIdx.x, warp = t >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;                              // which 64 key columns
+  const int t = (warp & 3) * 32 + lane;                    // tile row = TMEM lane
 
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = base;                                      // Q, K are dead once S = Q K^T has completed:
@@ -68,7 +88,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   uint8_t* sV = base + 4 * AT_TILE;
   AttnSmem* sm = reinterpret_cast<AttnSmem*>(base + 5 * AT_TILE);
 
-  if (t == 0) {
+  if (tid == 0) {
     ptx::tma_prefetch_desc(&map_qkv);
     ptx::mbar_init(&sm->bar_load, 1);
     ptx::mbar_init(&sm->bar_s, 1);
@@ -81,7 +101,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_s = sm->tmem_base;
   const uint32_t tmem_o = tmem_s;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
 
   // key range of this row: the compacted rows of its own window
   int lo = 0, hi = 0;
@@ -92,12 +112,17 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
   }
   const int rows16 = (rows + 15) & ~15;
   const float sc = 0.17677669529663688110f * 1.44269504088896340736f;   // 32^-0.5 * log2(e)
+  // 32-column chunks of this warp's half that any of its rows needs
+  const int wlo = max(__reduce_min_sync(kFull, t < rows ? lo : 128) & ~31, half * 64);
+  const int whi = min(__reduce_max_sync(kFull, t < rows ? hi : 0), half * 64 + 64);
+  const int r8 = t & 7;
+  uint8_t* prow = sP + (t >> 3) * 1024 + r8 * 128;
 
   const int h_begin = blockIdx.y * heads_per_cta;
   for (int hi_ = 0; hi_ < heads_per_cta; ++hi_) {
     const int h = h_begin + hi_;
     const uint32_t ph = (uint32_t)(hi_ & 1);
-    if (t == 0) {
+    if (tid == 0) {
       ptx::mbar_arrive_expect_tx(&sm->bar_load, 3 * AT_TILE);
       ptx::tma_load_2d(sQ, &map_qkv, &sm->bar_load, h * 96, row0);
       ptx::tma_load_2d(sK, &map_qkv, &sm->bar_load, h * 96 + 32, row0);
@@ -113,45 +138,58 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     ptx::mbar_wait(&sm->bar_s, ph);
     ptx::tc_fence_after();
 
-    // ---- softmax over this row's window (two passes over TMEM: max, then exp / sum / P) ----
-    // A warp only visits the 32-column chunks that some of its rows need (block-diagonal mask: with
-    // two 60-token windows per tile most warps skip a third of the columns); skipped chunks of P are zero.
-    const int wlo = __reduce_min_sync(kFull, t < rows ? lo : 128) & ~31;
-    const int whi = __reduce_max_sync(kFull, t < rows ? hi : 0);
+    // ---- softmax over this row's window: pass 1 = max over the valid columns of this thread's half ----
     float mx = -INFINITY;
     for (int c0 = wlo; c0 < whi; c0 += 32) {
       uint32_t raw[32];
       ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
       ptx::tmem_ld_wait();
+      if (lo <= c0 && c0 + 32 <= hi) {                      // chunk entirely inside this row's window
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = c0 + j;
-        if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(raw[j]));
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c0 + j;
+          if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(raw[j]));
+        }
       }
     }
-    float sum = 0.f;
+    pmax[half][t] = mx;
+    __syncthreads();
+    mx = fmaxf(pmax[0][t], pmax[1][t]);
     const float mxs = mx * sc;
-    const int r8 = t & 7;
-    uint8_t* prow = sP + (t >> 3) * 1024 + r8 * 128;
-    for (int c0 = 0; c0 < rows16; c0 += 32) {
+
+    // ---- pass 2: p = 2^((s - max) * scale*log2e), bf16 P into the SWIZZLE_128B operand tile, row sum ----
+    float sum = 0.f;
+    for (int c0 = half * 64; c0 < min(half * 64 + 64, rows16); c0 += 32) {
       uint32_t pk[16];
       if (c0 >= wlo && c0 < whi) {
         uint32_t raw[32];
         ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
         ptx::tmem_ld_wait();
+        if (lo <= c0 && c0 + 32 <= hi) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const int col = c0 + j;
-          float p0, p1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[j]), sc, -mxs)));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs)));
-          p0 = (col >= lo && col < hi) ? p0 : 0.f;
-          p1 = (col + 1 >= lo && col + 1 < hi) ? p1 : 0.f;
-          const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-          // the row sum uses the bf16-rounded probabilities the PV product will see
-          const float2 f2 = __bfloat1622float2(b2);
-          sum += f2.x + f2.y;
-          pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+          for (int j = 0; j < 32; j += 2) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(ex2_fast(fmaf(__uint_as_float(raw[j]), sc, -mxs)),
+                                                            ex2_fast(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs)));
+            const float2 f2 = __bfloat1622float2(b2);        // the row sum uses the bf16-rounded probabilities PV will see
+            sum += f2.x + f2.y;
+            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int col = c0 + j;
+            float p0 = ex2_fast(fmaf(__uint_as_float(raw[j]), sc, -mxs));
+            float p1 = ex2_fast(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs));
+            p0 = (col >= lo && col < hi) ? p0 : 0.f;
+            p1 = (col + 1 >= lo && col + 1 < hi) ? p1 : 0.f;
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+            const float2 f2 = __bfloat1622float2(b2);
+            sum += f2.x + f2.y;
+            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
         }
       } else {
 #pragma unroll
@@ -166,15 +204,16 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
         *reinterpret_cast<uint4*>(prow + kb * 16384 + chunk * 16) = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
       }
     }
+    psum[half][t] = sum;
     // V rows past the tile may be uninitialised memory (0 * NaN = NaN): zero the ones the PV product reads
-    if (t >= rows && t < rows16) {
+    if (half == 1 && t >= rows && t < rows16) {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(sV + t * 64 + cc * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     ptx::fence_proxy_async();                               // generic-proxy smem writes -> visible to tcgen05
     ptx::tc_fence_before();
     __syncthreads();
-    if (t == 0) {
+    if (tid == 0) {
       ptx::tc_fence_after();
       const uint32_t id_o = idesc_bf16(128, 32, 1);
       const uint32_t pa = ptx::smem_u32(sP), va = ptx::smem_u32(sV);
@@ -188,14 +227,14 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
     ptx::mbar_wait(&sm->bar_o, ph);
     ptx::tc_fence_after();
     {
-      uint32_t raw[32];
-      ptx::tmem_ld_32x32(tmem_o + lane_sel, raw);
+      uint32_t raw[16];                                       // this thread's 16 of the 32 output dims
+      tmem_ld_32x16(tmem_o + lane_sel + (uint32_t)(half * 16), raw);
       ptx::tmem_ld_wait();
       if (t < rows) {
-        const float il = 1.0f / sum;
-        __nv_bfloat16* dst = att + (size_t)(row0 + t) * C + h * 32;
+        const float il = 1.0f / (psum[0][t] + psum[1][t]);
+        __nv_bfloat16* dst = att + (size_t)(row0 + t) * C + h * 32 + half * 16;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
           uint4 o;
           __nv_bfloat162 b2;
           b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 0]) * il, __uint_as_float(raw[cc * 8 + 1]) * il); o.x = *reinterpret_cast<uint32_t*>(&b2);
@@ -207,7 +246,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const __grid_constant
       }
     }
     ptx::tc_fence_before();
-    __syncthreads();          // everyone is done with S, O and the smem tiles before the next head reuses them
+    __syncthreads();          // everyone is done with S, O, pmax/psum and the smem tiles before the next head reuses them
     ptx::tc_fence_after();
   }
   if (warp == 0) ptx::tmem_dealloc(tmem_s, AT_TMEM_COLS);
@@ -306,7 +345,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   // enough CTAs to fill the chip: all heads in one CTA when there are many tiles, one head per CTA otherwise
   int hpc = heads;
   while (hpc > 1 && (long long)NW * (heads / hpc) < 4 * 148 && hpc % 2 == 0) hpc /= 2;
-  attention_tc_kernel<<<dim3(NW, heads / hpc), 128, smem, st>>>(mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T);
+  attention_tc_kernel<<<dim3(NW, heads / hpc), 256, smem, st>>>(mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

@@ -402,6 +402,25 @@ extern "C" int sast_lstm_fwd(const float* x, const float* h_prev, const float* c
                              h_prev ? C : (1 << 30));
 }
 
+// D[M, N/2] (bf16) = GLU(A W^T + bias) with W rows interleaved value_j, gate_j: the layer's MLP-in GEMM, standalone
+extern "C" int sast_gemm_bf16_glu(const uint16_t* A, const uint16_t* W, const float* bias, uint16_t* D, int32_t M, int32_t N,
+                                  int32_t K, void* stream) {
+  using namespace sast;
+  SAST_CHECK_PTR(A); SAST_CHECK_PTR(W); SAST_CHECK_PTR(D);
+  if (M <= 0 || N <= 0 || K <= 0 || N % 64 != 0) return SAST_E_SHAPE;
+  const int BN = pick_bn(N, (M + TC_BM - 1) / TC_BM);
+  if (BN == 0 || K % 8 != 0) return SAST_E_SHAPE;
+  CUtensorMap ma, mw;
+  int rc = make_tmap_bf16_2d(&ma, A, M, K, K, TC_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&mw, W, N, K, K, BN);
+  if (rc) return rc;
+  EpiParams ep{};
+  ep.ldo = N / 2;
+  ep.out_bf16 = (__nv_bfloat16*)D;
+  return launch_tc<EPI_GLU>(ma, mw, bias, N, K, BN, nullptr, M, M, ep, (cudaStream_t)stream);
+}
+
 extern "C" int sast_gemm_bf16(const uint16_t* A, const uint16_t* W, const float* bias, void* D, int32_t d_is_bf16, int32_t M,
                               int32_t N, int32_t K, void* stream) {
   using namespace sast;

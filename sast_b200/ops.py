@@ -520,3 +520,15 @@ def lstm_fwd(x: Tensor, h_prev: Optional[Tensor], c_prev: Optional[Tensor], w_pa
 @lstm_fwd.register_fake
 def _(x, h_prev, c_prev, w_packed, bias_packed):
     return torch.empty_like(x, dtype=torch.float32), torch.empty_like(x, dtype=torch.float32)
+
+
+def gemm_bf16_glu(A: Tensor, Wt_interleaved: Tensor, bias_interleaved: Optional[Tensor] = None) -> Tensor:
+    """bf16 [M, N/2] = value * gelu_erf(gate) of A @ Wt.T + bias; Wt rows interleaved value_j, gate_j."""
+    L.require_cuda(A, "A")
+    A, Wt = A.contiguous(), Wt_interleaved.contiguous()
+    M, K = A.shape
+    N = Wt.shape[0]
+    D = torch.empty(M, N // 2, device=A.device, dtype=torch.bfloat16)
+    L.check(L.lib().sast_gemm_bf16_glu(A.data_ptr(), Wt.data_ptr(), L.ptr(bias_interleaved), D.data_ptr(), M, N, K,
+                                       L.stream_ptr(A.device)), "sast_gemm_bf16_glu")
+    return D

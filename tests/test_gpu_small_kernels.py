@@ -107,3 +107,18 @@ def test_score_to_selection_flip_rate(tensor_core):
     flips = int((got != ref).sum())
     assert 0.2 < ref.float().mean() < 0.9           # a genuinely partial selection
     assert flips <= 1e-4 * ref.numel() + 1, f"{flips} flips of {ref.numel()}"
+
+
+@pytest.mark.parametrize("M,I,K", [(300, 160, 64), (1000, 320, 128), (130, 672, 256)])
+def test_gemm_glu_epilogue(M, I, K):
+    """GLU epilogue of the tcgen05 GEMM (ops.py:135-137: value * erf-GELU(gate)) on interleaved weight rows."""
+    gen = torch.Generator().manual_seed(M + I)
+    A = torch.randn(M, K, generator=gen).to(torch.bfloat16)
+    W = (torch.randn(2 * I, K, generator=gen) / K ** 0.5).to(torch.bfloat16)       # [value rows | gate rows]
+    b = torch.randn(2 * I, generator=gen)
+    y = A.float() @ W.float().t() + b
+    ref = y[:, :I] * torch.nn.functional.gelu(y[:, I:])
+    Wi = torch.stack((W[:I], W[I:]), dim=1).reshape(2 * I, K)
+    bi = torch.stack((b[:I], b[I:]), dim=1).reshape(-1)
+    got = ops.gemm_bf16_glu(A.to(DEV), Wi.to(DEV), bi.to(DEV)).float().cpu()
+    assert (got - ref).abs().max() < 3e-2 and ((got - ref).abs() / (ref.abs() + 1.0)).max() < 1e-2
