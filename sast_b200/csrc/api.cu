@@ -1,6 +1,7 @@
 // Library info entry points.
 #include "common.cuh"
 #include <atomic>
+#include <cstdlib>
 
 static std::atomic<unsigned long long> g_launches{0};
 extern "C" void sast_count_launch_(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -24,3 +25,14 @@ extern "C" size_t sast_struct_size(int32_t which) {
   }
   return 0;
 }
+
+namespace sast {
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAST_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+}  // namespace sast

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
                                                            __nv_bfloat16* __restrict__ att, int C, int heads_per_cta,
                                                            const int* __restrict__ tiles, const int* __restrict__ win_row0,
                                                            const int* __restrict__ row_tok, int T) {
+  pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float pmax[2][128], psum[2][128];
   const int w = blockIdx.x;
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(128) attention_bf16_kernel(const __nv_bfloat16
                                                              __nv_bfloat16* __restrict__ att, int C,
                                                              const int* __restrict__ win_K,
                                                              const int* __restrict__ win_row0) {
+  pdl_entry();
   extern __shared__ __align__(16) float kv[];      // k [K][32] then v [K][32]
   const int w = blockIdx.x, h = blockIdx.y;
   const int K = win_K[w];
@@ -328,7 +330,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   const int heads = C / 32;
   if (variant == 1) {
     const size_t smem = (size_t)T * 64 * sizeof(float);
-    attention_bf16_kernel<<<dim3(NW, heads), 128, smem, st>>>(qkv, att, C, sel.win_K, sel.win_row0);
+    sast::launch_k(attention_bf16_kernel, dim3(NW, heads), 128, smem, st, qkv, att, C, sel.win_K, sel.win_row0);
     SAST_LAUNCH_CHECK();
     return SAST_OK;
   }
@@ -345,7 +347,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   // enough CTAs to fill the chip: all heads in one CTA when there are many tiles, one head per CTA otherwise
   int hpc = heads;
   while (hpc > 1 && (long long)NW * (heads / hpc) < 4 * 148 && hpc % 2 == 0) hpc /= 2;
-  attention_tc_kernel<<<dim3(NW, heads / hpc), 256, smem, st>>>(mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T);
+  sast::launch_k(attention_tc_kernel, dim3(NW, heads / hpc), 256, smem, st, mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

@@ -16,6 +16,34 @@ extern "C" void sast_count_launch_(void);
 
 namespace sast {
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// Every kernel of this library is launched with programmaticStreamSerialization allowed and starts with
+// pdl_entry(): it blocks until the preceding kernel in the stream has completed and its writes are
+// visible (griddepcontrol.wait), then lets the NEXT kernel of the stream begin launching
+// (griddepcontrol.launch_dependents).  The ~90 small launches of a forward thereby overlap their launch
+// latency with the tail of their predecessor; data dependencies are exactly those of stream order.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();     // api.cu: SAST_B200_PDL=0 turns the launch attribute off (A/B knob)
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through SAST_LAUNCH_CHECK
+}
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

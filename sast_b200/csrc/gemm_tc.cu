@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const float* __restrict__ bias, int N, int K, int BN, int stages,
                                                                 const int* __restrict__ counts, int m_static, EpiParams ep) {
+  pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(16) float stage_smem[TC_EPI_WARPS][32 * 32];   // epilogue transpose tiles (XOR-swizzled 16-byte groups)
   const int M = counts ? counts[1] : m_static;
@@ -339,7 +340,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* 
   }
   const long long tiles = ((max_rows + TC_BM - 1) / TC_BM) * (N / BN);       // worst case; the kernel clips to counts[1]
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(ma, ma2 ? *ma2 : ma, k_split, mw, bias, N, K, BN, stages, counts, m_static, ep);
+  sast::launch_k(gemm_tc_kernel<EPI>, grid, TC_THREADS, smem, st, ma, ma2 ? *ma2 : ma, k_split, mw, bias, N, K, BN, stages, counts, m_static, ep);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) gather_ln_kernel(const float* __restrict_
                                                         const float* __restrict__ w2, const float* __restrict__ b2,
                                                         float eps, const int* __restrict__ tok_row, Geom g, int flavor,
                                                         float* __restrict__ n2f, __nv_bfloat16* __restrict__ n2h) {
+  pdl_entry();
   constexpr int GROUPS = 32 / LPT;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPT, l = lane % LPT;
@@ -150,6 +151,7 @@ template <int EPI>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
                                                        const float* __restrict__ bias, int N, int K,
                                                        const int* __restrict__ counts, EpiParams ep) {
+  pdl_entry();
   __shared__ __align__(16) float As[GK][GM + GPAD];
   __shared__ __align__(16) float Bs[GK][GN + GPAD];
   const int M = counts[1];
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ att, int C,
                                                             const int* __restrict__ win_K, const int* __restrict__ win_row0) {
+  pdl_entry();
   extern __shared__ __align__(16) float kv[];      // k [K][32] then v [K][32]
   const int w = blockIdx.x, h = blockIdx.y;
   const int K = win_K[w];
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(128) attention_f32_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------
 __global__ void cb_mean_kernel(const float* __restrict__ m, int C, const int* __restrict__ win_row0, int N, float inv_nt,
                                float* __restrict__ mean) {
+  pdl_entry();
   __shared__ float red[8][32];
   const int b = blockIdx.x, c = blockIdx.y * 32 + threadIdx.x;
   const int r0 = win_row0[b * N], r1 = win_row0[(b + 1) * N];
@@ -289,6 +293,7 @@ __global__ void cb_scatter_kernel(const float* __restrict__ m, const float* __re
                                   const float* __restrict__ gamma, const int* __restrict__ counts,
                                   const int* __restrict__ row_tok, const int* __restrict__ row_pix, Geom g,
                                   float* __restrict__ out) {
+  pdl_entry();
   const int S = counts[1];
   const int c4 = g.C / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)S * c4; i += (long long)gridDim.x * blockDim.x) {
@@ -313,6 +318,7 @@ __global__ void cb_scatter_kernel(const float* __restrict__ m, const float* __re
 template <bool GATHER, int LPT, int NV>
 __global__ void __launch_bounds__(256) rows_copy_kernel(float* __restrict__ map, float* __restrict__ rows,
                                                         const int* __restrict__ counts, const int* __restrict__ row_pix, int C) {
+  pdl_entry();
   constexpr int GROUPS = 32 / LPT, RPG = 4;              // rows per lane group per pass
   const int S = counts[1];
   const int lane = threadIdx.x & 31;
@@ -350,13 +356,13 @@ static int launch_rows_copy(float* map, float* rows, const sast_selection* sel, 
   // a row is read by consecutive lanes (whole 128-byte lines per request), 4 rows per lane group in flight
   // (measured: wider per-lane strips -- 4 lanes x 64 B per row -- lose ~7 % of bandwidth to partial lines)
   const dim3 grid(148 * 8), block(256);
-  if (C <= 32) rows_copy_kernel<GATHER, 8, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 64) rows_copy_kernel<GATHER, 16, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 96) rows_copy_kernel<GATHER, 32, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 128) rows_copy_kernel<GATHER, 32, 1><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 256) rows_copy_kernel<GATHER, 32, 2><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 512) rows_copy_kernel<GATHER, 32, 4><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
-  else if (C <= 1024) rows_copy_kernel<GATHER, 32, 8><<<grid, block, 0, st>>>(map, rows, sel->counts, sel->row_pix, C);
+  if (C <= 32) sast::launch_k(rows_copy_kernel<GATHER, 8, 1>, grid, block, 0, st, map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 64) sast::launch_k(rows_copy_kernel<GATHER, 16, 1>, grid, block, 0, st, map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 96) sast::launch_k(rows_copy_kernel<GATHER, 32, 1>, grid, block, 0, st, map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 128) sast::launch_k(rows_copy_kernel<GATHER, 32, 1>, grid, block, 0, st, map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 256) sast::launch_k(rows_copy_kernel<GATHER, 32, 2>, grid, block, 0, st, map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 512) sast::launch_k(rows_copy_kernel<GATHER, 32, 4>, grid, block, 0, st, map, rows, sel->counts, sel->row_pix, C);
+  else if (C <= 1024) sast::launch_k(rows_copy_kernel<GATHER, 32, 8>, grid, block, 0, st, map, rows, sel->counts, sel->row_pix, C);
   else return SAST_E_UNSUPPORTED;
   SAST_LAUNCH_CHECK();
   return SAST_OK;
@@ -398,7 +404,7 @@ template <int EPI>
 static int launch_gemm_f32(const float* A, int lda, const float* W, const float* bias, int N, int K, const int* counts,
                            long long max_rows, const EpiParams& ep, cudaStream_t st) {
   const dim3 grid((unsigned)((max_rows + GM - 1) / GM), (unsigned)((N + GN - 1) / GN));
-  gemm_f32_kernel<EPI><<<grid, 256, 0, st>>>(A, lda, W, bias, N, K, counts, ep);
+  sast::launch_k(gemm_f32_kernel<EPI>, grid, 256, 0, st, A, lda, W, bias, N, K, counts, ep);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }
@@ -407,7 +413,7 @@ template <int LPT, int NV, int TPW>
 static int launch_gather_ln_t(const sast_layer_args& a, const Geom& g, const LayerWorkspace& ws, cudaStream_t st) {
   const long long tok_per_cta = 8ll * (32 / LPT) * TPW;
   const unsigned grid = (unsigned)((g.P + tok_per_cta - 1) / tok_per_cta);
-  gather_ln_kernel<LPT, NV, TPW><<<grid, 256, 0, st>>>(a.x, a.out, a.w.ln1_w, a.w.ln1_b, a.w.ln2_w, a.w.ln2_b, a.w.ln_eps,
+  sast::launch_k(gather_ln_kernel<LPT, NV, TPW>, grid, 256, 0, st, a.x, a.out, a.w.ln1_w, a.w.ln1_b, a.w.ln2_w, a.w.ln2_b, a.w.ln_eps,
                                                         a.sel.tok_row, g, a.flavor, ws.n2f, ws.n2h);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
@@ -473,7 +479,7 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
     if (rc) return rc;
     // attention
     const size_t smem = (size_t)g.T * 64 * sizeof(float);
-    attention_f32_kernel<<<dim3(g.NW, heads), 128, smem, st>>>((const float*)ws.qkv, (float*)ws.att, C, a.sel.win_K, a.sel.win_row0);
+    sast::launch_k(attention_f32_kernel, dim3(g.NW, heads), 128, smem, st, (const float*)ws.qkv, (float*)ws.att, C, a.sel.win_K, a.sel.win_row0);
     SAST_LAUNCH_CHECK();
     // proj + LayerScale + shortcut
     ep.out_f32 = ws.yf; ep.ldo = C; ep.resid = ws.n2f; ep.ldr = C; ep.gamma = w.gamma1;
@@ -519,9 +525,9 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
     if (rc) return rc;
   }
   if (a.enable_cb) {
-    cb_mean_kernel<<<dim3(g.B, (C + 31) / 32), dim3(32, 8), 0, st>>>(ws.mtmp, C, a.sel.win_row0, g.N, 1.0f / (float)(g.N * g.T), ws.cbmean);
+    sast::launch_k(cb_mean_kernel, dim3(g.B, (C + 31) / 32), dim3(32, 8), 0, st, ws.mtmp, C, a.sel.win_row0, g.N, 1.0f / (float)(g.N * g.T), ws.cbmean);
     SAST_LAUNCH_CHECK();
-    cb_scatter_kernel<<<148 * 8, 256, 0, st>>>(ws.mtmp, ws.yf, ws.cbmean, w.gamma2, a.sel.counts, a.sel.row_tok, a.sel.row_pix, g, a.out);
+    sast::launch_k(cb_scatter_kernel, 148 * 8, 256, 0, st, ws.mtmp, ws.yf, ws.cbmean, w.gamma2, a.sel.counts, a.sel.row_tok, a.sel.row_pix, g, a.out);
     SAST_LAUNCH_CHECK();
   }
   return SAST_OK;

@@ -18,6 +18,7 @@ constexpr int PAD_PX = 256;
 template <typename T>
 __global__ void __launch_bounds__(256) pad_input_kernel(const T* __restrict__ x, int B, int Cin, int H, int W, int pad,
                                                         int cgroup, float* __restrict__ out) {
+  pdl_entry();
   extern __shared__ __align__(16) uint8_t tile_raw[];
   T* tile = reinterpret_cast<T*>(tile_raw);            // [Cin][PAD_PX + 4]
   constexpr int LD = PAD_PX + 4;
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256) pad_input_kernel(const T* __restrict__ x,
 __global__ void __launch_bounds__(256) pad_nhwc_kernel(const float4* __restrict__ x, int B, int H, int W, int C4, int pad,
                                                        long long sb, long long sy, long long sx,   // input strides in float4 units
                                                        float4* __restrict__ out) {
+  pdl_entry();
   const int Ho = H + 2 * pad, Wo = W + 2 * pad;
   const long long total = (long long)B * Ho * Wo * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -87,6 +89,7 @@ template <int LPT, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                         const float* __restrict__ w, const float* __restrict__ b, float eps,
                                                         long long P, int C) {
+  pdl_entry();
   constexpr int GROUPS = 32 / LPT, TPW = 4;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPT, l = lane % LPT;
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) lstm_gates_kernel(const float* __restrict__ mix, const float* __restrict__ bias,
                                                          const float* __restrict__ c_prev, long long P, int C,
                                                          float* __restrict__ h_out, float* __restrict__ c_out) {
+  pdl_entry();
   const int c4n = C / 4;
   const long long total = P * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -199,9 +203,9 @@ extern "C" int sast_pad_input(const void* x, int32_t dtype, int32_t B, int32_t C
   if (cgroup >= Cin) cgroup = Cin; else cgroup &= ~3;
   const size_t smem = (size_t)cgroup * (PAD_PX + 4) * esz;
   switch (dtype) {
-    case SAST_U8: pad_input_kernel<uint8_t><<<grid, 256, smem, st>>>((const uint8_t*)x, B, Cin, H, W, pad, cgroup, out); break;
-    case SAST_I32: pad_input_kernel<int32_t><<<grid, 256, smem, st>>>((const int32_t*)x, B, Cin, H, W, pad, cgroup, out); break;
-    case SAST_F32: pad_input_kernel<float><<<grid, 256, smem, st>>>((const float*)x, B, Cin, H, W, pad, cgroup, out); break;
+    case SAST_U8: sast::launch_k(pad_input_kernel<uint8_t>, grid, 256, smem, st, (const uint8_t*)x, B, Cin, H, W, pad, cgroup, out); break;
+    case SAST_I32: sast::launch_k(pad_input_kernel<int32_t>, grid, 256, smem, st, (const int32_t*)x, B, Cin, H, W, pad, cgroup, out); break;
+    case SAST_F32: sast::launch_k(pad_input_kernel<float>, grid, 256, smem, st, (const float*)x, B, Cin, H, W, pad, cgroup, out); break;
     default: return SAST_E_UNSUPPORTED;
   }
   SAST_LAUNCH_CHECK();
@@ -215,7 +219,7 @@ extern "C" int sast_pad_nhwc(const float* x, int32_t B, int32_t H, int32_t W, in
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 4 != 0 || pad < 0) return SAST_E_SHAPE;
   if (stride_b % 4 || stride_y % 4 || stride_x % 4) return SAST_E_SHAPE;
   const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad) * (C / 4);
-  pad_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, B, H, W, C / 4, pad, stride_b / 4,
+  sast::launch_k(pad_nhwc_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const float4*)x, B, H, W, C / 4, pad, stride_b / 4,
                                                                          stride_y / 4, stride_x / 4, (float4*)out);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
@@ -230,7 +234,7 @@ extern "C" int sast_layernorm(const float* x, const float* weight, const float* 
 #define SAST_LN(LPT, NV)                                                                              \
   do {                                                                                                \
     const long long per_cta = 8ll * (32 / LPT) * 4;                                                   \
-    layernorm_kernel<LPT, NV><<<(unsigned)((P + per_cta - 1) / per_cta), 256, 0, st>>>(x, out, weight, bias, eps, P, C); \
+    sast::launch_k(layernorm_kernel<LPT, NV>, (unsigned)((P + per_cta - 1) / per_cta), 256, 0, st, x, out, weight, bias, eps, P, C); \
   } while (0)
   if (C <= 32) SAST_LN(8, 1);
   else if (C <= 64) SAST_LN(16, 1);
@@ -248,7 +252,7 @@ extern "C" int sast_lstm_gates(const float* mix, const float* bias, const float*
   using namespace sast;
   SAST_CHECK_PTR(mix); SAST_CHECK_PTR(h_out); SAST_CHECK_PTR(c_out);
   if (P <= 0 || C <= 0 || C % 4 != 0) return SAST_E_SHAPE;
-  lstm_gates_kernel<<<grid_for(P * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(mix, bias, c_prev, P, C, h_out, c_out);
+  sast::launch_k(lstm_gates_kernel, grid_for(P * (C / 4), 256), 256, 0, (cudaStream_t)stream, mix, bias, c_prev, P, C, h_out, c_out);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

@@ -48,6 +48,7 @@ template <typename T>
 __global__ void __launch_bounds__(512) nonzero_ratio_kernel(const T* __restrict__ x, int Cin, int H, int W,
                                                             float f0, float f1, float f2, float f3,
                                                             float* __restrict__ r) {
+  pdl_entry();
   extern __shared__ float cell0[];        // [8][w0] level-0 maxima of the current band
   __shared__ int red[4][16];
   const int plane = blockIdx.x;           // b*Cin + c
@@ -120,13 +121,13 @@ extern "C" int sast_nonzero_ratio(const void* x, int32_t dtype, int32_t B, int32
   const dim3 grid(B * Cin), block(512);
   switch (dtype) {
     case SAST_U8:
-      sast::nonzero_ratio_kernel<uint8_t><<<grid, block, smem, st>>>((const uint8_t*)x, Cin, H, W, f[0], f[1], f[2], f[3], r);
+      sast::launch_k(sast::nonzero_ratio_kernel<uint8_t>, grid, block, smem, st, (const uint8_t*)x, Cin, H, W, f[0], f[1], f[2], f[3], r);
       break;
     case SAST_I32:
-      sast::nonzero_ratio_kernel<int32_t><<<grid, block, smem, st>>>((const int32_t*)x, Cin, H, W, f[0], f[1], f[2], f[3], r);
+      sast::launch_k(sast::nonzero_ratio_kernel<int32_t>, grid, block, smem, st, (const int32_t*)x, Cin, H, W, f[0], f[1], f[2], f[3], r);
       break;
     case SAST_F32:
-      sast::nonzero_ratio_kernel<float><<<grid, block, smem, st>>>((const float*)x, Cin, H, W, f[0], f[1], f[2], f[3], r);
+      sast::launch_k(sast::nonzero_ratio_kernel<float>, grid, block, smem, st, (const float*)x, Cin, H, W, f[0], f[1], f[2], f[3], r);
       break;
     default:
       return SAST_E_UNSUPPORTED;

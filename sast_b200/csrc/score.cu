@@ -12,6 +12,7 @@ namespace sast {
 // ctrl[b,c] = sum_j exp(Wc[c,j]) * (r[b,j] + 1e-6);  sig = sigmoid(ctrl);  inv = amp/ctrl (inf -> 0)
 __global__ void controls_kernel(const float* __restrict__ r, const float* __restrict__ ctrl_w, int n_bins, int C,
                                 float amp, float* __restrict__ sig, float* __restrict__ inv) {
+  pdl_entry();
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ x,
                                                     const float* __restrict__ bs, const float* __restrict__ sig,
                                                     const float* __restrict__ inv, int HW, int C, long long P,
                                                     float* __restrict__ xw, float* __restrict__ l1_out) {
+  pdl_entry();
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ x,
 
 // tok_score[p] = sum over channel slices, in slice order (deterministic)
 __global__ void score_reduce_kernel(const float* __restrict__ part, int ny, long long P, float* __restrict__ tok_score) {
+  pdl_entry();
   const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (p >= P) return;
   float s = 0.f;
@@ -124,6 +127,7 @@ __global__ void score_reduce_kernel(const float* __restrict__ part, int ny, long
 
 __global__ void add_pos_kernel(const float4* __restrict__ x, const float4* __restrict__ pos, long long pos_bstride4,
                                long long HWC4, long long total4, float4* __restrict__ out) {
+  pdl_entry();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = x[i];
     const float4 p = pos[(i / HWC4) * pos_bstride4 + (i % HWC4)];
@@ -147,7 +151,7 @@ extern "C" int sast_score_fwd(const sast_score_args* a, void* stream) {
   if (a->score_w == nullptr) {   // non-first block: only x + pos (SAST.py:105, :124-128)
     const long long total4 = P * g.C / 4;
     const int blocks = (int)((total4 + 255) / 256 < 148 * 16 ? (total4 + 255) / 256 : 148 * 16);
-    sast::add_pos_kernel<<<blocks, 256, 0, st>>>((const float4*)a->x, (const float4*)a->pos, a->pos_batch_stride / 4,
+    sast::launch_k(sast::add_pos_kernel, blocks, 256, 0, st, (const float4*)a->x, (const float4*)a->pos, a->pos_batch_stride / 4,
                                                  (long long)HW * g.C / 4, total4, (float4*)a->xw);
     SAST_LAUNCH_CHECK();
     return SAST_OK;
@@ -156,7 +160,7 @@ extern "C" int sast_score_fwd(const sast_score_args* a, void* stream) {
   SAST_CHECK_PTR(a->ctrl_scratch);
   float* sig = a->ctrl_scratch;
   float* inv = a->ctrl_scratch + (size_t)g.B * g.C;
-  sast::controls_kernel<<<g.B, 128, 0, st>>>(a->r, a->ctrl_w, a->n_bins, g.C, a->amp, sig, inv);
+  sast::launch_k(sast::controls_kernel, g.B, 128, 0, st, a->r, a->ctrl_w, a->n_bins, g.C, a->amp, sig, inv);
   SAST_LAUNCH_CHECK();
   float* part_buf = a->ctrl_scratch + 2 * (size_t)g.B * g.C;
   int ny;
@@ -166,7 +170,7 @@ extern "C" int sast_score_fwd(const sast_score_args* a, void* stream) {
     int rc = sast::launch_score_tc(a, sig, inv, part, &ny, st);
     if (rc) return rc;
     if (ny > 1) {
-      sast::score_reduce_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(part, ny, P, a->tok_score);
+      sast::launch_k(sast::score_reduce_kernel, (unsigned)((P + 255) / 256), 256, 0, st, part, ny, P, a->tok_score);
       SAST_LAUNCH_CHECK();
     }
     return SAST_OK;
@@ -174,11 +178,11 @@ extern "C" int sast_score_fwd(const sast_score_args* a, void* stream) {
   ny = (g.C + sast::BN - 1) / sast::BN;
   const dim3 grid((unsigned)((P + sast::BM - 1) / sast::BM), ny);
   float* part = ny == 1 ? a->tok_score : part_buf;
-  sast::score_kernel<<<grid, 256, 0, st>>>(a->x, a->pos, a->pos_batch_stride, a->score_w, a->score_b, sig, inv, HW, g.C, P,
+  sast::launch_k(sast::score_kernel, grid, 256, 0, st, a->x, a->pos, a->pos_batch_stride, a->score_w, a->score_b, sig, inv, HW, g.C, P,
                                            a->xw, part);
   SAST_LAUNCH_CHECK();
   if (ny > 1) {
-    sast::score_reduce_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(part, ny, P, a->tok_score);
+    sast::launch_k(sast::score_reduce_kernel, (unsigned)((P + 255) / 256), 256, 0, st, part, ny, P, a->tok_score);
     SAST_LAUNCH_CHECK();
   }
   return SAST_OK;

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
                                                                  const float* __restrict__ sig, const float* __restrict__ inv,
                                                                  int HW, int C, int BN, long long P, float* __restrict__ xw,
                                                                  float* __restrict__ l1_out) {
+  pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];     // ring | ScSmem | epilogue transpose tiles
   const int m_tiles = (int)((P + SC_BM - 1) / SC_BM), n_tiles = C / BN;
   const int total_tiles = m_tiles * n_tiles;
@@ -269,7 +270,7 @@ int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long tiles = ((P + SC_BM - 1) / SC_BM) * (C / BN);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  score_tc_kernel<<<grid, SC_THREADS, smem, st>>>(mh, ml, a->x, a->pos, a->pos_batch_stride, a->score_b, sig, inv, g.H * g.W, C, BN, P,
+  sast::launch_k(score_tc_kernel, grid, SC_THREADS, smem, st, mh, ml, a->x, a->pos, a->pos_batch_stride, a->score_b, sig, inv, g.H * g.W, C, BN, P,
                                                   a->xw, l1_part);
   SAST_LAUNCH_CHECK();
   *n_slices = C / BN;

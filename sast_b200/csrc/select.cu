@@ -52,6 +52,7 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
 }
 
 __global__ void __launch_bounds__(kSelThreads) win_logit_kernel(SelectParams p) {
+  pdl_entry();
   const int flavor = pick_flavor(p, blockIdx.z);
   const sast_selection& sel = pick_sel(p, blockIdx.z);
   const Geom g = make_geom(p.a.g, flavor);
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(kSelThreads) win_logit_kernel(SelectParams p) 
 }
 
 __global__ void __launch_bounds__(kSelThreads) select_flags_kernel(SelectParams p) {
+  pdl_entry();
   const int flavor = pick_flavor(p, blockIdx.z);
   const sast_selection& sel = pick_sel(p, blockIdx.z);
   const sast_select_args& a = p.a;
@@ -173,6 +175,7 @@ __device__ __forceinline__ void block_excl_scan2(int v0, int v1, int& e0, int& e
 }
 
 __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p) {
+  pdl_entry();
   const int flavor = pick_flavor(p, blockIdx.z);
   const sast_selection& sel = pick_sel(p, blockIdx.z);
   const Geom g = make_geom(p.a.g, flavor);
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
 }
 
 __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelectParams p) {
+  pdl_entry();
   const int flavor = pick_flavor(p, blockIdx.z);
   const sast_selection& sel = pick_sel(p, blockIdx.z);
   const Geom g = make_geom(p.a.g, flavor);
@@ -342,14 +346,14 @@ extern "C" int sast_select2(const sast_select_args* a, int32_t flavor_b, const s
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned wblocks = (unsigned)((g.NW + sast::kSelWarps - 1) / sast::kSelWarps);
   if (a->mode == SAST_SEL_SCORES) {
-    sast::win_logit_kernel<<<dim3(wblocks, 1, nf), sast::kSelThreads, 0, st>>>(p);
+    sast::launch_k(sast::win_logit_kernel, dim3(wblocks, 1, nf), sast::kSelThreads, 0, st, p);
     SAST_LAUNCH_CHECK();
   }
-  sast::select_flags_kernel<<<dim3((g.N + sast::kSelWarps - 1) / sast::kSelWarps, g.B, nf), sast::kSelThreads, 0, st>>>(p);
+  sast::launch_k(sast::select_flags_kernel, dim3((g.N + sast::kSelWarps - 1) / sast::kSelWarps, g.B, nf), sast::kSelThreads, 0, st, p);
   SAST_LAUNCH_CHECK();
-  sast::select_scan_kernel<<<dim3(g.B, 1, nf), sast::kSelThreads, smem, st>>>(p);
+  sast::launch_k(sast::select_scan_kernel, dim3(g.B, 1, nf), sast::kSelThreads, smem, st, p);
   SAST_LAUNCH_CHECK();
-  sast::select_tokens_kernel<<<dim3(wblocks, 1, nf), sast::kSelThreads, 0, st>>>(p);
+  sast::launch_k(sast::select_tokens_kernel, dim3(wblocks, 1, nf), sast::kSelThreads, 0, st, p);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

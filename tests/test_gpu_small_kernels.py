@@ -121,4 +121,4 @@ def test_gemm_glu_epilogue(M, I, K):
     Wi = torch.stack((W[:I], W[I:]), dim=1).reshape(2 * I, K)
     bi = torch.stack((b[:I], b[I:]), dim=1).reshape(-1)
     got = ops.gemm_bf16_glu(A.to(DEV), Wi.to(DEV), bi.to(DEV)).float().cpu()
-    assert (got - ref).abs().max() < 3e-2 and ((got - ref).abs() / (ref.abs() + 1.0)).max() < 1e-2
+    assert ((got - ref).abs() / (ref.abs() + 1.0)).max() < 1e-2      # bf16 output: 2^-8 relative
