@@ -8,7 +8,7 @@
 //   warp 0   TMA producer   (one lane; ring of 4 {A 128x64, W BNx64} bf16 stages, runs ahead across tiles)
 //   warp 1   TMEM allocator + MMA issuer (one lane; tcgen05.mma M=128,N=BN,K=16, 4 per k-block; two
 //            accumulators so the next tile is multiplied while the previous one is drained)
-//   warps 2-9 epilogue (two groups of 4, one per accumulator): tcgen05.ld 32 lanes x 32 columns per warp (warp w owns TMEM
+//   warps 2-   epilogue (two or three groups of 4, one per accumulator): tcgen05.ld 32 lanes x 32 columns per warp (warp w owns TMEM
 //            lanes 32*(w%4)..+31 = output rows); bias / LayerScale / residual / GLU / scatter in registers.
 // M (= number of selected tokens) is read from device memory; CTAs past it exit at once.
 // K tails (K % 64 != 0) rely on TMA zero fill and issue only the k-steps that hold data.
@@ -18,14 +18,17 @@
 namespace sast {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
-constexpr int TC_EPI_WARPS = 8;                       // two groups of 4 (one per TMEM accumulator)
-constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_MAX_GROUPS = 3;
+// epilogue groups of 4 warps, one TMEM accumulator each: the math-heavy epilogues (erf-GELU, LSTM gates: ~30
+// instructions per output) are issue bound, so they get three groups; the rest are fine with two
+constexpr int tc_groups(int epi) { return (epi == EPI_GLU || epi == EPI_LSTM) ? 3 : 2; }
+constexpr int tc_threads(int epi) { return 64 + tc_groups(epi) * 128; }   // warp 0 TMA, warp 1 MMA, then the epilogue warps
 
 struct TcSmem {            // lives after the operand ring (which needs 1024-byte alignment)
   uint64_t full[TC_STAGES];
   uint64_t empty[TC_STAGES];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[TC_MAX_GROUPS];
+  uint64_t tmem_empty[TC_MAX_GROUPS];
   uint32_t tmem_base;
 };
 
@@ -44,14 +47,15 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 // warp ping-pongs between two TMEM accumulators, and the two epilogue groups (4 warps each, one per
 // accumulator) drain tile i while tile i+1 is being loaded and multiplied.
 template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_a2, int k_split,
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const float* __restrict__ bias, int N, int K, int BN, int stages,
                                                                 const int* __restrict__ counts, int m_static, EpiParams ep) {
   pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(16) float stage_smem[TC_EPI_WARPS][32 * 32];   // epilogue transpose tiles (XOR-swizzled 16-byte groups)
+  constexpr int NG = tc_groups(EPI);
+  __shared__ __align__(16) float stage_smem[NG * 4][32 * 32];   // epilogue transpose tiles (XOR-swizzled 16-byte groups)
   const int M = counts ? counts[1] : m_static;
   const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = N / BN;
   const int total_tiles = m_tiles * n_tiles;
@@ -73,11 +77,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     ptx::tma_prefetch_desc(&map_a);
     ptx::tma_prefetch_desc(&map_w);
     for (int s = 0; s < stages; ++s) { ptx::mbar_init(&sm->full[s], 1); ptx::mbar_init(&sm->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&sm->tmem_full[a], 1); ptx::mbar_init(&sm->tmem_empty[a], 4); }
+    for (int a = 0; a < NG; ++a) { ptx::mbar_init(&sm->tmem_full[a], 1); ptx::mbar_init(&sm->tmem_empty[a], 4); }
     ptx::fence_barrier_init();
   }
-  uint32_t tmem_cols = 32;                                          // two accumulators of BN columns, power of two
-  while (tmem_cols < (uint32_t)(2 * BN)) tmem_cols <<= 1;
+  uint32_t tmem_cols = 32;                                          // NG accumulators of BN columns, power of two
+  while (tmem_cols < (uint32_t)(NG * BN)) tmem_cols <<= 1;
   if (warp == 1) ptx::tmem_alloc(&sm->tmem_base, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                                    : ptx::umma_idesc_bf16(TC_BM, (uint32_t)BN);
       uint32_t it = 0, ti = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-        const uint32_t acc = ti & 1, use = ti >> 1;
+        const uint32_t acc = ti % NG, use = ti / NG;
         ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);       // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
@@ -136,8 +140,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int quarter = warp & 3;
     uint32_t ti = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-      if ((int)(ti & 1) != group) continue;
-      const uint32_t use = ti >> 1;
+      if ((int)(ti % NG) != group) continue;
+      const uint32_t use = ti / NG;
       const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
       const uint32_t tmem_d = tmem_base + (uint32_t)group * (uint32_t)BN + ((uint32_t)(quarter * 32) << 16);
       ptx::mbar_wait(&sm->tmem_full[group], use & 1);
@@ -340,7 +344,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* 
   }
   const long long tiles = ((max_rows + TC_BM - 1) / TC_BM) * (N / BN);       // worst case; the kernel clips to counts[1]
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-  sast::launch_k(gemm_tc_kernel<EPI>, grid, TC_THREADS, smem, st, ma, ma2 ? *ma2 : ma, k_split, mw, bias, N, K, BN, stages, counts, m_static, ep);
+  sast::launch_k(gemm_tc_kernel<EPI>, grid, tc_threads(EPI), smem, st, ma, ma2 ? *ma2 : ma, k_split, mw, bias, N, K, BN, stages, counts, m_static, ep);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }
@@ -348,9 +352,9 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* 
 // Widest N tile (multiple of 32, <= 256 so that two accumulators fit the 512 TMEM columns) that divides N:
 // every extra n-tile re-reads the A tile and pays the per-tile hand-shakes again.
 // ... unless that leaves SMs idle: with few row tiles (late stages, small batches) narrower tiles win.
-static int pick_bn(int N, long long m_tiles = 1 << 20) {
+static int pick_bn(int N, long long m_tiles = 1 << 20, int groups = 2) {
   int best = 0;
-  for (int bn = 256; bn >= 32; bn -= 32) {
+  for (int bn = 512 / groups / 32 * 32; bn >= 32; bn -= 32) {      // `groups` accumulators must fit the 512 TMEM columns
     if (N % bn != 0) continue;
     if (!best) best = bn;
     if (m_tiles * (N / bn) >= sm_count()) return bn;     // widest tile that still fills the chip
@@ -361,7 +365,7 @@ static int pick_bn(int N, long long m_tiles = 1 << 20) {
 
 int launch_gemm_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, int N, int K, const int* counts,
                    long long max_rows, int epi, const EpiParams& ep, cudaStream_t st) {
-  const int BN = pick_bn(N, (max_rows + TC_BM - 1) / TC_BM);
+  const int BN = pick_bn(N, (max_rows + TC_BM - 1) / TC_BM, tc_groups(epi));
   if (BN == 0 || K % 8 != 0 || lda % 8 != 0) return SAST_E_SHAPE;
   CUtensorMap ma, mw;
   int rc = make_tmap_bf16_2d(&ma, A, max_rows, K, lda, TC_BM);
@@ -389,7 +393,7 @@ extern "C" int sast_lstm_fwd(const float* x, const float* h_prev, const float* c
   if (P <= 0 || C <= 0 || C % 8 != 0 || P >= (1ll << 31)) return SAST_E_SHAPE;
   if ((h_prev == nullptr) != (c_prev == nullptr)) return SAST_E_NULL;
   const int K = h_prev ? 2 * C : C, N = 4 * C;
-  const int BN = pick_bn(N, (P + TC_BM - 1) / TC_BM);
+  const int BN = pick_bn(N, (P + TC_BM - 1) / TC_BM, tc_groups(EPI_LSTM));
   if (BN == 0) return SAST_E_SHAPE;
   CUtensorMap ma, ma2, mw;
   int rc = make_tmap_f32_box(&ma, x, P, C, C, 32, TC_BM);
@@ -409,7 +413,7 @@ extern "C" int sast_gemm_bf16_glu(const uint16_t* A, const uint16_t* W, const fl
   using namespace sast;
   SAST_CHECK_PTR(A); SAST_CHECK_PTR(W); SAST_CHECK_PTR(D);
   if (M <= 0 || N <= 0 || K <= 0 || N % 64 != 0) return SAST_E_SHAPE;
-  const int BN = pick_bn(N, (M + TC_BM - 1) / TC_BM);
+  const int BN = pick_bn(N, (M + TC_BM - 1) / TC_BM, tc_groups(EPI_GLU));
   if (BN == 0 || K % 8 != 0) return SAST_E_SHAPE;
   CUtensorMap ma, mw;
   int rc = make_tmap_bf16_2d(&ma, A, M, K, K, TC_BM);
