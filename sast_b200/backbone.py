@@ -99,6 +99,10 @@ class ConvDownsampling_Cf2Cl(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         """x: NCHW (the stem takes the raw uint8 / int32 / float histogram; later stages take the
         previous stage's h, NCHW-logical over channels-last memory).  Returns NHWC fp32."""
+        if torch.is_grad_enabled() and (x.requires_grad or self.conv.weight.requires_grad):
+            # training: the dense callers run as stock differentiable torch ops (cuDNN conv + LayerNorm)
+            y = self.conv(x.float()).permute(0, 2, 3, 1)
+            return self.norm(y)
         pad = self.conv.padding[0] if isinstance(self.conv.padding, tuple) else int(self.conv.padding)
         if x.is_contiguous() and not (x.shape[1] == 1 or x.shape[2:] == (1, 1)):
             xp = ops.pad_input(x, pad)
@@ -153,8 +157,8 @@ class DWSConvLSTM2d(nn.Module):
     def forward(self, x: Tensor, h_and_c_previous: LstmState = None) -> Tuple[Tensor, Tensor]:
         """x: [N,C,H,W] (any memory format; channels-last makes every step copy-free).  Returns
         (h, c) as NCHW-logical tensors over channels-last memory."""
-        fusable = isinstance(self.conv3x3_dws, nn.Identity) and not self.training and self.dim % 8 == 0 and \
-            not (torch.is_grad_enabled() and self.conv1x1.weight.requires_grad)
+        fusable = isinstance(self.conv3x3_dws, nn.Identity) and self.dim % 8 == 0 and \
+            not (torch.is_grad_enabled() and (x.requires_grad or self.conv1x1.weight.requires_grad))
         if fusable and self.precision == L.FP32:
             # validation grade: the 1x1 conv through cuDNN/cuBLAS (fp32 when TF32 is disabled), gates fused
             C = self.dim

@@ -255,6 +255,29 @@ class MS_WSA(nn.Module):
         self._pack_key, self._packed = key, ws
         return ws
 
+    def run_autograd(self, xw: Tensor, sel_mask: Tensor, B: int, enable_CB: bool) -> Tensor:
+        """Differentiable form for training (xw [B*N,T,C] partitioned, sel_mask [B*N,T] bool): the dense-equivalent
+        statement of the layer in plain torch ops, so autograd provides the backward.  Selection
+        is not differentiable in the reference either (gradients reach to_scores / to_controls only through
+        the STP weight, SAST.py:113-114).  Hand-written backward kernels are round-2 work."""
+        F_ = nn.functional
+        Wn, T, C = xw.shape
+        n1 = self.norm1(xw)
+        n2 = self.norm2(n1)
+        qkv = self.qkv(n2).view(Wn, T, self.num_heads, 3 * self.dim_head).transpose(1, 2)
+        q, k, v = qkv.chunk(3, dim=3)
+        att = (q @ k.transpose(-2, -1)) * self.scale
+        att = att.masked_fill(~sel_mask[:, None, None, :], float("-inf"))
+        att = torch.nan_to_num(att.softmax(dim=-1), nan=0.0)
+        o = self.proj((att @ v).transpose(1, 2).reshape(Wn, T, C))
+        y = n2 + self.ls1(o)
+        m = self.mlp(y)
+        if enable_CB:
+            ms = torch.where(sel_mask[..., None], m, torch.zeros_like(m)).view(B, -1, C)
+            m = (0.5 * ms + 0.5 * ms.mean(dim=1, keepdim=True)).view(Wn, T, C)
+        out = y + self.ls2(m)
+        return torch.where(sel_mask[..., None], out, n1)
+
     def run(self, x: Tensor, sel: ops.Selection, flavor: int, enable_CB: bool) -> Tensor:
         """x [B,H,W,C] NHWC with a window/grid selection -> [B,H,W,C]."""
         return ops.layer_fwd(x, sel.pool, self.packed_weights(), sel.p0, sel.p1, flavor, self.precision,
@@ -349,6 +372,8 @@ class SAST_block(nn.Module):
         N = H * W // T
         self.B, self.N = B, N
         pos = self._position(pos_emb, x)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._partition_attn_autograd(x, pos, r, index_list)
         if self.first_block:
             w_hi, w_lo = self._score_split()
             xw, tok = ops.score_fwd(x, pos, r, self.to_controls.weight, self.to_scores.weight, self.to_scores.bias,
@@ -364,6 +389,39 @@ class SAST_block(nn.Module):
             sel2 = self._as_selection(index_list[1], B, H, W, L.GRID)
         x1 = self.win_attn.run(xw, sel1, L.WINDOW, self.enable_CB)
         x2 = self.grid_attn.run(x1, sel2, L.GRID, self.enable_CB)
+        count = LazyCount((sel1.counts[1], B), (sel2.counts[1], B))
+        return x2, count, [sel1, sel2]
+
+    def _partition_attn_autograd(self, x: Tensor, pos: Tensor, r: Tensor, index_list):
+        """Training path: selection by the CUDA kernels (no gradient, as in the reference), everything that
+        carries gradient in differentiable torch ops (see MS_WSA.run_autograd)."""
+        B, H, W, C = x.shape
+        p0, p1 = self.partition_size
+        T = p0 * p1
+        N = H * W // T
+        x0 = x + (pos if pos.dim() == 4 else pos.unsqueeze(0))
+        if self.first_block:
+            ctrl = self.to_controls(r + 1e-6)[:, None, None, :]
+            s = self.act(self.to_scores(x0))
+            xw = ctrl.sigmoid() * s.sigmoid() * x0
+            with torch.no_grad():
+                inv = self.amp_value / ctrl
+                inv = torch.where(torch.isinf(inv), torch.zeros_like(inv), inv)
+                tok = (inv * s).abs().sum(-1).contiguous()                      # [B,H,W] per-token score
+                thr_w, thr_t = ops.thresholds(N, T, self.bounce_value)
+                pool1, pool2 = ops.select_pair(tok, p0, p1, thr_w, thr_t)
+            sel1 = ops.Selection(pool1, B, H, W, p0, p1)
+            sel2 = ops.Selection(pool2, B, H, W, p0, p1)
+        else:
+            xw = x0
+            sel1 = self._as_selection(index_list[0], B, H, W, L.WINDOW)
+            sel2 = self._as_selection(index_list[1], B, H, W, L.GRID)
+        m1 = (sel1.tok_row >= 0).view(B * N, T)
+        m2 = (sel2.tok_row >= 0).view(B * N, T)
+        x1 = self.win_attn.run_autograd(window_partition(xw, (p0, p1)).reshape(B * N, T, C), m1, B, self.enable_CB)
+        x1 = window_reverse(x1, (p0, p1), (H, W))
+        x2 = self.grid_attn.run_autograd(grid_partition(x1, (p0, p1)).reshape(B * N, T, C), m2, B, self.enable_CB)
+        x2 = grid_reverse(x2, (p0, p1), (H, W))
         count = LazyCount((sel1.counts[1], B), (sel2.counts[1], B))
         return x2, count, [sel1, sel2]
 

@@ -158,3 +158,37 @@ def test_block_bf16_against_fp32_path(C, part, B, H, W, amp, r_scale):
     assert torch.isfinite(outs[L.BF16][0]).all()
     err = (outs[L.FP32][0] - outs[L.BF16][0]).abs().max().item()
     assert err < 6e-2, err
+
+
+def test_block_training_gradients_match_oracle(golden):
+    """Training path (selection by the kernels, differentiable torch ops for everything that carries
+    gradient): loss and every parameter gradient against autograd through the CPU oracle."""
+    g = golden("block_c64_w6x10")
+    m = g.meta
+    blk, params = build_block(m, L.FP32)
+    blk.train()
+    pos = pos_module(m)
+    x = g.t("x")
+    wgt = torch.randn(x.shape, generator=torch.Generator().manual_seed(3))
+    # oracle side (CPU autograd)
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    x_ref = x.clone().requires_grad_(True)
+    y_ref, cnt_ref, _ = O.sast_block(x_ref, O.position_table(m["H"], m["W"], m["C"]), g.t("r"), p_ref, tuple(m["part"]),
+                                     amp=m["AMP"], bounce=m["BOUNCE"], enable_CB=m["enable_CB"])
+    (y_ref * wgt).sum().backward()
+    # product side
+    x_gpu = x.to(DEV).requires_grad_(True)
+    y, cnt, _ = blk(x_gpu, pos, g.t("r").to(DEV), None)
+    assert int(cnt) == cnt_ref
+    assert (y.detach().cpu() - y_ref.detach()).abs().max() < 2e-4
+    (y * wgt.to(DEV)).sum().backward()
+    assert (x_gpu.grad.cpu() - x_ref.grad).abs().max() < 2e-3 * x_ref.grad.abs().max()
+    sd = dict(blk.named_parameters())
+    checked = 0
+    for k, ref in p_ref.items():
+        got = sd[k].grad
+        assert got is not None, k
+        scale = ref.grad.abs().max().clamp_min(1e-6)
+        assert (got.cpu() - ref.grad).abs().max() < 2e-3 * scale, k
+        checked += 1
+    assert checked == len(params)

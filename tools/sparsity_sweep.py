@@ -43,10 +43,15 @@ for (C, H, W, tag) in ((64, 96, 160, "stage1"), (256, 24, 40, "stage3")):
             sel = ops.Selection(ops.select_from_flags(wf.to(dev), tf.to(dev), B, H, W, p0, p1, L.WINDOW), B, H, W, p0, p1)
             S = int(sel.counts[1])
 
-            def run():
+            # one layer call captured in a CUDA graph: the replay is timed, not the Python dispatch
+            with torch.no_grad():
+                for _ in range(2):
+                    layer.run(x, sel, L.WINDOW, False)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph), torch.no_grad():
                 layer.run(x, sel, L.WINDOW, False)
-
-            t = _time_kernel(run, dev, iters=10)
+            t = _time_kernel(graph.replay, dev, iters=10)
             min_bytes = 2.0 * P * C * 4
             print(json.dumps({"shape": tag, "C": C, "tokens": P, "precision": pname, "keep_target": keep,
                               "keep_actual": S / P, "selected": S, "us_per_layer": t * 1e6,
