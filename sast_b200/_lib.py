@@ -89,6 +89,7 @@ def _load():
         "sast_pad_nhwc": (C.c_int, [vp, i32, i32, i32, i32, i32, i64, i64, i64, vp, vp]),
         "sast_layernorm": (C.c_int, [vp, vp, vp, f32, i64, i32, vp, vp]),
         "sast_lstm_gates": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp]),
+        "sast_stem_fwd": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, f32, vp, vp]),
         "sast_lstm_fwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -106,7 +107,7 @@ def _load():
 EXPORTS = ("sast_abi_version", "sast_build_info", "sast_struct_size", "sast_launch_count", "sast_selection_bytes", "sast_selection_bind",
            "sast_nonzero_ratio", "sast_score_fwd", "sast_select", "sast_select2", "sast_layer_workspace_bytes",
            "sast_layer_fwd", "sast_gather", "sast_scatter", "sast_gemm_bf16", "sast_gemm_bf16_glu", "sast_pad_input", "sast_pad_nhwc",
-           "sast_layernorm", "sast_lstm_gates", "sast_lstm_fwd")
+           "sast_layernorm", "sast_lstm_gates", "sast_lstm_fwd", "sast_stem_fwd")
 
 _lib = None
 

@@ -87,6 +87,22 @@ class ConvDownsampling_Cf2Cl(nn.Module):
                               bias=False, padding_mode='replicate')
         self.norm = nn.LayerNorm(dim_out, eps=1e-5, elementwise_affine=norm_affine)
 
+    def _fused_stem_ok(self, x: Tensor, pad: int) -> bool:
+        """uint8 histograms through the one-kernel stem (implicit GEMM on tcgen05 + LayerNorm); other dtypes
+        and geometries take the cuDNN route below."""
+        c = self.conv
+        return (x.dtype == torch.uint8 and x.dim() == 4 and tuple(c.kernel_size) == (7, 7) and tuple(c.stride) == (4, 4)
+                and pad == 3 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0 and c.out_channels % 32 == 0
+                and c.out_channels <= 256 and getattr(self, "fused_stem", True))
+
+    def _stem_pack(self):
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_skey", None) != key:
+            self._spack = ops.pack_stem_weight(w)
+            self._skey = key
+        return self._spack
+
     def _weight_cl(self) -> Tensor:
         """Conv weight in channels-last memory format (what the NHWC cuDNN kernels want), cached."""
         w = self.conv.weight
@@ -104,6 +120,9 @@ class ConvDownsampling_Cf2Cl(nn.Module):
             y = self.conv(x.float()).permute(0, 2, 3, 1)
             return self.norm(y)
         pad = self.conv.padding[0] if isinstance(self.conv.padding, tuple) else int(self.conv.padding)
+        if self._fused_stem_ok(x, pad):
+            w_hi, w_lo, gpad = self._stem_pack()
+            return ops.stem_fwd(x, w_hi, w_lo, gpad, self.norm.weight, self.norm.bias, self.norm.eps)
         if x.is_contiguous() and not (x.shape[1] == 1 or x.shape[2:] == (1, 1)):
             xp = ops.pad_input(x, pad)
         else:

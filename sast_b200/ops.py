@@ -532,3 +532,40 @@ def gemm_bf16_glu(A: Tensor, Wt_interleaved: Tensor, bias_interleaved: Optional[
     L.check(L.lib().sast_gemm_bf16_glu(A.data_ptr(), Wt.data_ptr(), L.ptr(bias_interleaved), D.data_ptr(), M, N, K,
                                        L.stream_ptr(A.device)), "sast_gemm_bf16_glu")
     return D
+
+
+def pack_stem_weight(w: Tensor) -> Tuple[Tensor, Tensor, int]:
+    """conv.weight [Cout,Cin,7,7] fp32 -> (w_hi, w_lo) bf16 [Cout, G*8] with K ordered (c, ky, kx padded to 8) and the
+    Cin*7 (c,ky) groups padded to a multiple of 8; w_hi + w_lo ~= w to 2^-17."""
+    Cout, Cin, kh, kw = w.shape
+    assert (kh, kw) == (7, 7)
+    groups = Cin * 7
+    gpad = (groups + 7) // 8 * 8
+    wp = torch.zeros(Cout, gpad, 8, device=w.device, dtype=torch.float32)
+    wp[:, :groups, :7] = w.detach().float().reshape(Cout, groups, 7)
+    wp = wp.reshape(Cout, gpad * 8)
+    hi = wp.to(torch.bfloat16)
+    lo = (wp - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous(), gpad
+
+
+@torch.library.custom_op("sast::stem_fwd", mutates_args=())
+def stem_fwd(x: Tensor, w_hi: Tensor, w_lo: Tensor, n_groups_pad: int, ln_w: Optional[Tensor], ln_b: Optional[Tensor],
+             eps: float) -> Tensor:
+    """uint8 [B,Cin,H,W] -> LayerNorm(conv7x7/4) fp32 NHWC [B,H/4,W/4,Cout]; see sast_stem_fwd."""
+    L.require_cuda(x, "x")
+    assert x.dtype == torch.uint8
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    Cout = w_hi.shape[0]
+    out = torch.empty(B, H // 4, W // 4, Cout, device=x.device, dtype=torch.float32)
+    L.check(L.lib().sast_stem_fwd(x.data_ptr(), B, Cin, H, W, w_hi.data_ptr(), w_lo.data_ptr(), Cout, n_groups_pad,
+                                  L.ptr(ln_w), L.ptr(ln_b), float(eps), out.data_ptr(), L.stream_ptr(x.device)),
+            "sast_stem_fwd")
+    return out
+
+
+@stem_fwd.register_fake
+def _(x, w_hi, w_lo, n_groups_pad, ln_w, ln_b, eps):
+    B, Cin, H, W = x.shape
+    return x.new_empty(B, H // 4, W // 4, w_hi.shape[0], dtype=torch.float32)

@@ -96,3 +96,30 @@ def test_downsample_module(cin, cout, factor, dtype):
         assert (got2.cpu() - ref).abs().max() < 5e-5
     finally:
         torch.backends.cudnn.allow_tf32 = True
+
+
+@pytest.mark.parametrize("B,H,W,cout,density", [(2, 48, 80, 64, 0.1), (1, 384, 640, 64, 0.3), (3, 36, 52, 32, 0.9), (2, 64, 64, 128, 0.02)])
+def test_fused_stem(B, H, W, cout, density):
+    """sast_stem_fwd (implicit-GEMM 7x7/4 conv with replicate padding + LayerNorm, uint8 in) against the oracle's
+    fp32 conv: the bf16 hi/lo weight split keeps it fp32-grade (no TF32-sized error)."""
+    mod = sast_b200.ConvDownsampling_Cf2Cl(20, cout, 4, Config(type="patch", overlap=True, norm_affine=True)).eval()
+    p = make_params({"conv.weight": (cout, 20, 7, 7), "norm.weight": (cout,), "norm.bias": (cout,)}, seed=cout + H)
+    mod.load_state_dict(p)
+    mod = mod.to(DEV)
+    x = event_histogram(B, 20, H, W, density, seed=H)
+    x[:, :, 0, :] = 7          # make the replicated borders matter
+    x[:, :, :, 0] = 9
+    x[:, :, -1, :] = 3
+    x[:, :, :, -1] = 5
+    ref = O.conv_downsample(x.float(), p, 4)
+    with torch.no_grad():
+        got = mod(x.to(DEV))
+        mod.fused_stem = False
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            got_cudnn = mod(x.to(DEV))
+        finally:
+            torch.backends.cudnn.allow_tf32 = True
+    assert got.shape == ref.shape
+    assert (got.cpu() - ref).abs().max() < 1e-4, (got.cpu() - ref).abs().max()
+    assert (got_cudnn.cpu() - ref).abs().max() < 1e-4
