@@ -93,20 +93,27 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       const int b = pp / (Ho * Wo), rem = pp - b * (Ho * Wo);
       const int oy = rem / Wo, ox = rem - oy * Wo;
       const uint8_t* xb = x + (size_t)b * Cin * H * W;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const uint32_t s = it % ST_STAGES, round = it / ST_STAGES;
-        uint32_t w0[4], w1[4], w2[4];
+      // input words of one k-block: 4 groups x {left, centre, right} aligned words; the NEXT k-block's words are
+      // requested before the current ones are converted (software pipelining: the loads never sit on the
+      // critical path of the conversion)
+      uint32_t w0[4], w1[4], w2[4], n0[4], n1[4], n2[4];
+      auto load_block = [&](int kb, uint32_t (&a0)[4], uint32_t (&a1)[4], uint32_t (&a2)[4]) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {          // global loads first: independent of the ring slot
+        for (int j = 0; j < 4; ++j) {
           int gidx = kb * 8 + gh * 4 + j;
           if (gidx >= n_groups) gidx = n_groups - 1;          // padding groups: finite data, zero weights
           const int c = gidx / 7, ky = gidx - c * 7;
           const int iy = min(max(4 * oy - 3 + ky, 0), H - 1);  // replicate padding (rows)
           const uint32_t* row = reinterpret_cast<const uint32_t*>(xb + ((size_t)c * H + iy) * W);
-          w1[j] = row[ox];                                      // columns 4ox .. 4ox+3
-          w0[j] = ox > 0 ? row[ox - 1] : (w1[j] & 0xFFu) * 0x01010101u;   // replicate padding (left edge)
-          w2[j] = (ox + 1 < Wo) ? row[ox + 1] : 0u;             // only tap 7 (zero weight) reads it
+          a1[j] = row[ox];                                      // columns 4ox .. 4ox+3
+          a0[j] = ox > 0 ? row[ox - 1] : (a1[j] & 0xFFu) * 0x01010101u;   // replicate padding (left edge)
+          a2[j] = (ox + 1 < Wo) ? row[ox + 1] : 0u;             // only tap 7 (zero weight) reads it
         }
+      };
+      load_block(0, w0, w1, w2);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % ST_STAGES, round = it / ST_STAGES;
+        if (kb + 1 < nkb) load_block(kb + 1, n0, n1, n2);
         ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
         uint8_t* st = base + (size_t)s * stage_bytes;
         if (t == 0) {
@@ -127,6 +134,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
         }
         ptx::fence_proxy_async();
         ptx::mbar_arrive(&sm->full[s]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { w0[j] = n0[j]; w1[j] = n1[j]; w2[j] = n2[j]; }
       }
     }
   } else if (warp == 8) {
