@@ -220,9 +220,9 @@ int sast_lstm_gates(const float* mix, const float* bias, const float* c_prev, in
 /*
  * Stem as one kernel (ref: sast_rnn.py:153 x.float(), ops.py:54-91 ConvDownsampling_Cf2Cl with patch_size 4):
  * x [B,Cin,H,W] uint8 NCHW -> out [B,H/4,W/4,Cout] fp32 NHWC = LayerNorm(conv 7x7, stride 4, replicate padding 3,
- * no bias), an implicit GEMM on tcgen05.  Weights come pre-packed: bf16 [Cout, n_groups_pad*8], K ordered
+ * no bias), an implicit GEMM on tcgen05.  Weights come pre-packed: fp16 [Cout, n_groups_pad*8], K ordered
  * (c, ky, kx) with kx padded 7 -> 8 and (c,ky) groups padded to a multiple of 8 (zeros), split w = w_hi + w_lo
- * so that the product is fp32-grade (event counts are exact in bf16).  H, W % 4 == 0; Cout % 32 == 0, <= 256.
+ * so that the product is fp32-grade (event counts are exact in fp16).  H, W % 4 == 0; Cout % 32 == 0, <= 256.
  */
 int sast_stem_fwd(const uint8_t* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const uint16_t* w_hi,
                   const uint16_t* w_lo, int32_t Cout, int32_t n_groups_pad, const float* ln_w, const float* ln_b,

@@ -4,13 +4,13 @@
 //
 // Implicit GEMM on tcgen05: M = output pixels (128 per tile), N = Cout, K ordered (c, ky, kx) with kx padded
 // 7 -> 8 so that one (c, ky) group is 8 consecutive input bytes = one 16-byte bf16 chunk of the A operand.
-// Event counts are small integers: exact in bf16.  The fp32 weights are split w = w_hi + w_lo (both bf16,
-// |w - w_hi - w_lo| <= 2^-17 |w|) and both halves are multiplied, so the result is fp32-grade (tighter than
-// the TF32 path cuDNN takes by default) at bf16 tensor-core speed.
+// Event counts are small integers: exact in fp16.  The fp32 weights are split w = w_hi + w_lo (both fp16,
+// |w - w_hi - w_lo| <= ~2^-22 |w| for the weight magnitudes of a conv layer) and both halves are multiplied, so
+// the result is fp32-grade (tighter than the TF32 path cuDNN takes by default) at 16-bit tensor-core speed.
 //
 // Persistent CTAs, 14 warps:
 //   warps 0-7   A producers: two threads per output pixel, four (c,ky) groups each per k-block: three coalesced
-//               32-bit loads (L1-resident input rows) -> 8 bytes -> 8 bf16 -> one STS.128 into the SWIZZLE_128B tile;
+//               32-bit loads (L1-resident input rows) -> 8 bytes -> 8 fp16 -> one STS.128 into the SWIZZLE_128B tile;
 //               thread 0 also TMA-loads the packed weight tiles
 //   warp 8      TMEM allocator + MMA issuer (two accumulators)
 //   warp 9      idle (keeps the epilogue warps on TMEM lane quarters 2,3,0,1)
@@ -18,6 +18,7 @@
 //               shared-memory transpose, dense 128-byte row stores
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cuda_fp16.h>
 
 namespace sast {
 
@@ -32,16 +33,14 @@ struct StSmem {
   uint32_t tmem_base;
 };
 
-// four bytes (one 32-bit word, little endian) -> two packed bf16x2 words; bytes are exact in bf16
-__device__ __forceinline__ void bytes4_to_bf16x4(uint32_t w, uint32_t& lo, uint32_t& hi) {
-  // float(b) = as_float(0x4B000000 | b) - 2^23, exact; bf16 keeps it exactly for b < 256
-  const float f0 = __uint_as_float(0x4B000000u | (w & 0xFFu)) - 8388608.0f;
-  const float f1 = __uint_as_float(0x4B000000u | ((w >> 8) & 0xFFu)) - 8388608.0f;
-  const float f2 = __uint_as_float(0x4B000000u | ((w >> 16) & 0xFFu)) - 8388608.0f;
-  const float f3 = __uint_as_float(0x4B000000u | (w >> 24)) - 8388608.0f;
-  const __nv_bfloat162 a = __floats2bfloat162_rn(f0, f1), b = __floats2bfloat162_rn(f2, f3);
-  lo = *reinterpret_cast<const uint32_t*>(&a);
-  hi = *reinterpret_cast<const uint32_t*>(&b);
+// four bytes (one 32-bit word, little endian) -> two packed f16x2 words, exactly: the f16 with bits 0x6400|b is
+// 1024 + b, so one PRMT builds two such halves and one HSUB2 removes the 1024 (2 instructions per 2 bytes)
+__device__ __forceinline__ void bytes4_to_f16x4(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  const uint32_t a = __byte_perm(w, 0x64646464u, 0x4140), b = __byte_perm(w, 0x64646464u, 0x4342);
+  const __half2 k = __half2half2(__ushort_as_half((unsigned short)0x6400));
+  const __half2 ra = __hsub2(*reinterpret_cast<const __half2*>(&a), k), rb = __hsub2(*reinterpret_cast<const __half2*>(&b), k);
+  lo = *reinterpret_cast<const uint32_t*>(&ra);
+  hi = *reinterpret_cast<const uint32_t*>(&rb);
 }
 
 __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_constant__ CUtensorMap map_whi,
@@ -105,9 +104,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
           const int c = gidx / 7, ky = gidx - c * 7;
           const int iy = min(max(4 * oy - 3 + ky, 0), H - 1);  // replicate padding (rows)
           const uint32_t* row = reinterpret_cast<const uint32_t*>(xb + ((size_t)c * H + iy) * W);
+          // three aligned words; nothing here may depend on a loaded value (the loads must stay in flight):
+          // the left-edge replicate is patched in at conversion time
           a1[j] = row[ox];                                      // columns 4ox .. 4ox+3
-          a0[j] = ox > 0 ? row[ox - 1] : (a1[j] & 0xFFu) * 0x01010101u;   // replicate padding (left edge)
-          a2[j] = (ox + 1 < Wo) ? row[ox + 1] : 0u;             // only tap 7 (zero weight) reads it
+          a0[j] = row[ox > 0 ? ox - 1 : ox];
+          a2[j] = row[ox + 1 < Wo ? ox + 1 : ox];               // only tap 7 (zero weight) reads it
         }
       };
       load_block(0, w0, w1, w2);
@@ -124,11 +125,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           // taps kx = 0..7 are input columns 4ox-3 .. 4ox+4: bytes 1..3 of w0, all of w1, byte 0 of w2
+          if (ox == 0) w0[j] = (w1[j] & 0xFFu) * 0x01010101u;          // replicate padding (left edge)
           const uint32_t lo4 = __byte_perm(w0[j], w1[j], 0x4321);      // columns 4ox-3 .. 4ox
           const uint32_t hi4 = __byte_perm(w1[j], w2[j], 0x4321);      // columns 4ox+1 .. 4ox+4
           uint4 v;
-          bytes4_to_bf16x4(lo4, v.x, v.y);
-          bytes4_to_bf16x4(hi4, v.z, v.w);
+          bytes4_to_f16x4(lo4, v.x, v.y);
+          bytes4_to_f16x4(hi4, v.z, v.w);
           const int g = gh * 4 + j;
           *reinterpret_cast<uint4*>(st + (uint32_t)(m >> 3) * 1024 + (uint32_t)(m & 7) * 128 + (uint32_t)((g ^ (m & 7)) * 16)) = v;
         }
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
   } else if (warp == 8) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(ST_BM, (uint32_t)Cout);
+      const uint32_t idesc = (1u << 4) | (((uint32_t)Cout >> 3) << 17) | ((ST_BM >> 4) << 24);   // kind::f16: A = B = F16, D = F32, K-major
       uint32_t it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1, use = ti >> 1;
@@ -243,8 +245,8 @@ int make_tmap_bf16_box(CUtensorMap* m, const void* ptr, long long rows, int cols
 }  // namespace sast
 
 // x [B,Cin,H,W] uint8 NCHW -> out [B,H/4,W/4,Cout] fp32 NHWC = LayerNorm(conv7x7 stride 4, replicate padding 3, no bias).
-// w_hi / w_lo: bf16 [Cout, Kp] with K ordered (c, ky, kx padded to 8), Kp = n_groups_pad*8, zero for padding entries;
-// w_hi + w_lo ~= conv.weight (bf16 split).  H, W multiples of 4; Cout multiple of 32, <= 256.
+// w_hi / w_lo: fp16 [Cout, Kp] with K ordered (c, ky, kx padded to 8), Kp = n_groups_pad*8, zero for padding entries;
+// w_hi + w_lo ~= conv.weight (fp16 split).  H, W multiples of 4; Cout multiple of 32, <= 256.
 extern "C" int sast_stem_fwd(const uint8_t* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const uint16_t* w_hi,
                              const uint16_t* w_lo, int32_t Cout, int32_t n_groups_pad, const float* ln_w, const float* ln_b,
                              float eps, float* out, void* stream) {

@@ -535,8 +535,8 @@ def gemm_bf16_glu(A: Tensor, Wt_interleaved: Tensor, bias_interleaved: Optional[
 
 
 def pack_stem_weight(w: Tensor) -> Tuple[Tensor, Tensor, int]:
-    """conv.weight [Cout,Cin,7,7] fp32 -> (w_hi, w_lo) bf16 [Cout, G*8] with K ordered (c, ky, kx padded to 8) and the
-    Cin*7 (c,ky) groups padded to a multiple of 8; w_hi + w_lo ~= w to 2^-17."""
+    """conv.weight [Cout,Cin,7,7] fp32 -> (w_hi, w_lo) fp16 [Cout, G*8] with K ordered (c, ky, kx padded to 8) and the
+    Cin*7 (c,ky) groups padded to a multiple of 8; w_hi + w_lo ~= w to ~2^-22."""
     Cout, Cin, kh, kw = w.shape
     assert (kh, kw) == (7, 7)
     groups = Cin * 7
@@ -544,8 +544,8 @@ def pack_stem_weight(w: Tensor) -> Tuple[Tensor, Tensor, int]:
     wp = torch.zeros(Cout, gpad, 8, device=w.device, dtype=torch.float32)
     wp[:, :groups, :7] = w.detach().float().reshape(Cout, groups, 7)
     wp = wp.reshape(Cout, gpad * 8)
-    hi = wp.to(torch.bfloat16)
-    lo = (wp - hi.float()).to(torch.bfloat16)
+    hi = wp.to(torch.float16)
+    lo = (wp - hi.float()).to(torch.float16)
     return hi.contiguous(), lo.contiguous(), gpad
 
 
