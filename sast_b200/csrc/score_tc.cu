@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
   if (threadIdx.x == 0) {
     ptx::tma_prefetch_desc(&map_whi);
     ptx::tma_prefetch_desc(&map_wlo);
-    for (int s = 0; s < SC_STAGES; ++s) { ptx::mbar_init(&sm->full[s], 129); ptx::mbar_init(&sm->empty[s], 1); }
+    for (int s = 0; s < SC_STAGES; ++s) { ptx::mbar_init(&sm->full[s], 5 /* 4 loader warps + the TMA expect_tx arrive */); ptx::mbar_init(&sm->empty[s], 1); }
     for (int a = 0; a < SC_GROUPS; ++a) { ptx::mbar_init(&sm->tmem_full[a], 1); ptx::mbar_init(&sm->tmem_empty[a], 4); }
     ptx::fence_barrier_init();
   }
@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
           *reinterpret_cast<float4*>(st + a_bytes + off) = make_float4(to_tf32(a0 - h0), to_tf32(a1 - h1), to_tf32(a2 - h2), to_tf32(a3 - h3));
         }
         ptx::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
-        ptx::mbar_arrive(&sm->full[s]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sm->full[s]);     // one arrive per warp, not per thread
       }
     }
   } else if (warp == SC_MMA_WARP) {

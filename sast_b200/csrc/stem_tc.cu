@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     ptx::tma_prefetch_desc(&map_whi);
     ptx::tma_prefetch_desc(&map_wlo);
-    for (int s = 0; s < ST_STAGES; ++s) { ptx::mbar_init(&sm->full[s], 257); ptx::mbar_init(&sm->empty[s], 1); }
+    for (int s = 0; s < ST_STAGES; ++s) { ptx::mbar_init(&sm->full[s], 9 /* 8 producer warps + the TMA expect_tx arrive */); ptx::mbar_init(&sm->empty[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&sm->tmem_full[a], 1); ptx::mbar_init(&sm->tmem_empty[a], 4); }
     ptx::fence_barrier_init();
   }
@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
           *reinterpret_cast<uint4*>(st + (uint32_t)(m >> 3) * 1024 + (uint32_t)(m & 7) * 128 + (uint32_t)((g ^ (m & 7)) * 16)) = v;
         }
         ptx::fence_proxy_async();
-        ptx::mbar_arrive(&sm->full[s]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sm->full[s]);        // one arrive per warp: 256 serialized smem atomics per k-block otherwise
 #pragma unroll
         for (int j = 0; j < 4; ++j) { w0[j] = n0[j]; w1[j] = n1[j]; w2[j] = n2[j]; }
       }

@@ -192,3 +192,47 @@ def test_block_training_gradients_match_oracle(golden):
         assert (got.cpu() - ref.grad).abs().max() < 2e-3 * scale, k
         checked += 1
     assert checked == len(params)
+
+
+@pytest.mark.parametrize("case", ["single_window", "T128", "empty_scene", "dense_B1", "many_frames"])
+@pytest.mark.parametrize("precision", [L.FP32, L.BF16], ids=["fp32", "bf16"])
+def test_block_edge_cases_against_oracle(case, precision):
+    """Edge geometries and scenes the domain has: one window per frame (N=1: always selected, SAST.py:260-262
+    comment / Gen1 stage 4), the largest window the kernels take (T=128), an empty scene (r=0: the control
+    signal collapses to exp(W)*1e-6 and selection becomes extremely peaked), a dense single frame, many frames."""
+    from sast_b200.config import attention_config
+    from sast_b200.backbone import PositionEmbeddingSine
+    from oracle.golden_common import make_params, with_aliases
+    C, amp = 64, 2e-3
+    if case == "single_window":
+        part, B, H, W, r_scale = (8, 10), 3, 8, 10, 0.02
+    elif case == "T128":
+        part, B, H, W, r_scale = (8, 16), 2, 16, 32, 0.02
+    elif case == "empty_scene":
+        part, B, H, W, r_scale = (6, 10), 2, 12, 20, 0.0
+    elif case == "dense_B1":
+        part, B, H, W, r_scale, amp = (6, 10), 1, 24, 40, 1.0, 2e-4
+    else:
+        part, B, H, W, r_scale = (4, 5), 40, 8, 10, 0.02
+    blk = sast_b200.SAST_block(C, attention_config(part, AMP=amp), first_block=True)
+    shapes = {k: tuple(v.shape) for k, v in blk.state_dict().items() if ".sub_layers." not in k}
+    params = make_params(shapes, seed=11)
+    blk.load_state_dict(with_aliases(params, blk.state_dict().keys()))
+    blk = blk.to(DEV).eval()
+    blk.win_attn.precision = blk.grid_attn.precision = precision
+    gen = torch.Generator().manual_seed(len(case))
+    x = torch.randn(B, H, W, C, generator=gen) * torch.linspace(0.3, 1.7, W).view(1, 1, W, 1)
+    r = torch.rand(B, 20, generator=gen) * r_scale
+    y_ref, cnt_ref, lists_ref = O.sast_block(x, O.position_table(H, W, C), r, params, part, amp=amp)
+    pos = PositionEmbeddingSine(C // 2, normalize=True, input_size=(1, H, W))
+    with torch.no_grad():
+        y, cnt, lists = blk(x.to(DEV), pos, r.to(DEV), None)
+    assert torch.isfinite(y).all()
+    T = part[0] * part[1]
+    NW = B * (H * W // T)
+    for li in range(2):
+        ref_mask = sel_mask(lists_ref[li][0], lists_ref[li][3], NW, T)
+        got_mask = (lists[li].tok_row >= 0).cpu().view(NW, T)
+        assert torch.equal(got_mask, ref_mask), (case, li, int((got_mask != ref_mask).sum()))
+    assert int(cnt) == cnt_ref
+    assert (y.cpu() - y_ref).abs().max().item() < TOL[precision]
