@@ -7,12 +7,12 @@
 // The compacted buffer holds selected tokens only, so the reference's -1e4 column mask for
 // padding (SAST.py:223-226) has no counterpart: the only mask is "same window".
 //
-// Persistent CTAs: 8 consumer warps (two threads per tile row = TMEM lane, each on half of the key columns) + one
-// producer warp that TMA-prefetches the next (tile, head) unit; thread 0 issues the MMAs.
+// CTA = 256 threads, two threads per tile row (= TMEM lane), each on half of the key columns.  Thread 0 issues TMA and MMA.
+// 128 TMEM columns and 41 KB of shared memory per CTA -> 4 CTAs per SM hide each other's
+// load -> MMA -> softmax -> MMA latency chain.
 //   Q,K,V tiles [128 x 32] bf16: TMA boxes out of the qkv buffer ([rows, 3C], head-major
 //   [h][q,k,v][32]) in SWIZZLE_64B; Q,K are K-major operands, V is the MN-major B operand of PV.
-//   P [128 x 128] bf16 is written by the softmax threads in the SWIZZLE_128B K-major layout; O re-uses the
-//   TMEM columns of S once S has been consumed.
+//   P [128 x 128] bf16 is written by the softmax threads in the SWIZZLE_128B K-major layout.
 #include "layer.cuh"
 #include "ptx.cuh"
 
@@ -64,38 +64,34 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "memory");
 }
 
-// Persistent CTAs (two per SM) walk the windows w = blockIdx.x, +gridDim.x, ...; a window that leads an attention
-// tile (tiles[2w] > 0) yields one work unit per head.  288 threads:
-//   warps 0-7  consumers: warps w and w+4 own TMEM lanes 32*(w%4)..+31 (= tile rows); the low warp of a pair works
-//              on key columns [0,64), the high warp on [64,128).  Thread 0 issues the MMAs.
-//   warp 8     producer (one lane): TMA-loads Q, K, V of the NEXT unit into the other stage of a 2-deep ring
-//              while the current unit is in its softmax -- load latency is off the critical path.
-struct AttnSmem2 {
-  uint64_t full[2], empty[2], bar_s, bar_o;
-  uint32_t tmem_base;
-};
-
-__global__ void __launch_bounds__(288) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
-                                                           __nv_bfloat16* __restrict__ att, int C, int heads, int hsplit, int NW,
+// 256 threads: warps w and w+4 own TMEM lanes 32*(w%4)..+31 (= tile rows); the low warp of a pair works on key
+// columns [0,64), the high warp on [64,128) -- two threads per row halve the softmax latency chain and double
+// the warps the SM can interleave.
+__global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
+                                                           __nv_bfloat16* __restrict__ att, int C, int heads_per_cta,
                                                            const int* __restrict__ tiles, const int* __restrict__ win_row0,
                                                            const int* __restrict__ row_tok, int T) {
   pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float pmax[2][128], psum[2][128];
+  const int w = blockIdx.x;
+  const int rows = tiles[2 * w];
+  if (rows == 0) return;                                   // not a tile leader
+  const int row0 = win_row0[w];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // CTA -> (first window, window step, head range): with few windows the heads are split across CTAs
-  const int hpc = heads / hsplit;
-  const int h_begin = ((int)blockIdx.x % hsplit) * hpc, h_end = h_begin + hpc;
-  const int w_first = (int)blockIdx.x / hsplit, w_step = (int)gridDim.x / hsplit;
+  const int half = warp >> 2;                              // which 64 key columns
+  const int t = (warp & 3) * 32 + lane;                    // tile row = TMEM lane
 
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // stage s: Q | K | V (3 x 8 KB) at base + s*24 KB; P (32 KB) after the two stages
-  uint8_t* sP = base + 6 * AT_TILE;
-  AttnSmem2* sm = reinterpret_cast<AttnSmem2*>(base + 10 * AT_TILE);
+  uint8_t* sQ = base;                                      // Q, K are dead once S = Q K^T has completed:
+  uint8_t* sK = base + AT_TILE;                            // P (32 KB) is written over them
+  uint8_t* sP = base;
+  uint8_t* sV = base + 4 * AT_TILE;
+  AttnSmem* sm = reinterpret_cast<AttnSmem*>(base + 5 * AT_TILE);
 
   if (tid == 0) {
     ptx::tma_prefetch_desc(&map_qkv);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sm->full[i], 1); ptx::mbar_init(&sm->empty[i], 1); }
+    ptx::mbar_init(&sm->bar_load, 1);
     ptx::mbar_init(&sm->bar_s, 1);
     ptx::mbar_init(&sm->bar_o, 1);
     ptx::fence_barrier_init();
@@ -106,187 +102,155 @@ __global__ void __launch_bounds__(288) attention_tc_kernel(const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_s = sm->tmem_base;
   const uint32_t tmem_o = tmem_s;
+  const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
 
-  if (warp == 8) {
-    // ---------------- producer ----------------
-    if (lane == 0) {
-      uint32_t u = 0;
-      for (int w = w_first; w < NW; w += w_step) {
-        if (tiles[2 * w] == 0) continue;
-        const int row0 = win_row0[w];
-        for (int h = h_begin; h < h_end; ++h, ++u) {
-          const uint32_t s = u & 1, round = u >> 1;
-          ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
-          uint8_t* st = base + s * (3 * AT_TILE);
-          ptx::mbar_arrive_expect_tx(&sm->full[s], 3 * AT_TILE);
-          ptx::tma_load_2d(st, &map_qkv, &sm->full[s], h * 96, row0);
-          ptx::tma_load_2d(st + AT_TILE, &map_qkv, &sm->full[s], h * 96 + 32, row0);
-          ptx::tma_load_2d(st + 2 * AT_TILE, &map_qkv, &sm->full[s], h * 96 + 64, row0);
-        }
-      }
-    }
-  } else {
-    // ---------------- consumers ----------------
-    const int half = warp >> 2;                              // which 64 key columns
-    const int t = (warp & 3) * 32 + lane;                    // tile row = TMEM lane
-    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    const float sc = 0.17677669529663688110f * 1.44269504088896340736f;   // 32^-0.5 * log2(e)
-    const int r8 = t & 7;
-    uint8_t* prow = sP + (t >> 3) * 1024 + r8 * 128;
-    uint32_t u = 0;
-    for (int w = w_first; w < NW; w += w_step) {
-      const int rows = tiles[2 * w];
-      if (rows == 0) continue;                               // not a tile leader
-      const int row0 = win_row0[w];
-      // key range of this row: the compacted rows of its own window
-      int lo = 0, hi = 0;
-      if (t < rows) {
-        const int wi = row_tok[row0 + t] / T;
-        lo = win_row0[wi] - row0;
-        hi = win_row0[wi + 1] - row0;
-      }
-      const int rows16 = (rows + 15) & ~15;
-      // 32-column chunks of this warp's half that any of its rows needs
-      const int wlo = max(__reduce_min_sync(kFull, t < rows ? lo : 128) & ~31, half * 64);
-      const int whi = min(__reduce_max_sync(kFull, t < rows ? hi : 0), half * 64 + 64);
-
-      for (int h = h_begin; h < h_end; ++h, ++u) {
-        const uint32_t s = u & 1, round = u >> 1, ph = u & 1;
-        uint8_t* sQ = base + s * (3 * AT_TILE);
-        uint8_t* sK = sQ + AT_TILE;
-        uint8_t* sV = sQ + 2 * AT_TILE;
-        if (tid == 0) {
-          ptx::mbar_wait(&sm->full[s], round & 1);
-          ptx::tc_fence_after();
-          const uint32_t id_s = idesc_bf16(128, 128, 0);
-          const uint64_t dq = desc_sw64_kmajor(ptx::smem_u32(sQ)), dk = desc_sw64_kmajor(ptx::smem_u32(sK));
-          ptx::umma_f16_ss(tmem_s, dq, dk, id_s, 0u);
-          ptx::umma_f16_ss(tmem_s, dq + 2, dk + 2, id_s, 1u);          // +32 bytes: dims 16..31
-          ptx::umma_commit(&sm->bar_s);
-        }
-        ptx::mbar_wait(&sm->bar_s, ph);
-        ptx::tc_fence_after();
-
-        // ---- softmax over this row's window: pass 1 = max over the valid columns of this thread's half ----
-        float mx = -INFINITY;
-        for (int c0 = wlo; c0 < whi; c0 += 32) {
-          uint32_t raw[32];
-          ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
-          ptx::tmem_ld_wait();
-          if (lo <= c0 && c0 + 32 <= hi) {                      // chunk entirely inside this row's window
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = c0 + j;
-              if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(raw[j]));
-            }
-          }
-        }
-        pmax[half][t] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");        // consumers only (the producer warp never joins)
-        mx = fmaxf(pmax[0][t], pmax[1][t]);
-        const float mxs = mx * sc;
-
-        // ---- pass 2: p = 2^((s - max) * scale*log2e), bf16 P into the SWIZZLE_128B operand tile, row sum ----
-        float sum = 0.f;
-        for (int c0 = half * 64; c0 < min(half * 64 + 64, rows16); c0 += 32) {
-          uint32_t pk[16];
-          if (c0 >= wlo && c0 < whi) {
-            uint32_t raw[32];
-            ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
-            ptx::tmem_ld_wait();
-            if (lo <= c0 && c0 + 32 <= hi) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(ex2_fast(fmaf(__uint_as_float(raw[j]), sc, -mxs)),
-                                                                ex2_fast(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs)));
-                const float2 f2 = __bfloat1622float2(b2);        // the row sum uses the bf16-rounded probabilities PV will see
-                sum += f2.x + f2.y;
-                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const int col = c0 + j;
-                float p0 = ex2_fast(fmaf(__uint_as_float(raw[j]), sc, -mxs));
-                float p1 = ex2_fast(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs));
-                p0 = (col >= lo && col < hi) ? p0 : 0.f;
-                p1 = (col + 1 >= lo && col + 1 < hi) ? p1 : 0.f;
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-                const float2 f2 = __bfloat1622float2(b2);
-                sum += f2.x + f2.y;
-                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;
-          }
-          // 32 keys = 4 chunks of 16 bytes, SWIZZLE_128B K-major: chunk index XOR (row % 8)
-          const int kb = c0 >> 6;
-          const int cbase = (c0 & 63) >> 3;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int chunk = (cbase + cc) ^ r8;
-            *reinterpret_cast<uint4*>(prow + kb * 16384 + chunk * 16) = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-          }
-        }
-        psum[half][t] = sum;
-        // V rows past the tile may be uninitialised memory (0 * NaN = NaN): zero the ones the PV product reads
-        if (half == 1 && t >= rows && t < rows16) {
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(sV + t * 64 + cc * 16) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        ptx::fence_proxy_async();                               // generic-proxy smem writes -> visible to tcgen05
-        ptx::tc_fence_before();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tid == 0) {
-          ptx::tc_fence_after();
-          const uint32_t id_o = idesc_bf16(128, 32, 1);
-          const uint32_t pa = ptx::smem_u32(sP), va = ptx::smem_u32(sV);
-          for (int ks = 0; ks < rows16 / 16; ++ks) {
-            const uint64_t dp = ptx::umma_desc_sw128_kmajor(pa + (ks >> 2) * 16384) + (uint64_t)((ks & 3) * 2);
-            const uint64_t dv = desc_sw64_mnmajor(va + ks * 1024);
-            ptx::umma_f16_ss(tmem_o, dp, dv, id_o, ks ? 1u : 0u);
-          }
-          ptx::umma_commit(&sm->bar_o);
-          ptx::umma_commit(&sm->empty[s]);                      // Q, K, V of this stage are free once these MMAs retire
-        }
-        ptx::mbar_wait(&sm->bar_o, ph);
-        ptx::tc_fence_after();
-        {
-          uint32_t raw[16];                                       // this thread's 16 of the 32 output dims
-          tmem_ld_32x16(tmem_o + lane_sel + (uint32_t)(half * 16), raw);
-          ptx::tmem_ld_wait();
-          if (t < rows) {
-            const float il = 1.0f / (psum[0][t] + psum[1][t]);
-            __nv_bfloat16* dst = att + (size_t)(row0 + t) * C + h * 32 + half * 16;
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              uint4 o;
-              __nv_bfloat162 b2;
-              b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 0]) * il, __uint_as_float(raw[cc * 8 + 1]) * il); o.x = *reinterpret_cast<uint32_t*>(&b2);
-              b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 2]) * il, __uint_as_float(raw[cc * 8 + 3]) * il); o.y = *reinterpret_cast<uint32_t*>(&b2);
-              b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 4]) * il, __uint_as_float(raw[cc * 8 + 5]) * il); o.z = *reinterpret_cast<uint32_t*>(&b2);
-              b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 6]) * il, __uint_as_float(raw[cc * 8 + 7]) * il); o.w = *reinterpret_cast<uint32_t*>(&b2);
-              *reinterpret_cast<uint4*>(dst + cc * 8) = o;
-            }
-          }
-        }
-        ptx::tc_fence_before();
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // S, O, pmax/psum, P are free for the next unit
-        ptx::tc_fence_after();
-      }
-    }
+  // key range of this row: the compacted rows of its own window
+  int lo = 0, hi = 0;
+  if (t < rows) {
+    const int wi = row_tok[row0 + t] / T;
+    lo = win_row0[wi] - row0;
+    hi = win_row0[wi + 1] - row0;
   }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
+  const int rows16 = (rows + 15) & ~15;
+  const float sc = 0.17677669529663688110f * 1.44269504088896340736f;   // 32^-0.5 * log2(e)
+  // 32-column chunks of this warp's half that any of its rows needs
+  const int wlo = max(__reduce_min_sync(kFull, t < rows ? lo : 128) & ~31, half * 64);
+  const int whi = min(__reduce_max_sync(kFull, t < rows ? hi : 0), half * 64 + 64);
+  const int r8 = t & 7;
+  uint8_t* prow = sP + (t >> 3) * 1024 + r8 * 128;
+
+  const int h_begin = blockIdx.y * heads_per_cta;
+  for (int hi_ = 0; hi_ < heads_per_cta; ++hi_) {
+    const int h = h_begin + hi_;
+    const uint32_t ph = (uint32_t)(hi_ & 1);
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(&sm->bar_load, 3 * AT_TILE);
+      ptx::tma_load_2d(sQ, &map_qkv, &sm->bar_load, h * 96, row0);
+      ptx::tma_load_2d(sK, &map_qkv, &sm->bar_load, h * 96 + 32, row0);
+      ptx::tma_load_2d(sV, &map_qkv, &sm->bar_load, h * 96 + 64, row0);
+      ptx::mbar_wait(&sm->bar_load, ph);
+      ptx::tc_fence_after();
+      const uint32_t id_s = idesc_bf16(128, 128, 0);
+      const uint64_t dq = desc_sw64_kmajor(ptx::smem_u32(sQ)), dk = desc_sw64_kmajor(ptx::smem_u32(sK));
+      ptx::umma_f16_ss(tmem_s, dq, dk, id_s, 0u);
+      ptx::umma_f16_ss(tmem_s, dq + 2, dk + 2, id_s, 1u);          // +32 bytes: dims 16..31
+      ptx::umma_commit(&sm->bar_s);
+    }
+    ptx::mbar_wait(&sm->bar_s, ph);
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_s, AT_TMEM_COLS);
+
+    // ---- softmax over this row's window: pass 1 = max over the valid columns of this thread's half ----
+    float mx = -INFINITY;
+    for (int c0 = wlo; c0 < whi; c0 += 32) {
+      uint32_t raw[32];
+      ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
+      ptx::tmem_ld_wait();
+      if (lo <= c0 && c0 + 32 <= hi) {                      // chunk entirely inside this row's window
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c0 + j;
+          if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(raw[j]));
+        }
+      }
+    }
+    pmax[half][t] = mx;
+    __syncthreads();
+    mx = fmaxf(pmax[0][t], pmax[1][t]);
+    const float mxs = mx * sc;
+
+    // ---- pass 2: p = 2^((s - max) * scale*log2e), bf16 P into the SWIZZLE_128B operand tile, row sum ----
+    float sum = 0.f;
+    for (int c0 = half * 64; c0 < min(half * 64 + 64, rows16); c0 += 32) {
+      uint32_t pk[16];
+      if (c0 >= wlo && c0 < whi) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tmem_s + lane_sel + (uint32_t)c0, raw);
+        ptx::tmem_ld_wait();
+        if (lo <= c0 && c0 + 32 <= hi) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(ex2_fast(fmaf(__uint_as_float(raw[j]), sc, -mxs)),
+                                                            ex2_fast(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs)));
+            const float2 f2 = __bfloat1622float2(b2);        // the row sum uses the bf16-rounded probabilities PV will see
+            sum += f2.x + f2.y;
+            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int col = c0 + j;
+            float p0 = ex2_fast(fmaf(__uint_as_float(raw[j]), sc, -mxs));
+            float p1 = ex2_fast(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs));
+            p0 = (col >= lo && col < hi) ? p0 : 0.f;
+            p1 = (col + 1 >= lo && col + 1 < hi) ? p1 : 0.f;
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+            const float2 f2 = __bfloat1622float2(b2);
+            sum += f2.x + f2.y;
+            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+      }
+      // 32 keys = 4 chunks of 16 bytes, SWIZZLE_128B K-major: chunk index XOR (row % 8)
+      const int kb = c0 >> 6;
+      const int cbase = (c0 & 63) >> 3;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int chunk = (cbase + cc) ^ r8;
+        *reinterpret_cast<uint4*>(prow + kb * 16384 + chunk * 16) = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+      }
+    }
+    psum[half][t] = sum;
+    // V rows past the tile may be uninitialised memory (0 * NaN = NaN): zero the ones the PV product reads
+    if (half == 1 && t >= rows && t < rows16) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(sV + t * 64 + cc * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    ptx::fence_proxy_async();                               // generic-proxy smem writes -> visible to tcgen05
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const uint32_t id_o = idesc_bf16(128, 32, 1);
+      const uint32_t pa = ptx::smem_u32(sP), va = ptx::smem_u32(sV);
+      for (int ks = 0; ks < rows16 / 16; ++ks) {
+        const uint64_t dp = ptx::umma_desc_sw128_kmajor(pa + (ks >> 2) * 16384) + (uint64_t)((ks & 3) * 2);
+        const uint64_t dv = desc_sw64_mnmajor(va + ks * 1024);
+        ptx::umma_f16_ss(tmem_o, dp, dv, id_o, ks ? 1u : 0u);
+      }
+      ptx::umma_commit(&sm->bar_o);
+    }
+    ptx::mbar_wait(&sm->bar_o, ph);
+    ptx::tc_fence_after();
+    {
+      uint32_t raw[16];                                       // this thread's 16 of the 32 output dims
+      tmem_ld_32x16(tmem_o + lane_sel + (uint32_t)(half * 16), raw);
+      ptx::tmem_ld_wait();
+      if (t < rows) {
+        const float il = 1.0f / (psum[0][t] + psum[1][t]);
+        __nv_bfloat16* dst = att + (size_t)(row0 + t) * C + h * 32 + half * 16;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint4 o;
+          __nv_bfloat162 b2;
+          b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 0]) * il, __uint_as_float(raw[cc * 8 + 1]) * il); o.x = *reinterpret_cast<uint32_t*>(&b2);
+          b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 2]) * il, __uint_as_float(raw[cc * 8 + 3]) * il); o.y = *reinterpret_cast<uint32_t*>(&b2);
+          b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 4]) * il, __uint_as_float(raw[cc * 8 + 5]) * il); o.z = *reinterpret_cast<uint32_t*>(&b2);
+          b2 = __floats2bfloat162_rn(__uint_as_float(raw[cc * 8 + 6]) * il, __uint_as_float(raw[cc * 8 + 7]) * il); o.w = *reinterpret_cast<uint32_t*>(&b2);
+          *reinterpret_cast<uint4*>(dst + cc * 8) = o;
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();          // everyone is done with S, O, pmax/psum and the smem tiles before the next head reuses them
+    ptx::tc_fence_after();
   }
+  if (warp == 0) ptx::tmem_dealloc(tmem_s, AT_TMEM_COLS);
 }
 
 // ---- CUDA-core variant (debug / A-B knob SAST_B200_ATTN=simt): one thread per query row ----
@@ -374,24 +338,16 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   int rc = make_tmap_bf16_box(&mq, qkv, max_rows, 3 * C, 3 * C, 32, 128, 64);
   if (rc) return rc;
   static bool attr_done = false;
-  const size_t smem = 1024 + 10 * AT_TILE + sizeof(AttnSmem2);
+  const size_t smem = 1024 + 5 * AT_TILE + sizeof(AttnSmem);
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // two persistent CTAs per SM (83 KB smem, 128 TMEM columns each); with few windows split the heads across CTAs
-  int hsplit = 1;
-  while (hsplit < heads && (long long)NW * hsplit < 2 * sms && heads % (hsplit * 2) == 0) hsplit *= 2;
-  long long want = (long long)NW * hsplit;
-  int grid = (int)(want < 2 * sms ? want : 2 * sms);
-  grid = grid / hsplit * hsplit;
-  if (grid < hsplit) grid = hsplit;
-  sast::launch_k(attention_tc_kernel, dim3(grid), dim3(288), smem, st, mq, att, C, heads, hsplit, NW, sel.tiles, sel.win_row0,
-                 sel.row_tok, T);
+  // enough CTAs to fill the chip: all heads in one CTA when there are many tiles, one head per CTA otherwise
+  int hpc = heads;
+  while (hpc > 1 && (long long)NW * (heads / hpc) < 4 * 148 && hpc % 2 == 0) hpc /= 2;
+  sast::launch_k(attention_tc_kernel, dim3(NW, heads / hpc), 256, smem, st, mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }
