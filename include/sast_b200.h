@@ -94,7 +94,7 @@ int sast_selection_bind(void* pool, int32_t B, int32_t NW, int32_t P, sast_selec
  * count of non-zero cells after max-pooling by 4,8,16,32 (int16 wrap), times fp32(B/numel).
  */
 int sast_nonzero_ratio(const void* x, int32_t dtype, int32_t B, int32_t Cin, int32_t H, int32_t W,
-                       float* r, void* stream);
+                       float* r, int32_t* scratch /* [B*Cin*4] ints, zero on entry, left zero on exit */, void* stream);
 
 /*
  * a4  scoring module + STP weighting.  ref: SAST.py:105-119, 305-328.

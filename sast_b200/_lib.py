@@ -75,7 +75,7 @@ def _load():
         "sast_launch_count": (C.c_uint64, []),
         "sast_selection_bytes": (sz, [i32, i32, i32]),
         "sast_selection_bind": (C.c_int, [vp, i32, i32, i32, C.POINTER(Selection)]),
-        "sast_nonzero_ratio": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
+        "sast_nonzero_ratio": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
         "sast_score_fwd": (C.c_int, [C.POINTER(ScoreArgs), vp]),
         "sast_select": (C.c_int, [C.POINTER(SelectArgs), vp]),
         "sast_select2": (C.c_int, [C.POINTER(SelectArgs), i32, C.POINTER(Selection), vp]),

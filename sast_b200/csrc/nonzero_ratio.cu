@@ -1,6 +1,6 @@
 // a1: scene sparsity ratio r  (replaces sast_rnn.py:45-60 non_zero_ratio).
 //
-// One CTA per (frame, bin) plane.  The plane is walked in bands of 32 pixel rows (= 8 rows
+// The planes are cut in bands of 32 pixel rows (= 8 rows
 // of 4x4 level-0 cells = one row of level-3 cells): every thread max-reduces 4x4 cells with
 // 128-bit / 32-bit row loads (coalesced: neighbouring threads own neighbouring cells), the
 // level-0 maxima go to shared memory and levels 1..3 (8x8, 16x16, 32x32 pixels) are
@@ -44,49 +44,44 @@ template <> struct Load4<float> {
   }
 };
 
+// One CTA per (plane, band of 32 pixel rows): 1920 CTAs at 1 Mpx B=8 instead of 160 plane-sized ones.  Integer
+// counts are accumulated with atomicAdd (order independent, hence still bit-exact) into a zeroed scratch array;
+// a second tiny kernel turns them into ratios.
 template <typename T>
-__global__ void __launch_bounds__(512) nonzero_ratio_kernel(const T* __restrict__ x, int Cin, int H, int W,
-                                                            float f0, float f1, float f2, float f3,
-                                                            float* __restrict__ r) {
+__global__ void __launch_bounds__(256) nonzero_count_kernel(const T* __restrict__ x, int H, int W, int* __restrict__ counts) {
   pdl_entry();
-  extern __shared__ float cell0[];        // [8][w0] level-0 maxima of the current band
-  __shared__ int red[4][16];
-  const int plane = blockIdx.x;           // b*Cin + c
-  const int b = plane / Cin, c = plane - b * Cin;
+  extern __shared__ float cell0[];        // [8][w0] level-0 maxima of this band
+  __shared__ int red[4][8];
+  const int plane = blockIdx.x, band = blockIdx.y;
   const T* xp = x + (size_t)plane * H * W;
   const int h0 = H / 4, w0 = W / 4;
   const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   int cnt[4] = {0, 0, 0, 0};
-
-  for (int band = 0; band * 8 < h0; ++band) {
-    const int rows0 = min(8, h0 - band * 8);          // level-0 cell rows in this band
-    for (int i = threadIdx.x; i < rows0 * w0; i += blockDim.x) {
-      const int cy = i / w0, cx = i - cy * w0;
-      const T* p = xp + (size_t)((band * 8 + cy) * 4) * W + cx * 4;
+  const int rows0 = min(8, h0 - band * 8);          // level-0 cell rows in this band
+  for (int i = threadIdx.x; i < rows0 * w0; i += blockDim.x) {
+    const int cy = i / w0, cx = i - cy * w0;
+    const T* p = xp + (size_t)((band * 8 + cy) * 4) * W + cx * 4;
+    float v[4][4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) Load4<T>::ld(p + (size_t)rr * W, vec, v[rr]);     // 4 independent row loads in flight
+    float m = -INFINITY;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) m = fmaxf(m, fmaxf(fmaxf(v[rr][0], v[rr][1]), fmaxf(v[rr][2], v[rr][3])));
+    cell0[cy * w0 + cx] = m;
+    cnt[0] += (m != 0.0f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int lvl = 1; lvl < 4; ++lvl) {
+    const int s = 1 << lvl;                           // level-0 cells per side
+    const int rows = rows0 / s, cols = w0 / s;        // complete cells only (floor)
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+      const int cy = i / cols, cx = i - cy * cols;
       float m = -INFINITY;
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        float v[4];
-        Load4<T>::ld(p + (size_t)rr * W, vec, v);
-        m = fmaxf(m, fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])));
-      }
-      cell0[cy * w0 + cx] = m;
-      cnt[0] += (m != 0.0f);
+      for (int yy = 0; yy < s; ++yy)
+        for (int xx = 0; xx < s; ++xx) m = fmaxf(m, cell0[(cy * s + yy) * w0 + cx * s + xx]);
+      cnt[lvl] += (m != 0.0f);
     }
-    __syncthreads();
-#pragma unroll
-    for (int lvl = 1; lvl < 4; ++lvl) {
-      const int s = 1 << lvl;                           // level-0 cells per side
-      const int rows = rows0 / s, cols = w0 / s;        // complete cells only (floor)
-      for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
-        const int cy = i / cols, cx = i - cy * cols;
-        float m = -INFINITY;
-        for (int yy = 0; yy < s; ++yy)
-          for (int xx = 0; xx < s; ++xx) m = fmaxf(m, cell0[(cy * s + yy) * w0 + cx * s + xx]);
-        cnt[lvl] += (m != 0.0f);
-      }
-    }
-    __syncthreads();
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -98,16 +93,27 @@ __global__ void __launch_bounds__(512) nonzero_ratio_kernel(const T* __restrict_
   if (threadIdx.x < 4) {
     int tot = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[threadIdx.x][w];
-    const float f = threadIdx.x == 0 ? f0 : threadIdx.x == 1 ? f1 : threadIdx.x == 2 ? f2 : f3;
-    r[((size_t)b * 4 + threadIdx.x) * Cin + c] = f * (float)(int16_t)tot;   // int16 wrap as in the reference
+    if (tot) atomicAdd(&counts[plane * 4 + threadIdx.x], tot);
   }
+}
+
+__global__ void nonzero_finalize_kernel(int* __restrict__ counts, int planes, int Cin, float f0, float f1, float f2, float f3,
+                                        float* __restrict__ r) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= planes * 4) return;
+  const int plane = i >> 2, lvl = i & 3;
+  const int b = plane / Cin, c = plane - b * Cin;
+  const float f = lvl == 0 ? f0 : lvl == 1 ? f1 : lvl == 2 ? f2 : f3;
+  r[((size_t)b * 4 + lvl) * Cin + c] = f * (float)(int16_t)counts[i];       // int16 wrap as in the reference
+  counts[i] = 0;                                                             // leave the scratch zeroed for the next call
 }
 
 }  // namespace sast
 
 extern "C" int sast_nonzero_ratio(const void* x, int32_t dtype, int32_t B, int32_t Cin, int32_t H, int32_t W,
-                                  float* r, void* stream) {
-  SAST_CHECK_PTR(x); SAST_CHECK_PTR(r);
+                                  float* r, int32_t* scratch, void* stream) {
+  SAST_CHECK_PTR(x); SAST_CHECK_PTR(r); SAST_CHECK_PTR(scratch);
   if (B <= 0 || Cin <= 0 || H < 32 || W < 32) return SAST_E_SHAPE;
   float f[4];
   for (int l = 0; l < 4; ++l) {
@@ -118,20 +124,17 @@ extern "C" int sast_nonzero_ratio(const void* x, int32_t dtype, int32_t B, int32
   const size_t smem = (size_t)8 * (W / 4) * sizeof(float);
   if (smem > 48 * 1024) return SAST_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  const dim3 grid(B * Cin), block(512);
+  const int planes = B * Cin;
+  const dim3 grid(planes, (H / 4 + 7) / 8), block(256);
   switch (dtype) {
-    case SAST_U8:
-      sast::launch_k(sast::nonzero_ratio_kernel<uint8_t>, grid, block, smem, st, (const uint8_t*)x, Cin, H, W, f[0], f[1], f[2], f[3], r);
-      break;
-    case SAST_I32:
-      sast::launch_k(sast::nonzero_ratio_kernel<int32_t>, grid, block, smem, st, (const int32_t*)x, Cin, H, W, f[0], f[1], f[2], f[3], r);
-      break;
-    case SAST_F32:
-      sast::launch_k(sast::nonzero_ratio_kernel<float>, grid, block, smem, st, (const float*)x, Cin, H, W, f[0], f[1], f[2], f[3], r);
-      break;
-    default:
-      return SAST_E_UNSUPPORTED;
+    case SAST_U8: sast::launch_k(sast::nonzero_count_kernel<uint8_t>, grid, block, smem, st, (const uint8_t*)x, H, W, scratch); break;
+    case SAST_I32: sast::launch_k(sast::nonzero_count_kernel<int32_t>, grid, block, smem, st, (const int32_t*)x, H, W, scratch); break;
+    case SAST_F32: sast::launch_k(sast::nonzero_count_kernel<float>, grid, block, smem, st, (const float*)x, H, W, scratch); break;
+    default: return SAST_E_UNSUPPORTED;
   }
+  SAST_LAUNCH_CHECK();
+  sast::launch_k(sast::nonzero_finalize_kernel, dim3((planes * 4 + 127) / 128), dim3(128), 0, st, scratch, planes, Cin, f[0], f[1], f[2],
+                 f[3], r);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

@@ -52,8 +52,9 @@ def nonzero_ratio(x: Tensor) -> Tensor:
     x = x.contiguous()
     B, Cin, H, W = x.shape
     r = torch.empty(B, 4, Cin, device=x.device, dtype=torch.float32)
-    L.check(L.lib().sast_nonzero_ratio(x.data_ptr(), dt, B, Cin, H, W, r.data_ptr(), L.stream_ptr(x.device)),
-            "sast_nonzero_ratio")
+    scratch = torch.zeros(B * Cin * 4, device=x.device, dtype=torch.int32)
+    L.check(L.lib().sast_nonzero_ratio(x.data_ptr(), dt, B, Cin, H, W, r.data_ptr(), scratch.data_ptr(),
+                                       L.stream_ptr(x.device)), "sast_nonzero_ratio")
     return r
 
 

@@ -54,9 +54,9 @@ def test_selection_pool_layout():
 
 def test_argument_validation_without_gpu():
     lib = L.lib()
-    assert lib.sast_nonzero_ratio(0, L.U8, 1, 20, 64, 64, 0, 0) == -1
-    assert lib.sast_nonzero_ratio(16, 99, 1, 20, 64, 64, 16, 0) == -3
-    assert lib.sast_nonzero_ratio(16, L.U8, 1, 20, 8, 64, 16, 0) == -2
+    assert lib.sast_nonzero_ratio(0, L.U8, 1, 20, 64, 64, 0, 0, 0) == -1
+    assert lib.sast_nonzero_ratio(16, 99, 1, 20, 64, 64, 16, 16, 0) == -3
+    assert lib.sast_nonzero_ratio(16, L.U8, 1, 20, 8, 64, 16, 16, 0) == -2
     assert lib.sast_layer_workspace_bytes(1000, 64, 160, 2, L.BF16) > lib.sast_layer_workspace_bytes(1000, 64, 160, 2, L.FP32) // 2
     a = L.LayerArgs()
     assert lib.sast_layer_fwd(ctypes.byref(a), 0) == -1
