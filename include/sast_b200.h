@@ -90,7 +90,8 @@ int sast_selection_bind(void* pool, int32_t B, int32_t NW, int32_t P, sast_selec
 
 /*
  * a1  scene sparsity ratio r.  ref: sast_rnn.py:45-60 non_zero_ratio.
- * x [B,Cin,H,W] of `dtype` (SAST_U8 / SAST_I32 / SAST_F32) -> r [B,4,Cin] fp32, bit-exact:
+ * x [B,Cin,H,W] of `dtype` (SAST_U8 / SAST_I32 / SAST_F32) -> r [4,B,Cin] fp32 (level-major, so that the
+ * per-stage slice r[level] the scoring kernel takes is contiguous), bit-exact:
  * count of non-zero cells after max-pooling by 4,8,16,32 (int16 wrap), times fp32(B/numel).
  */
 int sast_nonzero_ratio(const void* x, int32_t dtype, int32_t B, int32_t Cin, int32_t H, int32_t W,

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
             __nv_bfloat162 o[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it)
-              o[it] = __floats2bfloat162_rn((a4[it].x + b4.x) * gelu_erf_fast(a4[it].y + b4.y), (a4[it].z + b4.z) * gelu_erf_fast(a4[it].w + b4.w));
+              o[it] = __floats2bfloat162_rn((a4[it].x + b4.x) * gelu_tanh_fit(a4[it].y + b4.y), (a4[it].z + b4.z) * gelu_tanh_fit(a4[it].w + b4.w));
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = m0 + quarter * 32 + it * 4 + r_sub;
@@ -213,11 +213,11 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
             float hn[8], cn[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              const float f = __fdividef(1.0f, 1.0f + __expf(-(a4[it].x + b4.x))), ig = __fdividef(1.0f, 1.0f + __expf(-(a4[it].y + b4.y)));
-              const float og = __fdividef(1.0f, 1.0f + __expf(-(a4[it].z + b4.z)));
-              const float g = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * (a4[it].w + b4.w)));     // tanh
+              // one MUFU.TANH per gate (10 MUFU per channel with exp + divide made this epilogue MUFU bound)
+              const float f = sigmoid_fast(a4[it].x + b4.x), ig = sigmoid_fast(a4[it].y + b4.y), og = sigmoid_fast(a4[it].z + b4.z);
+              const float g = tanh_fast(a4[it].w + b4.w);
               cn[it] = f * cprev[it] + ig * g;
-              hn[it] = og * (1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * cn[it])));
+              hn[it] = og * tanh_fast(cn[it]);
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {

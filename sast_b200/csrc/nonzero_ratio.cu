@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) nonzero_count_kernel(const T* __restrict_
   }
 }
 
-__global__ void nonzero_finalize_kernel(int* __restrict__ counts, int planes, int Cin, float f0, float f1, float f2, float f3,
+__global__ void nonzero_finalize_kernel(int* __restrict__ counts, int planes, int B, int Cin, float f0, float f1, float f2, float f3,
                                         float* __restrict__ r) {
   pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,7 +105,7 @@ __global__ void nonzero_finalize_kernel(int* __restrict__ counts, int planes, in
   const int plane = i >> 2, lvl = i & 3;
   const int b = plane / Cin, c = plane - b * Cin;
   const float f = lvl == 0 ? f0 : lvl == 1 ? f1 : lvl == 2 ? f2 : f3;
-  r[((size_t)b * 4 + lvl) * Cin + c] = f * (float)(int16_t)counts[i];       // int16 wrap as in the reference
+  r[((size_t)lvl * B + b) * Cin + c] = f * (float)(int16_t)counts[i];       // int16 wrap as in the reference
   counts[i] = 0;                                                             // leave the scratch zeroed for the next call
 }
 
@@ -133,7 +133,7 @@ extern "C" int sast_nonzero_ratio(const void* x, int32_t dtype, int32_t B, int32
     default: return SAST_E_UNSUPPORTED;
   }
   SAST_LAUNCH_CHECK();
-  sast::launch_k(sast::nonzero_finalize_kernel, dim3((planes * 4 + 127) / 128), dim3(128), 0, st, scratch, planes, Cin, f[0], f[1], f[2],
+  sast::launch_k(sast::nonzero_finalize_kernel, dim3((planes * 4 + 127) / 128), dim3(128), 0, st, scratch, planes, B, Cin, f[0], f[1], f[2],
                  f[3], r);
   SAST_LAUNCH_CHECK();
   return SAST_OK;

@@ -51,16 +51,16 @@ def nonzero_ratio(x: Tensor) -> Tensor:
         dt = L.F32 if x.is_floating_point() else L.I32
     x = x.contiguous()
     B, Cin, H, W = x.shape
-    r = torch.empty(B, 4, Cin, device=x.device, dtype=torch.float32)
+    r = torch.empty(4, B, Cin, device=x.device, dtype=torch.float32)          # level-major: r[:, i] below is contiguous
     scratch = torch.zeros(B * Cin * 4, device=x.device, dtype=torch.int32)
     L.check(L.lib().sast_nonzero_ratio(x.data_ptr(), dt, B, Cin, H, W, r.data_ptr(), scratch.data_ptr(),
                                        L.stream_ptr(x.device)), "sast_nonzero_ratio")
-    return r
+    return r.permute(1, 0, 2)                                                   # the reference's [B, 4, Cin]
 
 
 @nonzero_ratio.register_fake
 def _(x):
-    return x.new_empty(x.shape[0], 4, x.shape[1], dtype=torch.float32)
+    return x.new_empty(4, x.shape[0], x.shape[1], dtype=torch.float32).permute(1, 0, 2)
 
 
 # --------------------------------------------------------------------------------------------

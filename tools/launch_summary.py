@@ -11,7 +11,7 @@ detail = len(sys.argv) > 3
 with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
-idx = [i for i, r in enumerate(rows) if "nonzero_ratio" in r["Kernel Name"]]
+idx = [i for i, r in enumerate(rows) if "nonzero_count" in r["Kernel Name"] or "nonzero_ratio" in r["Kernel Name"]]
 s, e = idx[which], idx[which + 1]
 agg, tot = collections.OrderedDict(), 0.0
 for r in rows[s:e]:
