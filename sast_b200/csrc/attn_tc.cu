@@ -8,7 +8,7 @@
 // padding (SAST.py:223-226) has no counterpart: the only mask is "same window".
 //
 // CTA = 256 threads, two threads per tile row (= TMEM lane), each on half of the key columns.  Thread 0 issues TMA and MMA.
-// 128 TMEM columns and 41 KB of shared memory per CTA -> 4 CTAs per SM hide each other's
+// 128 TMEM columns and 42 KB of shared memory per CTA -> 4 CTAs per SM hide each other's
 // load -> MMA -> softmax -> MMA latency chain.
 //   Q,K,V tiles [128 x 32] bf16: TMA boxes out of the qkv buffer ([rows, 3C], head-major
 //   [h][q,k,v][32]) in SWIZZLE_64B; Q,K are K-major operands, V is the MN-major B operand of PV.
@@ -70,15 +70,19 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                            __nv_bfloat16* __restrict__ att, int C, int heads_per_cta,
                                                            const int* __restrict__ tiles, const int* __restrict__ win_row0,
-                                                           const int* __restrict__ row_tok, int T) {
+                                                           const int* __restrict__ row_tok, int T,
+                                                           long long* __restrict__ trace) {
+  // trace (debug, normally null): per CTA 16 clock64 stamps of thread 0 at the phase boundaries of its first head
+#define AT_STAMP(i) do { if (trace && threadIdx.x == 0 && hi_ == 0) trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
+  const long long t_entry = trace ? clock64() : 0;
   pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ float pmax[2][128], psum[2][128];
+  __shared__ float pmax[2][128];
   const int w = blockIdx.x;
   const int rows = tiles[2 * w];
   if (rows == 0) return;                                   // not a tile leader
   const int row0 = win_row0[w];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(kFull, tid >> 5, 0), lane = tid & 31;   // warp: provably uniform
   const int half = warp >> 2;                              // which 64 key columns
   const int t = (warp & 3) * 32 + lane;                    // tile row = TMEM lane
 
@@ -87,7 +91,8 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   uint8_t* sK = base + AT_TILE;                            // P (32 KB) is written over them
   uint8_t* sP = base;
   uint8_t* sV = base + 4 * AT_TILE;
-  AttnSmem* sm = reinterpret_cast<AttnSmem*>(base + 5 * AT_TILE);
+  uint8_t* sOnes = base + 5 * AT_TILE;                     // 1 KB of bf16 1.0: the (layout-agnostic) B operand of the row-sum MMA
+  AttnSmem* sm = reinterpret_cast<AttnSmem*>(base + 5 * AT_TILE + 1024);
 
   if (tid == 0) {
     ptx::tma_prefetch_desc(&map_qkv);
@@ -97,6 +102,8 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
     ptx::fence_barrier_init();
   }
   if (warp == 0) ptx::tmem_alloc(&sm->tmem_base, AT_TMEM_COLS);
+  reinterpret_cast<uint32_t*>(sOnes)[tid] = 0x3F803F80u;   // 256 threads x 4 bytes
+  ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -123,20 +130,36 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   for (int hi_ = 0; hi_ < heads_per_cta; ++hi_) {
     const int h = h_begin + hi_;
     const uint32_t ph = (uint32_t)(hi_ & 1);
-    if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(&sm->bar_load, 3 * AT_TILE);
-      ptx::tma_load_2d(sQ, &map_qkv, &sm->bar_load, h * 96, row0);
-      ptx::tma_load_2d(sK, &map_qkv, &sm->bar_load, h * 96 + 32, row0);
-      ptx::tma_load_2d(sV, &map_qkv, &sm->bar_load, h * 96 + 64, row0);
+    if (trace && tid == 0 && hi_ == 0) {
+      trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 0] = t_entry;
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = smid;
+    }
+    AT_STAMP(1);
+    if (warp == 0) {                                          // whole warp, uniform operands; one elected lane issues
+      const bool leader = ptx::elect_one();
+      if (leader) {
+        ptx::mbar_arrive_expect_tx(&sm->bar_load, 3 * AT_TILE);
+        ptx::tma_load_2d(sQ, &map_qkv, &sm->bar_load, h * 96, row0);
+        ptx::tma_load_2d(sK, &map_qkv, &sm->bar_load, h * 96 + 32, row0);
+        ptx::tma_load_2d(sV, &map_qkv, &sm->bar_load, h * 96 + 64, row0);
+      }
       ptx::mbar_wait(&sm->bar_load, ph);
+      AT_STAMP(2);
       ptx::tc_fence_after();
       const uint32_t id_s = idesc_bf16(128, 128, 0);
       const uint64_t dq = desc_sw64_kmajor(ptx::smem_u32(sQ)), dk = desc_sw64_kmajor(ptx::smem_u32(sK));
-      ptx::umma_f16_ss(tmem_s, dq, dk, id_s, 0u);
-      ptx::umma_f16_ss(tmem_s, dq + 2, dk + 2, id_s, 1u);          // +32 bytes: dims 16..31
-      ptx::umma_commit(&sm->bar_s);
+      if (leader) {
+        ptx::umma_f16_ss(tmem_s, dq, dk, id_s, 0u);
+        ptx::umma_f16_ss(tmem_s, dq + 2, dk + 2, id_s, 1u);          // +32 bytes: dims 16..31
+        ptx::umma_commit(&sm->bar_s);
+      }
+      ptx::mbar_wait(&sm->bar_s, ph);
     }
-    ptx::mbar_wait(&sm->bar_s, ph);
+    // only warp 0 polls the mbarriers; everybody else blocks in bar.sync
+    __syncthreads();
+    AT_STAMP(3);
     ptx::tc_fence_after();
 
     // ---- softmax over this row's window: pass 1 = max over the valid columns of this thread's half ----
@@ -157,12 +180,15 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
       }
     }
     pmax[half][t] = mx;
+    AT_STAMP(4);
     __syncthreads();
+    AT_STAMP(5);
     mx = fmaxf(pmax[0][t], pmax[1][t]);
     const float mxs = mx * sc;
 
-    // ---- pass 2: p = 2^((s - max) * scale*log2e), bf16 P into the SWIZZLE_128B operand tile, row sum ----
-    float sum = 0.f;
+    // ---- pass 2: p = 2^((s - max) * scale*log2e), bf16 P into the SWIZZLE_128B operand tile.  The row sums are
+    // not accumulated here (unpack + add per element on an issue-bound loop): the tensor core produces them as
+    // P x ones next to P x V, from the same bf16-rounded probabilities ----
     for (int c0 = half * 64; c0 < min(half * 64 + 64, rows16); c0 += 32) {
       uint32_t pk[16];
       if (c0 >= wlo && c0 < whi) {
@@ -174,8 +200,6 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
           for (int j = 0; j < 32; j += 2) {
             const __nv_bfloat162 b2 = __floats2bfloat162_rn(ex2_fast(fmaf(__uint_as_float(raw[j]), sc, -mxs)),
                                                             ex2_fast(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs)));
-            const float2 f2 = __bfloat1622float2(b2);        // the row sum uses the bf16-rounded probabilities PV will see
-            sum += f2.x + f2.y;
             pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
           }
         } else {
@@ -187,8 +211,6 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
             p0 = (col >= lo && col < hi) ? p0 : 0.f;
             p1 = (col + 1 >= lo && col + 1 < hi) ? p1 : 0.f;
             const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-            const float2 f2 = __bfloat1622float2(b2);
-            sum += f2.x + f2.y;
             pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
           }
         }
@@ -205,34 +227,50 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
         *reinterpret_cast<uint4*>(prow + kb * 16384 + chunk * 16) = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
       }
     }
-    psum[half][t] = sum;
     // V rows past the tile may be uninitialised memory (0 * NaN = NaN): zero the ones the PV product reads
     if (half == 1 && t >= rows && t < rows16) {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(sV + t * 64 + cc * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
+    AT_STAMP(6);
     ptx::fence_proxy_async();                               // generic-proxy smem writes -> visible to tcgen05
     ptx::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    AT_STAMP(7);
+    if (warp == 0) {
+      AT_STAMP(14);
       ptx::tc_fence_after();
-      const uint32_t id_o = idesc_bf16(128, 32, 1);
+      AT_STAMP(13);
+      const bool leader = ptx::elect_one();
+      const uint32_t id_o = idesc_bf16(128, 32, 1), id_sum = idesc_bf16(128, 16, 0);
       const uint32_t pa = ptx::smem_u32(sP), va = ptx::smem_u32(sV);
-      for (int ks = 0; ks < rows16 / 16; ++ks) {
-        const uint64_t dp = ptx::umma_desc_sw128_kmajor(pa + (ks >> 2) * 16384) + (uint64_t)((ks & 3) * 2);
-        const uint64_t dv = desc_sw64_mnmajor(va + ks * 1024);
-        ptx::umma_f16_ss(tmem_o, dp, dv, id_o, ks ? 1u : 0u);
+      const uint64_t d1 = desc_sw64_kmajor(ptx::smem_u32(sOnes));
+      const uint64_t dp0 = ptx::umma_desc_sw128_kmajor(pa), dv0 = desc_sw64_mnmajor(va);
+      const int nks = rows16 >> 4;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {                      // unrolled: the descriptor offsets are immediates
+        if (ks < nks && leader) {
+          // P: k-step = +32 bytes inside the 128-byte swizzle atom, next 64 keys = +16 KB; V: next 16 keys = +1 KB  (>>4 fields)
+          const uint64_t dp = dp0 + (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);
+          ptx::umma_f16_ss(tmem_o, dp, dv0 + (uint64_t)(ks * 64), id_o, ks ? 1u : 0u);
+          ptx::umma_f16_ss(tmem_o + 32, dp, d1, id_sum, ks ? 1u : 0u);      // columns 32..47: row sums of P
+        }
       }
-      ptx::umma_commit(&sm->bar_o);
+      AT_STAMP(11);
+      if (leader) ptx::umma_commit(&sm->bar_o);
+      AT_STAMP(12);
+      ptx::mbar_wait(&sm->bar_o, ph);
     }
-    ptx::mbar_wait(&sm->bar_o, ph);
+    __syncthreads();
+    AT_STAMP(8);
     ptx::tc_fence_after();
     {
-      uint32_t raw[16];                                       // this thread's 16 of the 32 output dims
+      uint32_t raw[16], rs;                                   // this thread's 16 of the 32 output dims, and the row sum
       tmem_ld_32x16(tmem_o + lane_sel + (uint32_t)(half * 16), raw);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(rs) : "r"(tmem_o + lane_sel + 32u) : "memory");
       ptx::tmem_ld_wait();
       if (t < rows) {
-        const float il = 1.0f / (psum[0][t] + psum[1][t]);
+        const float il = __fdividef(1.0f, __uint_as_float(rs));
         __nv_bfloat16* dst = att + (size_t)(row0 + t) * C + h * 32 + half * 16;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
@@ -246,10 +284,13 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
         }
       }
     }
+    AT_STAMP(9);
     ptx::tc_fence_before();
     __syncthreads();          // everyone is done with S, O, pmax/psum and the smem tiles before the next head reuses them
+    AT_STAMP(10);
     ptx::tc_fence_after();
   }
+#undef AT_STAMP
   if (warp == 0) ptx::tmem_dealloc(tmem_s, AT_TMEM_COLS);
 }
 
@@ -325,6 +366,8 @@ __global__ void __launch_bounds__(128) attention_bf16_kernel(const __nv_bfloat16
 int make_tmap_bf16_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows,
                        int swizzle_bytes);
 
+static long long* g_attn_trace = nullptr;      // debug: set through sast_debug_attn_trace, one launch's CTAs x 16 stamps
+
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, const sast_selection& sel, int NW, int T,
                         long long max_rows, int variant, cudaStream_t st) {
   const int heads = C / 32;
@@ -338,7 +381,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   int rc = make_tmap_bf16_box(&mq, qkv, max_rows, 3 * C, 3 * C, 32, 128, 64);
   if (rc) return rc;
   static bool attr_done = false;
-  const size_t smem = 1024 + 5 * AT_TILE + sizeof(AttnSmem);
+  const size_t smem = 1024 + 5 * AT_TILE + 1024 + sizeof(AttnSmem);
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -347,9 +390,13 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   // enough CTAs to fill the chip: all heads in one CTA when there are many tiles, one head per CTA otherwise
   int hpc = heads;
   while (hpc > 1 && (long long)NW * (heads / hpc) < 4 * 148 && hpc % 2 == 0) hpc /= 2;
-  sast::launch_k(attention_tc_kernel, dim3(NW, heads / hpc), 256, smem, st, mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T);
+  sast::launch_k(attention_tc_kernel, dim3(NW, heads / hpc), 256, smem, st, mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T, g_attn_trace);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }
 
 }  // namespace sast
+
+// Debug aid (tools/attn_trace.py): the next attention launches write thread 0's clock64 stamps at the phase
+// boundaries of each CTA's first head into buf ([grid.y * grid.x][16] int64; slot 15 = SM id).  Null switches it off.
+extern "C" void sast_debug_attn_trace(long long* buf) { sast::g_attn_trace = buf; }

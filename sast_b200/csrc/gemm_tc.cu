@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
   const uint32_t stage_bytes = a_bytes + w_bytes;
   TcSmem* sm = reinterpret_cast<TcSmem*>(base + (size_t)stages * stage_bytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // warp: provably uniform
   // operand element: bf16 (64 per 128-byte k-block row) or, for EPI_LSTM, fp32 read as TF32 (32 per row)
   constexpr bool kTf32 = (EPI == EPI_LSTM);
   constexpr int kBK = kTf32 ? 32 : TC_BK;
@@ -88,17 +88,21 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
   ptx::tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
 
+  // The producer and MMA warps run their loops as WHOLE warps on warp-uniform values and guard only the TMA /
+  // tcgen05 instructions with an elected lane: under `if (lane == 0)` the descriptors sit in per-thread registers
+  // and every UTCHMMA pays an ELECT / R2UR waterfall loop (~120 clk per instruction, measured in attn_tc).
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)stages, round = it / (uint32_t)stages;
-          ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
-          uint8_t* sa = base + (size_t)s * stage_bytes;
+    const bool leader = ptx::elect_one();
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % (uint32_t)stages, round = it / (uint32_t)stages;
+        ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
+        uint8_t* sa = base + (size_t)s * stage_bytes;
+        const int k0 = kb * kBK;
+        if (leader) {
           ptx::mbar_arrive_expect_tx(&sm->full[s], stage_bytes);
-          const int k0 = kb * kBK;
           if (k0 < k_split) ptx::tma_load_2d(sa, &map_a, &sm->full[s], k0, m0);
           else ptx::tma_load_2d(sa, &map_a2, &sm->full[s], k0 - k_split, m0);      // second A source ([x | h_prev])
           ptx::tma_load_2d(sa + a_bytes, &map_w, &sm->full[s], k0, n0);
@@ -106,33 +110,37 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = kTf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)BN >> 3) << 17) | ((TC_BM >> 4) << 24))
-                                   : ptx::umma_idesc_bf16(TC_BM, (uint32_t)BN);
-      uint32_t it = 0, ti = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-        const uint32_t acc = ti % NG, use = ti / NG;
-        ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);       // epilogue has drained this accumulator
+    const bool leader = ptx::elect_one();
+    const uint32_t idesc = kTf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)BN >> 3) << 17) | ((TC_BM >> 4) << 24))
+                                 : ptx::umma_idesc_bf16(TC_BM, (uint32_t)BN);
+    uint32_t it = 0, ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const uint32_t acc = ti % NG, use = ti / NG;
+      ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);       // epilogue has drained this accumulator
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % (uint32_t)stages, round = it / (uint32_t)stages;
+        ptx::mbar_wait(&sm->full[s], round & 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)stages, round = it / (uint32_t)stages;
-          ptx::mbar_wait(&sm->full[s], round & 1);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
-          const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
-          const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
-          const int krem = K - kb * kBK;
-          const int ksteps = krem >= kBK ? 4 : (krem + kKStep - 1) / kKStep;
-          for (int k = 0; k < ksteps; ++k) {
-            // advance one k-step = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
-            if (kTf32) ptx::umma_tf32_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-            else ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
+        const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
+        const uint64_t db = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
+        const int krem = K - kb * kBK;
+        const int ksteps = krem >= kBK ? 4 : (krem + kKStep - 1) / kKStep;
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < ksteps) {
+              // advance one k-step = 32 bytes along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+              if (kTf32) ptx::umma_tf32_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+              else ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&sm->empty[s]);          // frees the smem slot when these MMAs retire
         }
-        ptx::umma_commit(&sm->tmem_full[acc]);      // accumulator complete
       }
+      if (leader) ptx::umma_commit(&sm->tmem_full[acc]);      // accumulator complete
     }
   } else {
     // ---------------- epilogue: group g = (warp-2)/4 drains accumulator g; TMEM lane quarter = warp % 4 ----------------

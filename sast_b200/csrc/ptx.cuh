@@ -43,6 +43,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp.  Code that issues TMA / tcgen05.mma should be reached by the WHOLE warp with
+// warp-uniform operands and guard only the instruction with this predicate: under an `if (threadIdx.x == 0)` the
+// descriptors live in per-thread registers and every UTCHMMA pays an ELECT / R2UR waterfall loop (~120 clk each).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
   ScSmem* sm = reinterpret_cast<ScSmem*>(smem_raw + (size_t)SC_STAGES * stage_bytes);
   float* stage_all = reinterpret_cast<float*>(smem_raw + (size_t)SC_STAGES * stage_bytes + 256);
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // warp: provably uniform
   const int nkb = C / SC_BK;
 
   if (threadIdx.x == 0) {
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
         }
         ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
         uint8_t* st = base + (size_t)s * stage_bytes;
-        if (t == 0) {
+        if (warp == 0 && ptx::elect_one()) {     // warp-uniform operands, elected lane: no R2UR waterfall per TMA
           ptx::mbar_arrive_expect_tx(&sm->full[s], 2 * w_bytes);
           ptx::tma_load_2d(st + 2 * a_bytes, &map_whi, &sm->full[s], kb * SC_BK, n0);
           ptx::tma_load_2d(st + 2 * a_bytes + w_bytes, &map_wlo, &sm->full[s], kb * SC_BK, n0);
@@ -131,22 +131,23 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
       }
     }
   } else if (warp == SC_MMA_WARP) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(SC_BM, (uint32_t)BN);
-      uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t acc = ti % SC_GROUPS, use = ti / SC_GROUPS;
-        ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);
+    // ---------------- MMA issuer: whole warp on uniform values, one elected lane issues (no R2UR waterfall per UTCHMMA) ----------------
+    const bool leader = ptx::elect_one();
+    const uint32_t idesc = idesc_tf32(SC_BM, (uint32_t)BN);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t acc = ti % SC_GROUPS, use = ti / SC_GROUPS;
+      ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % SC_STAGES, round = it / SC_STAGES;
+        ptx::mbar_wait(&sm->full[s], round & 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % SC_STAGES, round = it / SC_STAGES;
-          ptx::mbar_wait(&sm->full[s], round & 1);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
-          const uint64_t dah = ptx::umma_desc_sw128_kmajor(sa), dal = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
-          const uint64_t dwh = ptx::umma_desc_sw128_kmajor(sa + 2 * a_bytes), dwl = ptx::umma_desc_sw128_kmajor(sa + 2 * a_bytes + w_bytes);
+        const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
+        const uint64_t dah = ptx::umma_desc_sw128_kmajor(sa), dal = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
+        const uint64_t dwh = ptx::umma_desc_sw128_kmajor(sa + 2 * a_bytes), dwl = ptx::umma_desc_sw128_kmajor(sa + 2 * a_bytes + w_bytes);
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {          // 8 tf32 = 32 bytes per k-step: +2 in the >>4 address field
             const uint64_t o = (uint64_t)(k * 2);
@@ -156,8 +157,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
           }
           ptx::umma_commit(&sm->empty[s]);
         }
-        ptx::umma_commit(&sm->tmem_full[acc]);
       }
+      if (leader) ptx::umma_commit(&sm->tmem_full[acc]);
     }
   } else {
     // ---------------- epilogue (warps 4..15: group = (warp-4)/4, TMEM lane quarter = warp % 4) ----------------

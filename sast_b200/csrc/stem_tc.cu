@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
   uint8_t* base = smem_raw;
   StSmem* sm = reinterpret_cast<StSmem*>(smem_raw + (size_t)ST_STAGES * stage_bytes);
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // warp: provably uniform
   const int nkb = n_groups_pad / 8;                                    // k-blocks of 8 groups x 8 taps
   const int n_groups = Cin * 7;
 
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
         if (kb + 1 < nkb) load_block(kb + 1, n0, n1, n2);
         ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
         uint8_t* st = base + (size_t)s * stage_bytes;
-        if (t == 0) {
+        if (warp == 0 && ptx::elect_one()) {     // warp-uniform operands, elected lane: no R2UR waterfall per TMA
           ptx::mbar_arrive_expect_tx(&sm->full[s], 2 * w_bytes);
           ptx::tma_load_2d(st + a_bytes, &map_whi, &sm->full[s], kb * 64, 0);
           ptx::tma_load_2d(st + a_bytes + w_bytes, &map_wlo, &sm->full[s], kb * 64, 0);
@@ -142,22 +142,23 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 8) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (((uint32_t)Cout >> 3) << 17) | ((ST_BM >> 4) << 24);   // kind::f16: A = B = F16, D = F32, K-major
-      uint32_t it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t acc = ti & 1, use = ti >> 1;
-        ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);
+    // ---------------- MMA issuer: whole warp on uniform values, one elected lane issues (no R2UR waterfall per UTCHMMA) ----------------
+    const bool leader = ptx::elect_one();
+    const uint32_t idesc = (1u << 4) | (((uint32_t)Cout >> 3) << 17) | ((ST_BM >> 4) << 24);   // kind::f16: A = B = F16, D = F32, K-major
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t acc = ti & 1, use = ti >> 1;
+      ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)Cout;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % ST_STAGES, round = it / ST_STAGES;
+        ptx::mbar_wait(&sm->full[s], round & 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (uint32_t)Cout;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % ST_STAGES, round = it / ST_STAGES;
-          ptx::mbar_wait(&sm->full[s], round & 1);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
-          const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
-          const uint64_t dh = ptx::umma_desc_sw128_kmajor(sa + a_bytes), dl = ptx::umma_desc_sw128_kmajor(sa + a_bytes + w_bytes);
+        const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
+        const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
+        const uint64_t dh = ptx::umma_desc_sw128_kmajor(sa + a_bytes), dl = ptx::umma_desc_sw128_kmajor(sa + a_bytes + w_bytes);
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t o = (uint64_t)(k * 2);
@@ -166,8 +167,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
           }
           ptx::umma_commit(&sm->empty[s]);
         }
-        ptx::umma_commit(&sm->tmem_full[acc]);
       }
+      if (leader) ptx::umma_commit(&sm->tmem_full[acc]);
     }
   } else if (warp >= 10) {
     // ---------------- epilogue: LayerNorm over channels (thread = pixel row), transposed store ----------------
