@@ -253,10 +253,11 @@ uint64_t sast_launch_count(void);
 int sast_gemm_bf16_glu(const uint16_t* A, const uint16_t* W, const float* bias, uint16_t* D, int32_t M, int32_t N,
                        int32_t K, void* stream);
 
-/* Debug aid (tools/attn_trace.py): while buf is non-null, attention launches of the tensor-core path write
- * thread 0's clock64 stamps at the phase boundaries of each CTA's first head into buf
- * ([grid.y * grid.x][16] int64, slot 15 = SM id).  Pass NULL to switch it off (the default). */
-void sast_debug_attn_trace(long long* buf);
+/* Debug aid (tools/attn_trace.py, tools/gemm_trace.py): while buf is non-null, launches of the tensor-core
+ * attention and GEMM kernels write thread-level clock64 stamps of their phase boundaries into buf
+ * (attention: [CTA][16], GEMM: [CTA][128] int64; last slot = SM id).  Pass NULL to switch it off (the default).
+ * Only the instrumented build (`make -C sast_b200/csrc trace`) stamps; the regular library ignores the call. */
+void sast_debug_trace(long long* buf, int32_t which /* 1 attention, 2 GEMM */);
 
 /* Library / build info. */
 int sast_abi_version(void);

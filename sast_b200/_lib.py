@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsast_b200.so")
+# SAST_B200_LIB selects another build of the same ABI (the instrumented `make trace` twin); there is still no fallback
+LIB_PATH = os.environ.get("SAST_B200_LIB") or os.path.join(_HERE, "libsast_b200.so")
 
 # enums (mirror include/sast_b200.h)
 WINDOW, GRID, FLAT = 0, 1, 2
@@ -73,7 +74,7 @@ def _load():
         "sast_build_info": (C.c_char_p, []),
         "sast_struct_size": (sz, [i32]),
         "sast_launch_count": (C.c_uint64, []),
-        "sast_debug_attn_trace": (None, [vp]),
+        "sast_debug_trace": (None, [vp, i32]),
         "sast_selection_bytes": (sz, [i32, i32, i32]),
         "sast_selection_bind": (C.c_int, [vp, i32, i32, i32, C.POINTER(Selection)]),
         "sast_nonzero_ratio": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
@@ -108,7 +109,7 @@ def _load():
 EXPORTS = ("sast_abi_version", "sast_build_info", "sast_struct_size", "sast_launch_count", "sast_selection_bytes", "sast_selection_bind",
            "sast_nonzero_ratio", "sast_score_fwd", "sast_select", "sast_select2", "sast_layer_workspace_bytes",
            "sast_layer_fwd", "sast_gather", "sast_scatter", "sast_gemm_bf16", "sast_gemm_bf16_glu", "sast_pad_input", "sast_pad_nhwc",
-           "sast_layernorm", "sast_lstm_gates", "sast_lstm_fwd", "sast_stem_fwd", "sast_debug_attn_trace")
+           "sast_layernorm", "sast_lstm_gates", "sast_lstm_fwd", "sast_stem_fwd", "sast_debug_trace")
 
 _lib = None
 

@@ -27,6 +27,8 @@ extern "C" size_t sast_struct_size(int32_t which) {
 }
 
 namespace sast {
+long long* g_trace = nullptr;   // debug: see sast_debug_trace
+int g_trace_which = 0;
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -36,3 +38,11 @@ bool pdl_enabled() {
   return v != 0;
 }
 }  // namespace sast
+
+// Debug aid (tools/attn_trace.py, tools/gemm_trace.py): while buf is non-null the tensor-core attention and GEMM
+// kernels (which: 1 = attention, 2 = GEMM) of the trace build write clock64 stamps of their phase boundaries into it
+// (layout: see the kernels).  Null = off (default).  The regular build ignores it.
+extern "C" void sast_debug_trace(long long* buf, int32_t which) {
+  sast::g_trace = buf;
+  sast::g_trace_which = buf ? which : 0;
+}

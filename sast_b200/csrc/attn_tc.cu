@@ -72,9 +72,11 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
                                                            const int* __restrict__ tiles, const int* __restrict__ win_row0,
                                                            const int* __restrict__ row_tok, int T,
                                                            long long* __restrict__ trace) {
-  // trace (debug, normally null): per CTA 16 clock64 stamps of thread 0 at the phase boundaries of its first head
-#define AT_STAMP(i) do { if (trace && threadIdx.x == 0 && hi_ == 0) trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
+  // trace (trace build only): per CTA 16 clock64 stamps of thread 0 at the phase boundaries of its first head
+#define AT_STAMP(i) SAST_STAMP(trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16, trace && threadIdx.x == 0 && hi_ == 0, (i))
+#ifdef SAST_TRACE
   const long long t_entry = trace ? clock64() : 0;
+#endif
   pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float pmax[2][128];
@@ -130,12 +132,14 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   for (int hi_ = 0; hi_ < heads_per_cta; ++hi_) {
     const int h = h_begin + hi_;
     const uint32_t ph = (uint32_t)(hi_ & 1);
+#ifdef SAST_TRACE
     if (trace && tid == 0 && hi_ == 0) {
       trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 0] = t_entry;
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = smid;
     }
+#endif
     AT_STAMP(1);
     if (warp == 0) {                                          // whole warp, uniform operands; one elected lane issues
       const bool leader = ptx::elect_one();
@@ -366,8 +370,6 @@ __global__ void __launch_bounds__(128) attention_bf16_kernel(const __nv_bfloat16
 int make_tmap_bf16_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows,
                        int swizzle_bytes);
 
-static long long* g_attn_trace = nullptr;      // debug: set through sast_debug_attn_trace, one launch's CTAs x 16 stamps
-
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, const sast_selection& sel, int NW, int T,
                         long long max_rows, int variant, cudaStream_t st) {
   const int heads = C / 32;
@@ -390,13 +392,9 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   // enough CTAs to fill the chip: all heads in one CTA when there are many tiles, one head per CTA otherwise
   int hpc = heads;
   while (hpc > 1 && (long long)NW * (heads / hpc) < 4 * 148 && hpc % 2 == 0) hpc /= 2;
-  sast::launch_k(attention_tc_kernel, dim3(NW, heads / hpc), 256, smem, st, mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T, g_attn_trace);
+  sast::launch_k(attention_tc_kernel, dim3(NW, heads / hpc), 256, smem, st, mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T, g_trace_which == 1 ? g_trace : nullptr);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }
 
 }  // namespace sast
-
-// Debug aid (tools/attn_trace.py): the next attention launches write thread 0's clock64 stamps at the phase
-// boundaries of each CTA's first head into buf ([grid.y * grid.x][16] int64; slot 15 = SM id).  Null switches it off.
-extern "C" void sast_debug_attn_trace(long long* buf) { sast::g_attn_trace = buf; }

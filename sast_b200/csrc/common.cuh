@@ -153,4 +153,15 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
   return fmaf(hx, t, hx);
 }
 
+extern long long* g_trace;   // api.cu; null unless sast_debug_trace armed it
+extern int g_trace_which;    // 1: attention kernels stamp, 2: GEMM kernels stamp
+
+// Phase stamps for tools/attn_trace.py / tools/gemm_trace.py.  Compiled in only with -DSAST_TRACE (`make trace` ->
+// libsast_b200_trace.so): even predicated-off stamps cost the GLU GEMM ~10 % through register allocation.
+#ifdef SAST_TRACE
+#define SAST_STAMP(ptr, cond, slot) do { if ((ptr) && (cond)) (ptr)[(slot)] = clock64(); } while (0)
+#else
+#define SAST_STAMP(ptr, cond, slot) ((void)0)
+#endif
+
 }  // namespace sast

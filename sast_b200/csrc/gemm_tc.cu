@@ -52,6 +52,10 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const float* __restrict__ bias, int N, int K, int BN, int stages,
                                                                 const int* __restrict__ counts, int m_static, EpiParams ep) {
+  // trace build only: [CTA][128] clock64: 0 entry, 1 set-up done, 2 end; per tile ti < 8: MMA warp 8+4ti {accumulator free,
+  // first k-block landed, last commit issued}, epilogue (quarter 0) 48+4ti {accumulator full, drained}, producer 100+ti; 127 SM id
+  [[maybe_unused]] long long* const trc = ep.trace ? ep.trace + (size_t)blockIdx.x * 128 : nullptr;
+  SAST_STAMP(trc, threadIdx.x == 0, 0);
   pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NG = tc_groups(EPI);
@@ -87,18 +91,23 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
+  SAST_STAMP(trc, threadIdx.x == 0, 1);
+#ifdef SAST_TRACE
+  if (trc && threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); trc[127] = smid; }
+#endif
 
   // The producer and MMA warps run their loops as WHOLE warps on warp-uniform values and guard only the TMA /
   // tcgen05 instructions with an elected lane: under `if (lane == 0)` the descriptors sit in per-thread registers
   // and every UTCHMMA pays an ELECT / R2UR waterfall loop (~120 clk per instruction, measured in attn_tc).
   if (warp == 0) {
     const bool leader = ptx::elect_one();
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    uint32_t it = 0, pti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++pti) {
       const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t s = it % (uint32_t)stages, round = it / (uint32_t)stages;
         ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
+        SAST_STAMP(trc, leader && kb == 0 && pti < 8, 100 + pti);
         uint8_t* sa = base + (size_t)s * stage_bytes;
         const int k0 = kb * kBK;
         if (leader) {
@@ -117,11 +126,13 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
       const uint32_t acc = ti % NG, use = ti / NG;
       ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);       // epilogue has drained this accumulator
+      SAST_STAMP(trc, leader && ti < 8, 8 + 4 * ti);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t s = it % (uint32_t)stages, round = it / (uint32_t)stages;
         ptx::mbar_wait(&sm->full[s], round & 1);
+        SAST_STAMP(trc, leader && kb == 0 && ti < 8, 9 + 4 * ti);
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
         const uint64_t da = ptx::umma_desc_sw128_kmajor(sa);
@@ -141,6 +152,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
         }
       }
       if (leader) ptx::umma_commit(&sm->tmem_full[acc]);      // accumulator complete
+      SAST_STAMP(trc, leader && ti < 8, 10 + 4 * ti);
     }
   } else {
     // ---------------- epilogue: group g = (warp-2)/4 drains accumulator g; TMEM lane quarter = warp % 4 ----------------
@@ -153,6 +165,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
       const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
       const uint32_t tmem_d = tmem_base + (uint32_t)group * (uint32_t)BN + ((uint32_t)(quarter * 32) << 16);
       ptx::mbar_wait(&sm->tmem_full[group], use & 1);
+      SAST_STAMP(trc, quarter == 0 && lane == 0 && ti < 8, 48 + 4 * ti);
       ptx::tc_fence_after();
       {
         // tcgen05.ld gives every lane 32 consecutive accumulator columns of ITS row; global memory wants the
@@ -262,6 +275,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
         }
       }
       // this warp's TMEM reads are complete: hand the accumulator back to the MMA warp
+      SAST_STAMP(trc, quarter == 0 && lane == 0 && ti < 8, 49 + 4 * ti);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&sm->tmem_empty[group]);
@@ -273,6 +287,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, tmem_cols);
   }
+  SAST_STAMP(trc, threadIdx.x == 0, 2);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -352,7 +367,9 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* 
   }
   const long long tiles = ((max_rows + TC_BM - 1) / TC_BM) * (N / BN);       // worst case; the kernel clips to counts[1]
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-  sast::launch_k(gemm_tc_kernel<EPI>, grid, tc_threads(EPI), smem, st, ma, ma2 ? *ma2 : ma, k_split, mw, bias, N, K, BN, stages, counts, m_static, ep);
+  EpiParams ept = ep;
+  ept.trace = g_trace_which == 2 ? g_trace : nullptr;
+  sast::launch_k(gemm_tc_kernel<EPI>, grid, tc_threads(EPI), smem, st, ma, ma2 ? *ma2 : ma, k_split, mw, bias, N, K, BN, stages, counts, m_static, ept);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

@@ -24,6 +24,7 @@ struct EpiParams {
   const float* gamma;      // [N] or nullptr (identity)
   const int* row_pix;      // compacted row -> NHWC pixel index, for EPI_SCATTER
   int C;                   // channels of the NHWC map (EPI_SCATTER)
+  long long* trace;        // debug stamps (sast_debug_trace), normally null
 };
 
 struct LayerWorkspace {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Phase timeline of attention_tc_kernel CTAs (debug aid): runs one MS-WSA layer at a stage shape of the
-1 Mpx B=8 workload with sast_debug_attn_trace armed and prints, per phase, the median / p90 clock deltas of
+1 Mpx B=8 workload with sast_debug_trace armed and prints, per phase, the median / p90 clock deltas of
 the CTAs' first head, plus how long each SM was busy.  Usage: attn_trace.py [stage 1..4]"""
 import os
 import sys
@@ -8,6 +8,7 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("SAST_B200_LIB", os.path.join(ROOT, "sast_b200", "libsast_b200_trace.so"))   # `make -C sast_b200/csrc trace`
 sys.path.insert(0, ROOT)
 import sast_b200  # noqa: E402
 from sast_b200 import _lib as L, ops  # noqa: E402
@@ -33,12 +34,12 @@ with torch.no_grad():
     torch.cuda.synchronize()
     heads = C // 32
     buf = torch.zeros(NW * heads * 16, dtype=torch.int64, device=dev)
-    L.lib().sast_debug_attn_trace(buf.data_ptr())
+    L.lib().sast_debug_trace(buf.data_ptr(), 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush.zero_()
     layer.run(x, sel, L.WINDOW, False)
     torch.cuda.synchronize()
-    L.lib().sast_debug_attn_trace(None)
+    L.lib().sast_debug_trace(None, 0)
 t = buf.view(-1, 16).cpu()
 t = t[t[:, 10] != 0]
 print(f"stage {stage}: C={C} windows={NW} traced CTAs={len(t)}")
