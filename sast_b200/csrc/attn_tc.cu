@@ -77,13 +77,17 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
 #ifdef SAST_TRACE
   const long long t_entry = trace ? clock64() : 0;
 #endif
-  pdl_entry();
+  // PDL: the selection record was written >= 2 kernels ago (select -> gather -> QKV GEMM -> here), so the whole prologue
+  // -- index loads, barriers, TMEM -- runs before griddepcontrol.wait and overlaps the tail of the QKV GEMM
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float pmax[2][128];
+  __shared__ int wst[130];                                 // first compacted row (tile relative) of each window of this tile
   const int w = blockIdx.x;
-  const int rows = tiles[2 * w];
+  const int2 tile = *reinterpret_cast<const int2*>(tiles + 2 * w);     // rows, one past the last window
+  const int rows = tile.x;
   if (rows == 0) return;                                   // not a tile leader
   const int row0 = win_row0[w];
+  const int nwin = min(tile.y - w, 128);
   const int tid = threadIdx.x, warp = __shfl_sync(kFull, tid >> 5, 0), lane = tid & 31;   // warp: provably uniform
   const int half = warp >> 2;                              // which 64 key columns
   const int t = (warp & 3) * 32 + lane;                    // tile row = TMEM lane
@@ -105,6 +109,7 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   }
   if (warp == 0) ptx::tmem_alloc(&sm->tmem_base, AT_TMEM_COLS);
   reinterpret_cast<uint32_t*>(sOnes)[tid] = 0x3F803F80u;   // 256 threads x 4 bytes
+  if (tid <= nwin) wst[tid] = win_row0[w + tid] - row0;
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
@@ -116,9 +121,10 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   // key range of this row: the compacted rows of its own window
   int lo = 0, hi = 0;
   if (t < rows) {
-    const int wi = row_tok[row0 + t] / T;
-    lo = win_row0[wi] - row0;
-    hi = win_row0[wi + 1] - row0;
+    for (int i = 0; i < nwin; ++i) {                       // 2-3 windows per tile as a rule
+      const int a = wst[i], b = wst[i + 1];
+      if (t >= a && t < b) { lo = a; hi = b; }
+    }
   }
   const int rows16 = (rows + 15) & ~15;
   const float sc = 0.17677669529663688110f * 1.44269504088896340736f;   // 32^-0.5 * log2(e)
@@ -129,6 +135,7 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   uint8_t* prow = sP + (t >> 3) * 1024 + r8 * 128;
 
   const int h_begin = blockIdx.y * heads_per_cta;
+  pdl_entry();                                             // qkv (the QKV GEMM's output) is read from here on
   for (int hi_ = 0; hi_ < heads_per_cta; ++hi_) {
     const int h = h_begin + hi_;
     const uint32_t ph = (uint32_t)(hi_ & 1);

@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
   // first k-block landed, last commit issued}, epilogue (quarter 0) 48+4ti {accumulator full, drained}, producer 100+ti; 127 SM id
   [[maybe_unused]] long long* const trc = ep.trace ? ep.trace + (size_t)blockIdx.x * 128 : nullptr;
   SAST_STAMP(trc, threadIdx.x == 0, 0);
-  pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NG = tc_groups(EPI);
   __shared__ __align__(16) float stage_smem[NG * 4][32 * 32];   // epilogue transpose tiles (XOR-swizzled 16-byte groups)
@@ -91,6 +90,9 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
+  // PDL: everything above (barriers, TMEM, index loads of data written >= 2 kernels ago) overlapped the tail of the
+  // preceding kernel; its output is read only from here on
+  pdl_entry();
   SAST_STAMP(trc, threadIdx.x == 0, 1);
 #ifdef SAST_TRACE
   if (trc && threadIdx.x == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); trc[127] = smid; }

@@ -50,7 +50,6 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
                                                                  const float* __restrict__ sig, const float* __restrict__ inv,
                                                                  int HW, int C, int BN, long long P, float* __restrict__ xw,
                                                                  float* __restrict__ l1_out) {
-  pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];     // ring | ScSmem | epilogue transpose tiles
   const int m_tiles = (int)((P + SC_BM - 1) / SC_BM), n_tiles = C / BN;
   const int total_tiles = m_tiles * n_tiles;
@@ -78,6 +77,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
+  // PDL: everything above (barriers, TMEM, index loads of data written >= 2 kernels ago) overlapped the tail of the
+  // preceding kernel; its output is read only from here on
+  pdl_entry();
 
   if (warp < 4) {
     // ---------------- loaders ----------------

@@ -49,7 +49,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
                                                                 int Cout, int n_groups_pad, const float* __restrict__ ln_w,
                                                                 const float* __restrict__ ln_b, float eps,
                                                                 float* __restrict__ out) {
-  pdl_entry();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(16) float stage_smem[4][32 * 32];
   const int Ho = H / 4, Wo = W / 4;
@@ -78,6 +77,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
+  // PDL: everything above (barriers, TMEM, index loads of data written >= 2 kernels ago) overlapped the tail of the
+  // preceding kernel; its output is read only from here on
+  pdl_entry();
 
   if (warp < 8) {
     // ---------------- A producers ----------------
