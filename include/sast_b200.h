@@ -78,9 +78,9 @@ typedef struct sast_selection {
   int32_t* row_pix;   /* [P]    first S entries: NHWC pixel index (b*H*W + y*W + x) of row r */
   float*   win_logit; /* [NW]   scratch: mean token score of window w (SCORES mode)         */
   uint8_t* tok_keep;  /* [P]    scratch: keep flag per token, partitioned order             */
-  int32_t* tiles;     /* [NW*2] attention tiles (consecutive windows of one frame, <= 128 rows):
-                                tiles[2w] = rows of the tile led by window w (0 = not a leader),
-                                tiles[2w+1] = one past the tile's last window                */
+  int32_t* tiles;     /* [NW*2] attention tiles (consecutive windows of one frame, <= 128 rows): the j-th tile
+                                of frame b is slot b*N + j: tiles[2 slot] = its first window (-1 = unused slot),
+                                tiles[2 slot + 1] = one past its last window                   */
 } sast_selection;
 
 /* Bytes of one int32 pool able to hold a sast_selection for (NW, P, B); see sast_selection_bind. */

@@ -70,8 +70,7 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv,
                                                            __nv_bfloat16* __restrict__ att, int C, int heads_per_cta,
                                                            const int* __restrict__ tiles, const int* __restrict__ win_row0,
-                                                           const int* __restrict__ row_tok, int T,
-                                                           long long* __restrict__ trace) {
+                                                           int B, long long* __restrict__ trace) {
   // trace (trace build only): per CTA 16 clock64 stamps of thread 0 at the phase boundaries of its first head
 #define AT_STAMP(i) SAST_STAMP(trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16, trace && threadIdx.x == 0 && hi_ == 0, (i))
 #ifdef SAST_TRACE
@@ -82,11 +81,13 @@ __global__ void __launch_bounds__(256) attention_tc_kernel(const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float pmax[2][128];
   __shared__ int wst[130];                                 // first compacted row (tile relative) of each window of this tile
-  const int w = blockIdx.x;
-  const int2 tile = *reinterpret_cast<const int2*>(tiles + 2 * w);     // rows, one past the last window
-  const int rows = tile.x;
-  if (rows == 0) return;                                   // not a tile leader
+  // grid.x is tile-major (j * B + b) over the per-frame slot lists, so the CTAs of unused slots are launched last
+  const int slot = (int)(blockIdx.x % (unsigned)B) * (int)(gridDim.x / (unsigned)B) + (int)(blockIdx.x / (unsigned)B);
+  const int2 tile = *reinterpret_cast<const int2*>(tiles + 2 * slot);  // first window, one past the last window
+  if (tile.x < 0) return;                                  // unused slot
+  const int w = tile.x;
   const int row0 = win_row0[w];
+  const int rows = win_row0[tile.y] - row0;
   const int nwin = min(tile.y - w, 128);
   const int tid = threadIdx.x, warp = __shfl_sync(kFull, tid >> 5, 0), lane = tid & 31;   // warp: provably uniform
   const int half = warp >> 2;                              // which 64 key columns
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(128) attention_bf16_kernel(const __nv_bfloat16
 int make_tmap_bf16_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows,
                        int swizzle_bytes);
 
-int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, const sast_selection& sel, int NW, int T,
+int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, const sast_selection& sel, int NW, int B, int T,
                         long long max_rows, int variant, cudaStream_t st) {
   const int heads = C / 32;
   if (variant == 1) {
@@ -399,7 +400,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   // enough CTAs to fill the chip: all heads in one CTA when there are many tiles, one head per CTA otherwise
   int hpc = heads;
   while (hpc > 1 && (long long)NW * (heads / hpc) < 4 * 148 && hpc % 2 == 0) hpc /= 2;
-  sast::launch_k(attention_tc_kernel, dim3(NW, heads / hpc), 256, smem, st, mq, att, C, hpc, sel.tiles, sel.win_row0, sel.row_tok, T, g_trace_which == 1 ? g_trace : nullptr);
+  sast::launch_k(attention_tc_kernel, dim3(NW, heads / hpc), 256, smem, st, mq, att, C, hpc, sel.tiles, sel.win_row0, B, g_trace_which == 1 ? g_trace : nullptr);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

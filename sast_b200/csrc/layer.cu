@@ -503,7 +503,7 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
     ep.out_bf16 = (__nv_bfloat16*)ws.qkv; ep.ldo = 3 * C;
     rc = launch_gemm_tc(ws.n2h, C, (const __nv_bfloat16*)w.qkv_w_bf16, w.qkv_b, 3 * C, C, a.sel.counts, g.P, EPI_STORE, ep, st);
     if (rc) return rc;
-    rc = launch_attention_tc((const __nv_bfloat16*)ws.qkv, (__nv_bfloat16*)ws.att, C, a.sel, g.NW, g.T, g.P, attention_variant(), st);
+    rc = launch_attention_tc((const __nv_bfloat16*)ws.qkv, (__nv_bfloat16*)ws.att, C, a.sel, g.NW, g.B, g.T, g.P, attention_variant(), st);
     if (rc) return rc;
     ep.out_f32 = ws.yf; ep.out_bf16 = ws.yh; ep.ldo = C; ep.resid = ws.n2f; ep.ldr = C; ep.gamma = w.gamma1;
     rc = launch_gemm_tc((const __nv_bfloat16*)ws.att, C, (const __nv_bfloat16*)w.proj_w_bf16, w.proj_b, C, C, a.sel.counts, g.P,

@@ -45,7 +45,7 @@ size_t layer_workspace_layout(long long P, int C, int I, int B, int precision, v
 int launch_gemm_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, const float* bias, int N, int K,
                    const int* counts, long long max_rows, int epi, const EpiParams& ep, cudaStream_t st);
 // variant 0: tcgen05 tiles; 1: CUDA-core kernel (debug knob SAST_B200_ATTN=simt)
-int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, const sast_selection& sel, int NW, int T,
+int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, const sast_selection& sel, int NW, int B, int T,
                         long long max_rows, int variant, cudaStream_t st);
 
 }  // namespace sast

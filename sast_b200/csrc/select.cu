@@ -11,7 +11,7 @@
 //                          probabilities / given flags: modes PROBS, FLAGS.)
 //   select_scan_kernel   : CTA per frame: exclusive prefix sums across frames and windows ->
 //                          win_rank, sel_win, win_row0, counts{M,S,Kmax}; greedy packing of
-//                          consecutive windows into <=128-row attention tiles.
+//                          consecutive windows into <=128-row attention tiles (dense per-frame slot list).
 //   select_tokens_kernel : warp per window: ballot/popc prefix inside the window -> tok_row,
 //                          row_tok, row_pix (compacted row <-> token <-> NHWC pixel).
 // The compare is `prob >= thr` on fp32 with thr = fp32((1/N)/(1+BOUNCE)) exactly as torch
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
         sel.win_rank[w] = run_m + em;
         sel.sel_win[run_m + em] = w;
       }
-      sel.tiles[2 * w] = 0;
+      sel.tiles[2 * w] = -1;           // tile slot n of this frame: unused until the packer below claims it
       sel.tiles[2 * w + 1] = 0;
     }
     run_m += tm; run_s += ts;
@@ -231,22 +231,23 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
     }
   }
   __syncthreads();
-  // greedy packing of consecutive windows of this frame into attention tiles of <= 128 rows:
-  // tiles[2w] = rows of the tile led by window w (0: not a leader), tiles[2w+1] = end window (exclusive)
+  // greedy packing of consecutive windows of this frame into attention tiles of <= 128 rows.  The j-th tile of
+  // frame b goes to slot b*N + j: tiles[2 slot] = first window, tiles[2 slot + 1] = one past its last window
+  // (first window -1: slot unused).  Slots are dense from j = 0, so a tile-major grid has its idle CTAs last.
   if (threadIdx.x == 0) {
-    int start = 0, rows = 0;
+    int start = 0, rows = 0, j = 0;
     for (int n = 0; n < g.N; ++n) {
       const int K = kbuf[n];
       if (rows + K > 128) {
-        sel.tiles[2 * (b * g.N + start)] = rows;
-        sel.tiles[2 * (b * g.N + start) + 1] = b * g.N + n;
-        start = n; rows = 0;
+        sel.tiles[2 * (b * g.N + j)] = b * g.N + start;
+        sel.tiles[2 * (b * g.N + j) + 1] = b * g.N + n;
+        ++j; start = n; rows = 0;
       }
       rows += K;
     }
     if (rows > 0) {
-      sel.tiles[2 * (b * g.N + start)] = rows;
-      sel.tiles[2 * (b * g.N + start) + 1] = b * g.N + g.N;
+      sel.tiles[2 * (b * g.N + j)] = b * g.N + start;
+      sel.tiles[2 * (b * g.N + j) + 1] = b * g.N + g.N;
     }
   }
 }
