@@ -224,9 +224,11 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
           }
           if (EPI == EPI_GLU) {                // columns interleaved value_j, gate_j
             __nv_bfloat162 o[8];
+            const float2 hb = make_float2(0.5f * b4.x, 0.5f * b4.z);     // the 0.5 of the GELU rides on the value branch
 #pragma unroll
             for (int it = 0; it < 8; ++it)
-              o[it] = __floats2bfloat162_rn((a4[it].x + b4.x) * gelu_tanh_fit(a4[it].y + b4.y), (a4[it].z + b4.z) * gelu_tanh_fit(a4[it].w + b4.w));
+              o[it] = __floats2bfloat162_rn(glu_tanh_fit(fmaf(a4[it].x, 0.5f, hb.x), a4[it].y + b4.y),
+                                            glu_tanh_fit(fmaf(a4[it].z, 0.5f, hb.y), a4[it].w + b4.w));
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int row = m0 + quarter * 32 + it * 4 + r_sub;
