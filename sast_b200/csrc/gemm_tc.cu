@@ -160,25 +160,37 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
     // ---------------- epilogue: group g = (warp-2)/4 drains accumulator g; TMEM lane quarter = warp % 4 ----------------
     const int group = (warp - 2) >> 2;
     const int quarter = warp & 3;
+    // tcgen05.ld gives every lane 32 consecutive accumulator columns of ITS row; global memory wants the
+    // opposite (a warp instruction covering whole row segments).  Phase A: each lane drops its 32 values
+    // into a [32 rows x 128 B] shared-memory tile with 8 x STS.128, 16-byte groups XOR-swizzled by
+    // (row % 8) -- conflict free.  Phase B: lane = (row-in-group r_sub, 16-byte column group gq); per
+    // iteration a warp handles 4 full rows: LDS.128, epilogue math on 4 columns whose bias / gamma are
+    // lane constants, one 4..16-byte store per output -- every global access is a dense row segment.
+    float* stage = &stage_smem[warp - 2][0];
+    const int r_sub = lane >> 3, gq = lane & 7, c4 = gq * 4;
+    // Global addresses are (warp-uniform base of the tile / chunk) + (32-bit lane offset that never changes):
+    // the offsets of this lane's 8 phase-B rows are computed once per kernel, so a store costs one instruction
+    // instead of a 64-bit multiply-add and a bounds test (these were a quarter of the GLU epilogue's instructions).
+    constexpr int kColShift = EPI == EPI_GLU ? 1 : EPI == EPI_LSTM ? 2 : 0;     // accumulator column -> output column
+    uint32_t ooff[8], roff[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const uint32_t r = (uint32_t)(quarter * 32 + it * 4 + r_sub);
+      ooff[it] = r * (uint32_t)ep.ldo + (uint32_t)(c4 >> kColShift);
+      roff[it] = r * (uint32_t)ep.ldr + (uint32_t)(c4 >> kColShift);
+    }
     uint32_t ti = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
       if ((int)(ti % NG) != group) continue;
       const uint32_t use = ti / NG;
       const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+      const bool full = m0 + TC_BM <= M;                   // warp-uniform: only the last row tile tests rows
+      const int row_lim = M - m0 - quarter * 32 - r_sub;   // row it is valid iff it * 4 < row_lim
       const uint32_t tmem_d = tmem_base + (uint32_t)group * (uint32_t)BN + ((uint32_t)(quarter * 32) << 16);
       ptx::mbar_wait(&sm->tmem_full[group], use & 1);
       SAST_STAMP(trc, quarter == 0 && lane == 0 && ti < 8, 48 + 4 * ti);
       ptx::tc_fence_after();
       {
-        // tcgen05.ld gives every lane 32 consecutive accumulator columns of ITS row; global memory wants the
-        // opposite (a warp instruction covering whole row segments).  Phase A: each lane drops its 32 values
-        // into a [32 rows x 128 B] shared-memory tile with 8 x STS.128, 16-byte groups XOR-swizzled by
-        // (row % 8) -- conflict free.  Phase B: lane = (row-in-group r_sub, 16-byte column group gq); per
-        // iteration a warp handles 4 full rows: LDS.128, epilogue math on 4 columns whose bias / gamma are
-        // lane constants, one 4..16-byte store per output -- every global access is a dense row segment.
-        float* stage = &stage_smem[warp - 2][0];
-        const int r_sub = lane >> 3, gq = lane & 7, c4 = gq * 4;
-        // rows of this lane in phase B (fixed per tile): r = it*4 + r_sub
         long long pixo[8];
         if (EPI == EPI_SCATTER) {
 #pragma unroll
@@ -191,21 +203,25 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
           uint32_t raw[32];
           ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
           const int n = n0 + c0 + c4;
+          const size_t ocol = (size_t)m0 * ep.ldo + (size_t)((n0 + c0) >> kColShift);    // warp-uniform
+          const size_t rcol = (size_t)m0 * ep.ldr + (size_t)((n0 + c0) >> kColShift);
           float4 r4[8];
           if (EPI == EPI_RESID || EPI == EPI_SCATTER) {    // residual rows in flight while the TMEM load completes
+            const float* rb = ep.resid + rcol;
+            if (full) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = m0 + quarter * 32 + it * 4 + r_sub;
-              r4[it] = row < M ? *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int it = 0; it < 8; ++it) r4[it] = *reinterpret_cast<const float4*>(rb + roff[it]);
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                r4[it] = it * 4 < row_lim ? *reinterpret_cast<const float4*>(rb + roff[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
           float cprev[8];
           if (EPI == EPI_LSTM) {
+            const float* pb = ep.resid ? ep.resid + rcol : nullptr;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = m0 + quarter * 32 + it * 4 + r_sub;
-              cprev[it] = (ep.resid && row < M) ? ep.resid[(size_t)row * ep.ldr + (n >> 2)] : 0.f;
-            }
+            for (int it = 0; it < 8; ++it) cprev[it] = (pb && (full || it * 4 < row_lim)) ? pb[roff[it]] : 0.f;
           }
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
           if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
@@ -215,7 +231,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
           for (int k = 0; k < 8; ++k)
             *reinterpret_cast<uint4*>(stage + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_uint4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]);
           __syncwarp();
-          // math for all 8 row-iterations is straight-line (independent chains interleave); only the stores are predicated
+          // math for all 8 row-iterations is straight-line (independent chains interleave)
           float4 a4[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -229,10 +245,14 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
             for (int it = 0; it < 8; ++it)
               o[it] = __floats2bfloat162_rn(glu_tanh_fit(fmaf(a4[it].x, 0.5f, hb.x), a4[it].y + b4.y),
                                             glu_tanh_fit(fmaf(a4[it].z, 0.5f, hb.y), a4[it].w + b4.w));
+            __nv_bfloat16* ob = ep.out_bf16 + ocol;
+            if (full) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = m0 + quarter * 32 + it * 4 + r_sub;
-              if (row < M) *reinterpret_cast<__nv_bfloat162*>(ep.out_bf16 + (size_t)row * ep.ldo + (n >> 1)) = o[it];
+              for (int it = 0; it < 8; ++it) *reinterpret_cast<__nv_bfloat162*>(ob + ooff[it]) = o[it];
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                if (it * 4 < row_lim) *reinterpret_cast<__nv_bfloat162*>(ob + ooff[it]) = o[it];
             }
           } else if (EPI == EPI_LSTM) {        // columns interleaved forget, input, output, cell-input of one channel
             float hn[8], cn[8];
@@ -244,33 +264,46 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
               cn[it] = f * cprev[it] + ig * g;
               hn[it] = og * tanh_fast(cn[it]);
             }
+            float* hb_ = ep.out_f32 + ocol;
+            float* cb = ep.out2_f32 + ocol;
+            if (full) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = m0 + quarter * 32 + it * 4 + r_sub;
-              if (row < M) {
-                ep.out2_f32[(size_t)row * ep.ldo + (n >> 2)] = cn[it];
-                ep.out_f32[(size_t)row * ep.ldo + (n >> 2)] = hn[it];
-              }
+              for (int it = 0; it < 8; ++it) { cb[ooff[it]] = cn[it]; hb_[ooff[it]] = hn[it]; }
+            } else {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                if (it * 4 < row_lim) { cb[ooff[it]] = cn[it]; hb_[ooff[it]] = hn[it]; }
             }
           } else {
+            float4 v4[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              const int row = m0 + quarter * 32 + it * 4 + r_sub;
-              if (row >= M) continue;
-              float v0 = a4[it].x + b4.x, v1 = a4[it].y + b4.y, v2 = a4[it].z + b4.z, v3 = a4[it].w + b4.w;
+              v4[it] = make_float4(a4[it].x + b4.x, a4[it].y + b4.y, a4[it].z + b4.z, a4[it].w + b4.w);
               if (EPI == EPI_RESID || EPI == EPI_SCATTER) {
-                v0 = r4[it].x + g4.x * v0; v1 = r4[it].y + g4.y * v1; v2 = r4[it].z + g4.z * v2; v3 = r4[it].w + g4.w * v3;
+                v4[it].x = r4[it].x + g4.x * v4[it].x; v4[it].y = r4[it].y + g4.y * v4[it].y;
+                v4[it].z = r4[it].z + g4.z * v4[it].z; v4[it].w = r4[it].w + g4.w * v4[it].w;
               }
-              if (EPI == EPI_SCATTER) {
-                *reinterpret_cast<float4*>(ep.out_f32 + pixo[it] + n) = make_float4(v0, v1, v2, v3);
-              } else {
-                if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + (size_t)row * ep.ldo + n) = make_float4(v0, v1, v2, v3);
-                if (ep.out_bf16) {
-                  const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+            }
+            if (EPI == EPI_SCATTER) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                if (pixo[it] >= 0) *reinterpret_cast<float4*>(ep.out_f32 + pixo[it] + n) = v4[it];
+            } else {
+              if (ep.out_f32) {
+                float* of = ep.out_f32 + ocol;
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                  if (full || it * 4 < row_lim) *reinterpret_cast<float4*>(of + ooff[it]) = v4[it];
+              }
+              if (ep.out_bf16) {
+                __nv_bfloat16* oh = ep.out_bf16 + ocol;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const __nv_bfloat162 lo = __floats2bfloat162_rn(v4[it].x, v4[it].y), hi = __floats2bfloat162_rn(v4[it].z, v4[it].w);
                   uint2 pk;
                   pk.x = *reinterpret_cast<const uint32_t*>(&lo);
                   pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                  *reinterpret_cast<uint2*>(ep.out_bf16 + (size_t)row * ep.ldo + n) = pk;
+                  if (full || it * 4 < row_lim) *reinterpret_cast<uint2*>(oh + ooff[it]) = pk;
                 }
               }
             }
