@@ -4,12 +4,13 @@
 // the canonical TN shape, so both operands are TMA-loaded as SWIZZLE_128B tiles and fed to
 // tcgen05.mma straight from shared memory; the fp32 accumulator lives in TMEM.
 //
-// Persistent CTAs (one per SM), each walking 128 x BN output tiles, 10 warps:
-//   warp 0   TMA producer   (one lane; ring of 4 {A 128x64, W BNx64} bf16 stages, runs ahead across tiles)
-//   warp 1   TMEM allocator + MMA issuer (one lane; tcgen05.mma M=128,N=BN,K=16, 4 per k-block; two
-//            accumulators so the next tile is multiplied while the previous one is drained)
-//   warps 2-   epilogue (two or three groups of 4, one per accumulator): tcgen05.ld 32 lanes x 32 columns per warp (warp w owns TMEM
-//            lanes 32*(w%4)..+31 = output rows); bias / LayerScale / residual / GLU / scatter in registers.
+// Persistent CTAs (one per SM), each walking 128 x BN output tiles, 14 warps:
+//   warp 0   TMA producer   (elected lane; ring of 4 {A 128x64, W BNx64} bf16 stages, runs ahead across tiles)
+//   warp 1   TMEM allocator + MMA issuer (elected lane; tcgen05.mma M=128,N=BN,K=16, 4 per k-block; three
+//            accumulators so the next tiles are multiplied while the previous ones are drained)
+//   warps 2-13 epilogue (three groups of 4, one per accumulator): tcgen05.ld 32 lanes x 32 columns per warp
+//            (warp w owns TMEM lanes 32*(w%4)..+31 = output rows); bias / LayerScale / residual / GLU / scatter
+//            in registers.
 // M (= number of selected tokens) is read from device memory; CTAs past it exit at once.
 // K tails (K % 64 != 0) rely on TMA zero fill and issue only the k-steps that hold data.
 #include "layer.cuh"
@@ -19,9 +20,10 @@ namespace sast {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;
 constexpr int TC_MAX_GROUPS = 3;
-// epilogue groups of 4 warps, one TMEM accumulator each: the math-heavy epilogues (erf-GELU, LSTM gates: ~30
-// instructions per output) are issue bound, so they get three groups; the rest are fine with two
-constexpr int tc_groups(int epi) { return (epi == EPI_GLU || epi == EPI_LSTM) ? 3 : 2; }
+// Epilogue groups of 4 warps, one TMEM accumulator each.  The epilogues dominate these kernels (a 128 x BN tile is
+// multiplied in ~650 clk and drained in 5-10k clk, tools/gemm_trace.py): three groups for every flavour -- the
+// math-heavy ones (GLU, LSTM gates) are issue bound, the others latency bound, and a third group helps both.
+constexpr int tc_groups(int epi) { return 3 + 0 * epi; }
 constexpr int tc_threads(int epi) { return 64 + tc_groups(epi) * 128; }   // warp 0 TMA, warp 1 MMA, then the epilogue warps
 
 struct TcSmem {            // lives after the operand ring (which needs 1024-byte alignment)
@@ -44,8 +46,8 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 
 // Persistent: every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest, so CTAs that
 // run side by side share the A tile in L2).  The TMA ring runs ahead across tile boundaries, the MMA
-// warp ping-pongs between two TMEM accumulators, and the two epilogue groups (4 warps each, one per
-// accumulator) drain tile i while tile i+1 is being loaded and multiplied.
+// warp cycles through three TMEM accumulators, and the three epilogue groups (4 warps each, one per
+// accumulator) drain tiles i, i+1 while tile i+2 is being loaded and multiplied.
 template <int EPI>
 __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_a2, int k_split,
@@ -499,7 +501,7 @@ extern "C" int sast_gemm_bf16(const uint16_t* A, const uint16_t* W, const float*
   using namespace sast;
   SAST_CHECK_PTR(A); SAST_CHECK_PTR(W); SAST_CHECK_PTR(D);
   if (M <= 0 || N <= 0 || K <= 0) return SAST_E_SHAPE;
-  const int BN = pick_bn(N, (M + TC_BM - 1) / TC_BM);
+  const int BN = pick_bn(N, (M + TC_BM - 1) / TC_BM, tc_groups(EPI_STORE));
   if (BN == 0 || K % 8 != 0) return SAST_E_SHAPE;
   CUtensorMap ma, mw;
   int rc = make_tmap_bf16_2d(&ma, A, M, K, K, TC_BM);
