@@ -191,35 +191,55 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
       float l1[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) l1[i] = 0.f;
+      // sig / inv are per (frame, channel): one load per chunk unless the tile straddles two frames (late stages only)
+      const bool one_frame = (m0 / HW) == ((min(m0 + SC_BM, (int)P) - 1) / HW);
+      const int gq = lane & 7;
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t raw[32];
         ptx::tmem_ld_32x32(tmem_d + (uint32_t)c0, raw);
         const int nc = n0 + c0;
-        float4 xv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)             // x rows for the weighted map, in flight while TMEM loads
-          if (xo[i] >= 0) xv[i] = *reinterpret_cast<const float4*>(x + xo[i] + nc);
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bs + nc + c4));
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(raw[j]);
-        __syncwarp();
+        // every global load of the chunk is issued before anything waits (a `continue` inside the row loop used to
+        // serialise 8 x 3 dependent L2 round trips per chunk: ~11k clk per tile)
+        float4 xv[8], pv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (xo[i] < 0) continue;
+          if (xo[i] >= 0) {
+            xv[i] = *reinterpret_cast<const float4*>(x + xo[i] + nc);
+            pv[i] = __ldg(reinterpret_cast<const float4*>(pos + po[i] + nc));      // small table, cache resident
+          } else {
+            xv[i] = make_float4(0.f, 0.f, 0.f, 0.f); pv[i] = xv[i];
+          }
+        }
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bs + nc + c4));
+        float4 sg0 = __ldg(reinterpret_cast<const float4*>(sig + co[0] + nc));
+        float4 iv0 = __ldg(reinterpret_cast<const float4*>(inv + co[0] + nc));
+        ptx::tmem_ld_wait();
+        // transpose through shared memory: 8 x STS.128 / 8 x LDS.128, 16-byte groups XOR-swizzled by (row % 8)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(stage + lane * 32 + ((k ^ (lane & 7)) << 2)) = make_uint4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]);
+        __syncwarp();
+        float4 a4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + r_sub;
-          const float4 sg = __ldg(reinterpret_cast<const float4*>(sig + co[i] + nc));
-          const float4 iv = __ldg(reinterpret_cast<const float4*>(inv + co[i] + nc));
-          const float4 pv = __ldg(reinterpret_cast<const float4*>(pos + po[i] + nc));      // small table, cache resident
-          const float* sp = stage + r * 33 + c4;
-          const float s0 = fmaxf(sp[0] + b4.x, 0.f), s1 = fmaxf(sp[1] + b4.y, 0.f), s2 = fmaxf(sp[2] + b4.z, 0.f),
-                      s3 = fmaxf(sp[3] + b4.w, 0.f);
+          a4[i] = *reinterpret_cast<const float4*>(stage + r * 32 + ((gq ^ (r & 7)) << 2));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 sg = sg0, iv = iv0;
+          if (!one_frame) {                       // warp-uniform
+            sg = __ldg(reinterpret_cast<const float4*>(sig + co[i] + nc));
+            iv = __ldg(reinterpret_cast<const float4*>(inv + co[i] + nc));
+          }
+          const float s0 = fmaxf(a4[i].x + b4.x, 0.f), s1 = fmaxf(a4[i].y + b4.y, 0.f), s2 = fmaxf(a4[i].z + b4.z, 0.f),
+                      s3 = fmaxf(a4[i].w + b4.w, 0.f);
           float4 o;
-          o.x = (sg.x * __fdividef(1.0f, 1.0f + __expf(-s0))) * (xv[i].x + pv.x);
-          o.y = (sg.y * __fdividef(1.0f, 1.0f + __expf(-s1))) * (xv[i].y + pv.y);
-          o.z = (sg.z * __fdividef(1.0f, 1.0f + __expf(-s2))) * (xv[i].z + pv.z);
-          o.w = (sg.w * __fdividef(1.0f, 1.0f + __expf(-s3))) * (xv[i].w + pv.w);
-          *reinterpret_cast<float4*>(xw + xo[i] + nc) = o;
+          o.x = (sg.x * sigmoid_fast(s0)) * (xv[i].x + pv[i].x);
+          o.y = (sg.y * sigmoid_fast(s1)) * (xv[i].y + pv[i].y);
+          o.z = (sg.z * sigmoid_fast(s2)) * (xv[i].z + pv[i].z);
+          o.w = (sg.w * sigmoid_fast(s3)) * (xv[i].w + pv[i].w);
+          if (xo[i] >= 0) *reinterpret_cast<float4*>(xw + xo[i] + nc) = o;
           l1[i] += (fabsf(iv.x * s0) + fabsf(iv.y * s1)) + (fabsf(iv.z * s2) + fabsf(iv.w * s3));
         }
         __syncwarp();
