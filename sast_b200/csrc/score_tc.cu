@@ -49,7 +49,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
                                                                  long long pos_bstride, const float* __restrict__ bs,
                                                                  const float* __restrict__ sig, const float* __restrict__ inv,
                                                                  int HW, int C, int BN, long long P, float* __restrict__ xw,
-                                                                 float* __restrict__ l1_out) {
+                                                                 float* __restrict__ l1_out, long long* __restrict__ trace) {
+  // trace build only: same [CTA][128] slot layout as gemm_tc_kernel (0 entry, 1 set-up done, 2 end; per tile ti < 8: MMA
+  // 8+4ti {accumulator free, first k-block ready, last commit}, epilogue quarter 0: 48+4ti {full, drained}, loaders 100+ti)
+  [[maybe_unused]] long long* const trc = trace ? trace + (size_t)blockIdx.x * 128 : nullptr;
+  SAST_STAMP(trc, threadIdx.x == 0, 0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];     // ring | ScSmem | epilogue transpose tiles
   const int m_tiles = (int)((P + SC_BM - 1) / SC_BM), n_tiles = C / BN;
   const int total_tiles = m_tiles * n_tiles;
@@ -81,13 +85,15 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
   // preceding kernel; its output is read only from here on
   pdl_entry();
 
+  SAST_STAMP(trc, threadIdx.x == 0, 1);
   if (warp < 4) {
     // ---------------- loaders ----------------
     const int t = threadIdx.x;                 // 0..127
     const int chunk = t & 7;                   // 16-byte chunk of the 128-byte k-block row
     const int rbase = t >> 3;                  // rows rbase, rbase+16, ... (8 rows per thread)
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    [[maybe_unused]] uint32_t pti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++pti) {
       const int m0 = (tile / n_tiles) * SC_BM;
       const int n0 = (tile % n_tiles) * BN;
       int xo[8], po[8];
@@ -112,6 +118,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
           }
         }
         ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
+        SAST_STAMP(trc, threadIdx.x == 0 && kb == 0 && pti < 8, 100 + pti);
         uint8_t* st = base + (size_t)s * stage_bytes;
         if (warp == 0 && ptx::elect_one()) {     // warp-uniform operands, elected lane: no R2UR waterfall per TMA
           ptx::mbar_arrive_expect_tx(&sm->full[s], 2 * w_bytes);
@@ -140,11 +147,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t acc = ti % SC_GROUPS, use = ti / SC_GROUPS;
       ptx::mbar_wait(&sm->tmem_empty[acc], (use & 1) ^ 1);
+      SAST_STAMP(trc, leader && ti < 8, 8 + 4 * ti);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t s = it % SC_STAGES, round = it / SC_STAGES;
         ptx::mbar_wait(&sm->full[s], round & 1);
+        SAST_STAMP(trc, leader && kb == 0 && ti < 8, 9 + 4 * ti);
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(base + (size_t)s * stage_bytes);
         const uint64_t dah = ptx::umma_desc_sw128_kmajor(sa), dal = ptx::umma_desc_sw128_kmajor(sa + a_bytes);
@@ -161,6 +170,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
         }
       }
       if (leader) ptx::umma_commit(&sm->tmem_full[acc]);
+      SAST_STAMP(trc, leader && ti < 8, 10 + 4 * ti);
     }
   } else {
     // ---------------- epilogue (warps 4..15: group = (warp-4)/4, TMEM lane quarter = warp % 4) ----------------
@@ -187,6 +197,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
         co[i] = b * C + c4;
       }
       ptx::mbar_wait(&sm->tmem_full[group], use & 1);
+      SAST_STAMP(trc, quarter == 0 && lane == 0 && ti < 8, 48 + 4 * ti);
       ptx::tc_fence_after();
       float l1[8];
 #pragma unroll
@@ -244,6 +255,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
         }
         __syncwarp();
       }
+      SAST_STAMP(trc, quarter == 0 && lane == 0 && ti < 8, 49 + 4 * ti);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&sm->tmem_empty[group]);
@@ -265,6 +277,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, tmem_cols);
   }
+  SAST_STAMP(trc, threadIdx.x == 0, 2);
 }
 
 int make_tmap_f32_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows);
@@ -295,7 +308,7 @@ int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv
   const long long tiles = ((P + SC_BM - 1) / SC_BM) * (C / BN);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   sast::launch_k(score_tc_kernel, grid, SC_THREADS, smem, st, mh, ml, a->x, a->pos, a->pos_batch_stride, a->score_b, sig, inv, g.H * g.W, C, BN, P,
-                                                  a->xw, l1_part);
+                                                  a->xw, l1_part, g_trace_which == 3 ? g_trace : nullptr);
   SAST_LAUNCH_CHECK();
   *n_slices = C / BN;
   return SAST_OK;

@@ -13,39 +13,71 @@ sys.path.insert(0, ROOT)
 from sast_b200 import _lib as L  # noqa: E402
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "glu"
-M, N, K = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (122880, 320 if kind == "glu" else 192, 64)
-dev = torch.device("cuda:0")
-lib = L.lib()
-st = L.stream_ptr(dev)
-A = torch.randn(M, K, device=dev).to(torch.bfloat16)
-W = (torch.randn(N, K, device=dev) / 8).to(torch.bfloat16)
-bias = torch.randn(N, device=dev)
-D = torch.empty(M, N // 2 if kind == "glu" else N, device=dev, dtype=torch.bfloat16)
+if kind == "score":          # scoring kernel at the stage-1 shape of the 1 Mpx B=8 workload (same stamp layout)
+    import sast_b200
+    from sast_b200 import ops
+    from sast_b200.config import backbone_config
+    dev = torch.device("cuda:0")
+    stage = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    net = sast_b200.build_recurrent_backbone(backbone_config((384, 640))).to(dev).eval()
+    blk = net.stages[stage - 1].att_blocks[0].att
+    B, C = 8, 64 << (stage - 1)
+    H, W = 96 >> (stage - 1), 160 >> (stage - 1)
+    x = torch.randn(B, H, W, C, device=dev)
+    pos = torch.randn(H, W, C, device=dev)
+    r = torch.rand(B, 20, device=dev)
+    with torch.no_grad():
+        hi, lo = ops.split_tf32(blk.to_scores.weight)
+        run = lambda: ops.score_fwd(x, pos, r, blk.to_controls.weight, blk.to_scores.weight, blk.to_scores.bias, 2e-4, hi, lo)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        buf = torch.zeros(148 * 128, dtype=torch.int64, device=dev)
+        torch.empty(256 << 20, dtype=torch.uint8, device=dev).zero_()
+        L.lib().sast_debug_trace(buf.data_ptr(), 3)
+        run()
+        torch.cuda.synchronize()
+        L.lib().sast_debug_trace(None, 0)
+    t = buf.view(148, 128).cpu()
+    t = t[t[:, 0] != 0]
+    print(f"score_tc stage {stage} [{B * H * W} x {C} x {C}]; CTAs traced {len(t)}")
+
+else:
+    M, N, K = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (122880, 320 if kind == "glu" else 192, 64)
+    dev = torch.device("cuda:0")
+    lib = L.lib()
+    st = L.stream_ptr(dev)
+    A = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=dev) / 8).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    D = torch.empty(M, N // 2 if kind == "glu" else N, device=dev, dtype=torch.bfloat16)
 
 
-def run():
-    if kind == "glu":
-        L.check(lib.sast_gemm_bf16_glu(A.data_ptr(), W.data_ptr(), bias.data_ptr(), D.data_ptr(), M, N, K, st), "glu")
-    else:
-        L.check(lib.sast_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), D.data_ptr(), 1, M, N, K, st), "gemm")
+    def run():
+        if kind == "glu":
+            L.check(lib.sast_gemm_bf16_glu(A.data_ptr(), W.data_ptr(), bias.data_ptr(), D.data_ptr(), M, N, K, st), "glu")
+        else:
+            L.check(lib.sast_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), D.data_ptr(), 1, M, N, K, st), "gemm")
 
 
-for _ in range(3):
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    buf = torch.zeros(148 * 128, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush.zero_()
+    lib.sast_debug_trace(buf.data_ptr(), 2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     run()
-torch.cuda.synchronize()
-buf = torch.zeros(148 * 128, dtype=torch.int64, device=dev)
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-flush.zero_()
-lib.sast_debug_trace(buf.data_ptr(), 2)
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-run()
-e1.record()
-torch.cuda.synchronize()
-lib.sast_debug_trace(None, 0)
-t = buf.view(148, 128).cpu()
-t = t[t[:, 0] != 0]
-print(f"{kind} GEMM [{M},{N},{K}]: {e0.elapsed_time(e1) * 1e3:.1f} us with stamps; CTAs traced {len(t)}")
+    e1.record()
+    torch.cuda.synchronize()
+    lib.sast_debug_trace(None, 0)
+    t = buf.view(148, 128).cpu()
+    t = t[t[:, 0] != 0]
+    print(f"{kind} GEMM [{M},{N},{K}]: {e0.elapsed_time(e1) * 1e3:.1f} us with stamps; CTAs traced {len(t)}")
+
+
 
 
 def med(col):
