@@ -8,7 +8,10 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ.setdefault("SAST_B200_LIB", os.path.join(ROOT, "sast_b200", "libsast_b200_trace.so"))   # `make -C sast_b200/csrc trace`
+os.environ.setdefault("SAST_B200_LIB", os.path.join(ROOT, "sast_b200", "libsast_b200_trace.so"))
+if not os.path.exists(os.environ["SAST_B200_LIB"]):          # the instrumented twin is not part of the default build
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "sast_b200", "csrc"), "trace"])
 sys.path.insert(0, ROOT)
 import sast_b200  # noqa: E402
 from sast_b200 import _lib as L, ops  # noqa: E402
