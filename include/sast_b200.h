@@ -255,9 +255,9 @@ int sast_gemm_bf16_glu(const uint16_t* A, const uint16_t* W, const float* bias, 
 
 /* Debug aid (tools/attn_trace.py, tools/gemm_trace.py): while buf is non-null, launches of the tensor-core
  * attention and GEMM kernels write thread-level clock64 stamps of their phase boundaries into buf
- * (attention: [CTA][16], GEMM: [CTA][128] int64; last slot = SM id).  Pass NULL to switch it off (the default).
+ * (attention: [CTA][16], GEMM and scoring: [CTA][128] int64; last slot = SM id).  Pass NULL to switch it off (the default).
  * Only the instrumented build (`make -C sast_b200/csrc trace`) stamps; the regular library ignores the call. */
-void sast_debug_trace(long long* buf, int32_t which /* 1 attention, 2 GEMM */);
+void sast_debug_trace(long long* buf, int32_t which /* 1 attention, 2 GEMM, 3 scoring */);
 
 /* Library / build info. */
 int sast_abi_version(void);

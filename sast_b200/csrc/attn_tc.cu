@@ -1,24 +1,28 @@
 // Attention over the compacted rows on the 5th-gen tensor cores (SAST_BF16 path):
 // per attention tile (consecutive selected windows of one frame, <= 128 compacted rows, packed
 // by select_scan_kernel) and head:  S = Q K^T (tcgen05, fp32 in TMEM) -> block-diagonal softmax
-// (a row only sees the keys of its own window) -> P (bf16, shared memory) -> O = P V (tcgen05)
-// -> O / rowsum -> bf16.                                                (replaces SAST.py:219-229)
+// (a row only sees the keys of its own window) -> P (bf16, shared memory) -> O = P V and the row sums
+// P 1 (tcgen05) -> O / rowsum -> bf16.                                  (replaces SAST.py:219-229)
 //
 // The compacted buffer holds selected tokens only, so the reference's -1e4 column mask for
 // padding (SAST.py:223-226) has no counterpart: the only mask is "same window".
 //
-// CTA = 256 threads, two threads per tile row (= TMEM lane), each on half of the key columns.  Thread 0 issues TMA and MMA.
-// 128 TMEM columns and 42 KB of shared memory per CTA -> 4 CTAs per SM hide each other's
-// load -> MMA -> softmax -> MMA latency chain.
+// CTA = 256 threads, two threads per tile row (= TMEM lane), each on half of the key columns.  Warp 0 issues TMA
+// and MMA through an elected lane and is the only one polling mbarriers; the others block in bar.sync.
+// 128 TMEM columns and 44 KB of shared memory per CTA -> 4 CTAs per SM hide each other's
+// load -> MMA -> softmax -> MMA latency chain.  The grid is tile-major over the per-frame tile slot lists
+// (blockIdx.x = slot * B + frame), so the CTAs of unused slots are launched last and exit at once.
 //   Q,K,V tiles [128 x 32] bf16: TMA boxes out of the qkv buffer ([rows, 3C], head-major
 //   [h][q,k,v][32]) in SWIZZLE_64B; Q,K are K-major operands, V is the MN-major B operand of PV.
 //   P [128 x 128] bf16 is written by the softmax threads in the SWIZZLE_128B K-major layout.
+//   A 1 KB tile of bf16 ones is the B operand of a second product into TMEM columns 32..47: the row sums of
+//   the bf16-rounded P, for free (the softmax loop is instruction bound).
 #include "layer.cuh"
 #include "ptx.cuh"
 
 namespace sast {
 
-constexpr uint32_t AT_TMEM_COLS = 128;     // S: columns [0,128); O re-uses columns [0,32) once S has been consumed
+constexpr uint32_t AT_TMEM_COLS = 128;     // S: columns [0,128); O re-uses [0,32) and the row sums [32,48) once S has been consumed
 constexpr int AT_TILE = 8192;              // one 128 x 32 bf16 operand tile
 
 struct AttnSmem {
@@ -397,7 +401,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
-  // enough CTAs to fill the chip: all heads in one CTA when there are many tiles, one head per CTA otherwise
+  // enough CTAs to fill the chip (4 per SM): all heads in one CTA when there are many tile slots, fewer otherwise
   int hpc = heads;
   while (hpc > 1 && (long long)NW * (heads / hpc) < 4 * 148 && hpc % 2 == 0) hpc /= 2;
   sast::launch_k(attention_tc_kernel, dim3(NW, heads / hpc), 256, smem, st, mq, att, C, hpc, sel.tiles, sel.win_row0, B, g_trace_which == 1 ? g_trace : nullptr);

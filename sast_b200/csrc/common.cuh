@@ -120,25 +120,7 @@ __device__ __forceinline__ int warp_max_i(int v) {
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// erf-GELU for the tensor-core epilogue: erf by Abramowitz-Stegun 7.1.26 (absolute error <= 1.5e-7, far
-// below the bf16 output rounding) -- one MUFU.RCP, one MUFU.EX2 and a degree-5 Horner instead of erff.
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  float ex;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z * 1.44269504088896340736f));
-  const float e = 1.0f - p * t * ex;                                          // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
-}
-// Cheaper still, for epilogues that are instruction-issue bound (the GLU GEMM): erf(x/sqrt2) ~= tanh(x (a + b x^2)),
-// a minimax fit over all x (|gelu error| <= 2.7e-4 from the fit + |x| 2.4e-4 from tanh.approx's 2^-11 relative
-// error; the bf16 rounding of the result is 2e-3 relative).  Both coefficients are positive, so the argument is
-// monotone and needs no clamp.  glu_tanh_fit returns value * gelu(x) in 6 instructions + ONE MUFU, with the 0.5 of
-// the GELU folded into the caller's bias add of the value branch (pass half_value = 0.5 * value).
+// single-MUFU transcendentals of the tensor-core epilogues (relative error 2^-11, below the bf16 / TF32 noise there)
 __device__ __forceinline__ float tanh_fast(float x) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
@@ -146,6 +128,11 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 // sigmoid through the same single MUFU: 1/(1+e^-x) = 0.5 + 0.5 tanh(x/2)   (absolute error <= 2.5e-4)
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// GELU of the tensor-core GLU epilogue, which is instruction-issue bound: erf(x/sqrt2) ~= tanh(x (a + b x^2)),
+// a minimax fit over all x (|gelu error| <= 2.7e-4 from the fit + |x| 2.4e-4 from tanh.approx's 2^-11 relative
+// error; the bf16 rounding of the result is 2e-3 relative).  Both coefficients are positive, so the argument is
+// monotone and needs no clamp.  glu_tanh_fit returns value * gelu(x) in 6 instructions + ONE MUFU, with the 0.5 of
+// the GELU folded into the caller's bias add of the value branch (pass half_value = 0.5 * value).
 __device__ __forceinline__ float glu_tanh_fit(float half_value, float x) {
   const float p = fmaf(3.470089e-2f, x * x, 8.0015708e-1f);
   const float t = tanh_fast(x * p);
@@ -153,7 +140,7 @@ __device__ __forceinline__ float glu_tanh_fit(float half_value, float x) {
 }
 
 extern long long* g_trace;   // api.cu; null unless sast_debug_trace armed it
-extern int g_trace_which;    // 1: attention kernels stamp, 2: GEMM kernels stamp
+extern int g_trace_which;    // 1: attention kernels stamp, 2: GEMM kernels, 3: scoring kernel
 
 // Phase stamps for tools/attn_trace.py / tools/gemm_trace.py.  Compiled in only with -DSAST_TRACE (`make trace` ->
 // libsast_b200_trace.so): even predicated-off stamps cost the GLU GEMM ~10 % through register allocation.

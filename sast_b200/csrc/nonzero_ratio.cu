@@ -1,7 +1,7 @@
 // a1: scene sparsity ratio r  (replaces sast_rnn.py:45-60 non_zero_ratio).
 //
-// The planes are cut in bands of 32 pixel rows (= 8 rows
-// of 4x4 level-0 cells = one row of level-3 cells): every thread max-reduces 4x4 cells with
+// The planes are cut in bands of 32 pixel rows (= 8 rows of 4x4 level-0 cells = one row of level-3 cells),
+// one CTA per (plane, band): every thread max-reduces 4x4 cells with
 // 128-bit / 32-bit row loads (coalesced: neighbouring threads own neighbouring cells), the
 // level-0 maxima go to shared memory and levels 1..3 (8x8, 16x16, 32x32 pixels) are
 // max-reduced from there.  "Cell != 0" is counted per level exactly like the cascaded

@@ -8,13 +8,16 @@
 //
 // Persistent CTAs, 13 warps:
 //   warps 0-3  loaders: x + pos formed on the fly (coalesced float4 rows), split into hi/lo and written
-//              to shared memory in the SWIZZLE_128B K-major operand layout; lane 0 also TMA-loads the
-//              pre-split weight tiles (W_hi, W_lo: [C,C] fp32, K-major like nn.Linear.weight)
-//   warps 4-11 epilogue, two groups of 4 (one TMEM accumulator each, tiles round-robin): TMEM ->
-//              shared-memory transpose -> coalesced rows: STP-weighted map xw = sigmoid(ctrl) sigmoid(s) x0
-//              and the per-token L1  sum_c |amp/ctrl_c s_c|.  The epilogue is the long pole (a sigmoid and
-//              ~20 flops per output), hence 8 of the 13 warps.
-//   warp 12    TMEM allocator + MMA issuer
+//              to shared memory in the SWIZZLE_128B K-major operand layout; an elected lane of warp 0 also
+//              TMA-loads the pre-split weight tiles (W_hi, W_lo: [C,C] fp32, K-major like nn.Linear.weight)
+//   warps 4-11 epilogue, two groups of 4 (one TMEM accumulator each, tiles round-robin): TMEM -> swizzled
+//              128-bit shared-memory transpose -> coalesced rows: STP-weighted map xw = sigmoid(ctrl) sigmoid(s) x0
+//              and the per-token L1  sum_c |amp/ctrl_c s_c|; every global load of a 32-column chunk is issued
+//              before anything waits on it.
+//   warp 12    TMEM allocator + MMA issuer (whole warp on uniform values, elected lane issues)
+// Measured (tools/gemm_trace.py score): loaders and epilogue each need 7-8 k clk per 128-row tile, the MMAs ~0.8 k;
+// with only two ring stages the loaders pay one DRAM round trip per k-block.  A deeper ring plus prefetching
+// loaders is the next step (tried with 17 warps: the 96-register budget then starved the epilogue).
 #include "common.cuh"
 #include "ptx.cuh"
 

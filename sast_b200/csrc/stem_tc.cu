@@ -3,7 +3,7 @@
 //   uint8 event histogram [B,Cin,H,W] (NCHW)  ->  LayerNorm(conv(x)) as fp32 NHWC [B,H/4,W/4,64].
 //
 // Implicit GEMM on tcgen05: M = output pixels (128 per tile), N = Cout, K ordered (c, ky, kx) with kx padded
-// 7 -> 8 so that one (c, ky) group is 8 consecutive input bytes = one 16-byte bf16 chunk of the A operand.
+// 7 -> 8 so that one (c, ky) group is 8 consecutive input bytes = one 16-byte fp16 chunk of the A operand.
 // Event counts are small integers: exact in fp16.  The fp32 weights are split w = w_hi + w_lo (both fp16,
 // |w - w_hi - w_lo| <= ~2^-22 |w| for the weight magnitudes of a conv layer) and both halves are multiplied, so
 // the result is fp32-grade (tighter than the TF32 path cuDNN takes by default) at 16-bit tensor-core speed.
@@ -11,8 +11,8 @@
 // Persistent CTAs, 14 warps:
 //   warps 0-7   A producers: two threads per output pixel, four (c,ky) groups each per k-block: three coalesced
 //               32-bit loads (L1-resident input rows) -> 8 bytes -> 8 fp16 -> one STS.128 into the SWIZZLE_128B tile;
-//               thread 0 also TMA-loads the packed weight tiles
-//   warp 8      TMEM allocator + MMA issuer (two accumulators)
+//               an elected lane of warp 0 also TMA-loads the packed weight tiles
+//   warp 8      TMEM allocator + MMA issuer (whole warp on uniform values, elected lane issues; two accumulators)
 //   warp 9      idle (keeps the epilogue warps on TMEM lane quarters 2,3,0,1)
 //   warps 10-13 epilogue: LayerNorm over the Cout channels of each pixel straight from TMEM, swizzled
 //               shared-memory transpose, dense 128-byte row stores
