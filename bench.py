@@ -36,10 +36,17 @@ WORKLOADS = {
 METRIC = "SAST frames/s @1Mpx 384x640 (backbone forward, benchmark.py protocol)"
 
 
-def make_inputs(batch, res, sparsity, n_buffers, seed=1):
+def make_inputs(batch, res, sparsity, n_buffers, seed=1, kind="binary"):
     """benchmark.py:58-60: (rand(B,20,H,W) > sparsity) as integers; uint8 here (the dataset's
-    own dtype, data/utils/representations.py) so a host->device copy moves 1 byte per bin."""
+    own dtype, data/utils/representations.py) so a host->device copy moves 1 byte per bin.
+    kind "poisson": event-count histograms clipped at 10 (count_cutoff of the dataset configs) with a fraction
+    1 - sparsity of non-empty bins -- the 'realistic' variant of BASELINE config 2."""
     g = torch.Generator().manual_seed(seed)
+    if kind == "poisson":
+        import math
+        lam = -math.log(max(min(sparsity, 1.0 - 1e-9), 1e-9))           # P(count > 0) = 1 - sparsity
+        rate = torch.full((batch, 20, res[0], res[1]), lam)
+        return [torch.poisson(rate, generator=g).clamp_(max=10).to(torch.uint8) for _ in range(n_buffers)]
     return [(torch.rand(batch, 20, res[0], res[1], generator=g) > sparsity).to(torch.uint8) for _ in range(n_buffers)]
 
 
@@ -106,7 +113,7 @@ def oracle_cfg(workload):
                 in_res_hw=list(workload["res"]), partition_size=[workload["res"][0] // mult, workload["res"][1] // mult])
 
 
-def cpu_baseline(workload, sparsity, frames, iters, warm, state_dict=None):
+def cpu_baseline(workload, sparsity, frames, iters, warm, state_dict=None, kind="binary"):
     """Times oracle.backbone_forward (test infrastructure standing in for the reference's CPU
     path: same torch-CPU ops in the same order) on `frames` frames with all host threads."""
     from oracle import sast_oracle as O
@@ -118,7 +125,7 @@ def cpu_baseline(workload, sparsity, frames, iters, warm, state_dict=None):
                                                                  partition_split_32=workload["split"]))
         state_dict = {k: v.detach() for k, v in net.state_dict().items()}
     cfg = oracle_cfg(workload)
-    x = make_inputs(frames, workload["res"], sparsity, 1)[0].int()      # benchmark.py feeds .int()
+    x = make_inputs(frames, workload["res"], sparsity, 1, kind=kind)[0].int()      # benchmark.py feeds .int()
     with torch.no_grad():
         for _ in range(warm):
             O.backbone_forward(x, None, state_dict, cfg)
@@ -136,7 +143,7 @@ def run_reference(args, workload):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     frames = workload["batch"]
-    fps, dt, counts = cpu_baseline(workload, args.sparsity, frames, max(args.steps, 1), max(args.warmup, 1))
+    fps, dt, counts = cpu_baseline(workload, args.sparsity, frames, max(args.steps, 1), max(args.warmup, 1), kind=args.input)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -182,7 +189,7 @@ def run_ours(args, workload):
     seq = workload.get("seq", 1)                    # frames per stream and step (1: benchmark.py protocol; 21: streaming)
     net = build_net(workload, args.precision, device)
     n_buf = 4
-    host = [t.pin_memory() for t in make_inputs(B, res, args.sparsity, n_buf, seed=1 + rank)]   # every rank: its own frames
+    host = [t.pin_memory() for t in make_inputs(B, res, args.sparsity, n_buf, seed=1 + rank, kind=args.input)]   # every rank: its own frames
     dev_in = [t.to(device) for t in host]
     lib = L.lib()
 
@@ -283,7 +290,7 @@ def run_ours(args, workload):
             threads = os.cpu_count() or 1
             torch.set_num_threads(threads)
             sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-            fps_cpu, dt_cpu, _ = cpu_baseline(workload, args.sparsity, B, 3, 1, sd)
+            fps_cpu, dt_cpu, _ = cpu_baseline(workload, args.sparsity, B, 3, 1, sd, kind=args.input)
             cpu = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{B} frames x 3 timed iterations (1 warm-up) of the same workload, oracle port of the "
                              f"reference PyTorch CPU path, fp32, {dt_cpu * 1e3:.0f} ms per iteration"}
@@ -294,7 +301,7 @@ def run_ours(args, workload):
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": workload["desc"], "batch_per_gpu": B, "global_batch": B * world,
                        "frames_per_step_per_gpu": B * seq, "sparsity": args.sparsity,
-                       "input": "uint8 (rand > sparsity), benchmark.py:58-60",
+                       "input": "uint8 (rand > sparsity), benchmark.py:58-60" if args.input == "binary" else "uint8 Poisson counts clipped at 10, 1 - sparsity of the bins non-empty",
                        "selected_tokens_per_stage": counts, "cuda_graph": not args.no_graph,
                        "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": f"inputs rotate over {n_buf} buffers; per-step working set (activations + workspaces) exceeds the 126 MB L2"},
@@ -321,6 +328,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1mpx_b8", choices=sorted(WORKLOADS))
     ap.add_argument("--sparsity", type=float, default=0.0, help="benchmark.py default 0.0 (every pixel active)")
+    ap.add_argument("--input", default="binary", choices=["binary", "poisson"],
+                    help="binary: (rand > sparsity) as benchmark.py does; poisson: event counts clipped at 10, 1 - sparsity non-empty")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
