@@ -28,7 +28,7 @@ from models.layers.SAST import ops as ref_ops  # noqa: E402
 from models.detection.recurrent_backbone import build_recurrent_backbone  # noqa: E402
 from models.detection.recurrent_backbone import sast_rnn as ref_rnn  # noqa: E402
 
-from oracle.golden_common import (canonical_keys, event_histogram, make_params,  # noqa: E402
+from oracle.golden_common import (canonical_keys, event_histogram, make_det_params, make_params,  # noqa: E402
                                   with_aliases)
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -207,6 +207,86 @@ def gen_backbone():
         print("   ", name, "P", p0, p1)
 
 
+def pick_conf(out, ncls):
+    """Confidence threshold that lets ~15 % of the anchors through (random weights have no meaningful score scale),
+    placed in the middle of a gap between two neighbouring scores so that rounding noise cannot move an anchor across it."""
+    score = (out[..., 4] * out[..., 5:5 + ncls].max(-1)[0]).flatten().sort()[0]
+    i = int(0.85 * score.numel())
+    gaps = score[i + 1:i + 40] - score[i:i + 39]
+    j = int(gaps.argmax())
+    return float((score[i + j] + score[i + j + 1]) / 2)
+
+
+def gen_yolox():
+    """YOLOX PAFPN + head + postprocess on fixed features (ref: yolo_pafpn.py:109-139, yolo_head.py:165-289,
+    boxes.py:32-76), and the whole detector on two recurrent steps (ref: detector.py:34-58)."""
+    from models.detection.yolox_extension.models.build import build_yolox_fpn, build_yolox_head
+    from models.detection.yolox.utils.boxes import postprocess
+
+    # ---- neck + head on given features (Gen1 geometry: strides 8/16/32 of 256x320), with and without depthwise convs ----
+    for name, depthwise, depth in (("yolox_head_gen1", False, 0.67), ("yolox_head_dw", True, 0.33)):
+        dims, strides, ncls, B = (64, 128, 256), (8, 16, 32), 2, 2
+        fpn = build_yolox_fpn(DictConfig(dict(name="PAFPN", depth=depth, in_stages=[2, 3, 4], depthwise=depthwise, act="silu")),
+                              in_channels=dims).eval()
+        head = build_yolox_head(DictConfig(dict(name="YoloX", depthwise=depthwise, act="silu", num_classes=ncls)),
+                                in_channels=dims, strides=strides).eval()
+        shapes_f = {k: tuple(v.shape) for k, v in fpn.state_dict().items()}
+        shapes_h = {k: tuple(v.shape) for k, v in head.state_dict().items()}
+        fpn.load_state_dict(make_det_params(shapes_f, seed=21), strict=True)
+        head.load_state_dict(make_det_params(shapes_h, seed=22), strict=True)
+        rng = np.random.RandomState(23)
+        feats = {st: torch.from_numpy(rng.standard_normal((B, c, 256 // s, 320 // s)).astype(np.float32))
+                 for st, c, s in zip((2, 3, 4), dims, strides)}
+        with torch.no_grad():
+            fo = fpn(feats)
+            out, losses = head(fo)
+            assert losses is None
+            conf = pick_conf(out, ncls)
+            dets = postprocess(out.clone(), ncls, conf_thre=conf, nms_thre=0.45)
+        arrays = dict(out=out, fpn0=fo[0][:, ::4], fpn2=fo[2][:, ::8])
+        for i, d in enumerate(dets):
+            arrays[f"det{i}"] = d if d is not None else torch.zeros(0, 7)
+        meta = dict(dims=list(dims), strides=list(strides), num_classes=ncls, B=B, depthwise=depthwise, depth=depth,
+                    seeds=[21, 22, 23], conf_thre=conf, nms_thre=0.45,
+                    shapes_fpn={k: list(v) for k, v in shapes_f.items()}, shapes_head={k: list(v) for k, v in shapes_h.items()})
+        save(name, meta=json.dumps(meta), **arrays)
+        print("   ", name, "anchors", out.shape[1], "detections", [len(arrays[f"det{i}"]) for i in range(B)])
+
+    # ---- whole detector: backbone (embed 32) + neck + head, two recurrent steps ----
+    embed, res, part, ncls, B = 32, (192, 320), (3, 5), 3, 2
+    cfg = backbone_cfg(embed, res, part, AMP=2e-4)
+    net = build_recurrent_backbone(cfg).eval()
+    dims, strides = net.get_stage_dims((2, 3, 4)), net.get_strides((2, 3, 4))
+    fpn = build_yolox_fpn(DictConfig(dict(name="PAFPN", depth=0.67, in_stages=[2, 3, 4], depthwise=False, act="silu")),
+                          in_channels=dims).eval()
+    head = build_yolox_head(DictConfig(dict(name="YoloX", depthwise=False, act="silu", num_classes=ncls)),
+                            in_channels=dims, strides=strides).eval()
+    sd = net.state_dict()
+    shapes = canonical_keys(sd)
+    net.load_state_dict(with_aliases(make_params(shapes, seed=77), sd.keys()), strict=True)
+    shapes_f = {k: tuple(v.shape) for k, v in fpn.state_dict().items()}
+    shapes_h = {k: tuple(v.shape) for k, v in head.state_dict().items()}
+    fpn.load_state_dict(make_det_params(shapes_f, seed=31), strict=True)
+    head.load_state_dict(make_det_params(shapes_h, seed=32), strict=True)
+    x0 = event_histogram(B, 20, res[0], res[1], 0.02, seed=5)
+    x1 = event_histogram(B, 20, res[0], res[1], 0.004, seed=6)
+    with torch.no_grad():
+        f0, s0, p0 = net(x0, None, None)
+        f1, s1, p1 = net(x1, s0, None)
+        out, _ = head(fpn(f1))
+        conf = pick_conf(out, ncls)
+        dets = postprocess(out.clone(), ncls, conf_thre=conf, nms_thre=0.45)
+    arrays = dict(out=out, P1=np.array(p1, dtype=np.int64))
+    for i, d in enumerate(dets):
+        arrays[f"det{i}"] = d if d is not None else torch.zeros(0, 7)
+    meta = dict(embed_dim=embed, in_res_hw=list(res), partition_size=list(part), num_classes=ncls, B=B, AMP=2e-4,
+                seeds=dict(backbone=77, fpn=31, head=32), x_seeds=[5, 6], x_density=[0.02, 0.004], conf_thre=conf, nms_thre=0.45,
+                shapes={k: list(v) for k, v in shapes.items()}, all_keys=sorted(sd.keys()),
+                shapes_fpn={k: list(v) for k, v in shapes_f.items()}, shapes_head={k: list(v) for k, v in shapes_h.items()})
+    save("detector_e32", meta=json.dumps(meta), **arrays)
+    print("    detector_e32 anchors", out.shape[1], "detections", [len(arrays[f"det{i}"]) for i in range(B)], "P", p1)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -219,6 +299,7 @@ def main():
     run_block("block_c64_dense", 64, (6, 10), 2, 12, 20, amp=2e-4, seed=4, r_scale=1.0)
     run_block("block_c256_w3x5", 256, (3, 5), 2, 6, 10, amp=2e-3, seed=5, r_scale=0.02)
     gen_backbone()
+    gen_yolox()
 
 
 if __name__ == "__main__":

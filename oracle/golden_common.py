@@ -41,6 +41,38 @@ def make_params(shapes: Dict[str, Sequence[int]], seed: int, gamma: float = 0.5)
     return out
 
 
+def make_det_params(shapes: Dict[str, Sequence[int]], seed: int) -> Dict[str, torch.Tensor]:
+    """Parameters and BatchNorm statistics of the YOLOX neck / head from ``numpy.random.RandomState(seed)``:
+    conv weights with a gain that keeps activations O(1) through ~20 layers, BN scale around 1, positive
+    running variances, predictor biases around 0 (so that post-processing sees a few hundred candidates)."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    for key in sorted(shapes):
+        shape = tuple(shapes[key])
+        leaf = key.split(".")[-1]
+        parent = key.split(".")[-2] if "." in key else ""
+        if leaf == "num_batches_tracked":
+            out[key] = torch.zeros(shape, dtype=torch.int64)
+            continue
+        z = rng.standard_normal(shape).astype(np.float32)
+        if parent == "bn" and leaf == "weight":
+            val = 1.0 + 0.1 * z
+        elif parent == "bn" and leaf == "bias":
+            val = 0.1 * z
+        elif leaf == "running_mean":
+            val = 0.1 * z
+        elif leaf == "running_var":
+            val = 0.6 + 0.4 * np.abs(z)
+        elif leaf == "bias":
+            val = 0.5 * z
+        else:
+            fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
+            gain = 0.3 if "_preds." in key else 1.4          # predictors: box regressions of O(1) before the exp
+            val = gain * z / np.sqrt(fan_in)
+        out[key] = torch.from_numpy(np.ascontiguousarray(val, dtype=np.float32))
+    return out
+
+
 def canonical_keys(state_dict) -> Dict[str, Tuple[int, ...]]:
     """Shapes of the state dict without the ``sub_layers.*`` aliases."""
     return {k: tuple(v.shape) for k, v in state_dict.items() if ".sub_layers." not in k}
