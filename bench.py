@@ -6,8 +6,8 @@ A *step* is one backbone forward (``benchmark.py:51-64`` protocol: ``forward_bac
 Default workload: 1 Mpx, B=8, 384x640 (BASELINE.json configs[1]).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (this repo)
-  python bench.py --impl reference ...                           # CPU arm: the oracle port of the
-                                                                 # reference PyTorch path, host cores
+  python bench.py --impl reference ...                           # CPU arm: the unmodified reference (baseline/_ref)
+                                                                 # on the host cores; --device cuda: eager on the GPU
 
 N>1: launched by torchrun, one rank per GPU; frames are sharded by batch (B per rank, weak
 scaling, no collective on the data path); time = max over ranks.
@@ -105,7 +105,9 @@ def build_net(workload, precision, device):
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's PyTorch path
+# Reference arm: the UNMODIFIED reference from baseline/_ref (staged by baseline/make_ref.py; git-ignored, ships with
+# the gpurun snapshot) through its own public API, build_recurrent_backbone(cfg).forward, in the timing loop of
+# benchmark.py:33-42.  If baseline/_ref is absent the oracle port (same torch ops in the same order) stands in.
 # ----------------------------------------------------------------------------------------------
 def oracle_cfg(workload):
     mult = 32 * workload["split"]
@@ -113,27 +115,79 @@ def oracle_cfg(workload):
                 in_res_hw=list(workload["res"]), partition_size=[workload["res"][0] // mult, workload["res"][1] // mult])
 
 
-def cpu_baseline(workload, sparsity, frames, iters, warm, state_dict=None, kind="binary"):
-    """Times oracle.backbone_forward (test infrastructure standing in for the reference's CPU
-    path: same torch-CPU ops in the same order) on `frames` frames with all host threads."""
-    from oracle import sast_oracle as O
+def load_reference():
+    """(DictConfig, build_recurrent_backbone) of the staged reference, or None."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "models")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from omegaconf import DictConfig                                             # the stand-in staged next to it
+    from models.detection.recurrent_backbone import build_recurrent_backbone    # reference code, unmodified
+    return DictConfig, build_recurrent_backbone
+
+
+def reference_backbone(workload, state_dict):
+    """The reference's RNNDetector for this workload (config/model/sast_yolox/default.yaml + experiment/*/base.yaml
+    as config/modifier.py resolves them), carrying `state_dict` (ours: the state-dict layouts are identical)."""
+    DictConfig, build = load_reference()
+    mult = 32 * workload["split"]
+    part = [workload["res"][0] // mult, workload["res"][1] // mult]
+    att = dict(partition_size=part, dim_head=32, attention_bias=True, mlp_activation="gelu", mlp_bias=True, mlp_ratio=4,
+               drop_mlp=0, drop_path=0, ls_init_value=1e-5, enable_CB=False, AMP=2e-4, BOUNCE=1e-3)
+    cfg = DictConfig(dict(
+        name="SASTRNN", input_channels=20, enable_masking=False, partition_split_32=workload["split"], embed_dim=64,
+        dim_multiplier=[1, 2, 4, 8], num_blocks=[1, 1, 1, 1], T_max_chrono_init=[4, 8, 16, 32], stem=dict(patch_size=4),
+        in_res_hw=list(workload["res"]),
+        stage=dict(downsample=dict(type="patch", overlap=True, norm_affine=True), attention=att,
+                   lstm=dict(dws_conv=False, dws_conv_only_hidden=True, dws_conv_kernel_size=3, drop_cell_update=0))))
+    net = build(cfg).eval()
+    net.load_state_dict(state_dict, strict=True)
+    return net
+
+
+def our_state_dict(workload):
+    import sast_b200
+    from sast_b200.config import backbone_config
+    torch.manual_seed(0)
+    net = sast_b200.build_recurrent_backbone(backbone_config(workload["res"], embed_dim=64,
+                                                             partition_split_32=workload["split"]))
+    return {k: v.detach() for k, v in net.state_dict().items()}
+
+
+def cpu_baseline(workload, sparsity, frames, iters, warm, state_dict=None, kind="binary", device="cpu"):
+    """frames/s of the reference path on `frames` frames per iteration (benchmark.py:33-42 loop: warm-up, sync,
+    timed iterations, sync).  Returns (fps, seconds per iteration, selected tokens per stage, kind)."""
     if state_dict is None:
-        import sast_b200
-        from sast_b200.config import backbone_config
-        torch.manual_seed(0)
-        net = sast_b200.build_recurrent_backbone(backbone_config(workload["res"], embed_dim=64,
-                                                                 partition_split_32=workload["split"]))
-        state_dict = {k: v.detach() for k, v in net.state_dict().items()}
-    cfg = oracle_cfg(workload)
+        state_dict = our_state_dict(workload)
     x = make_inputs(frames, workload["res"], sparsity, 1, kind=kind)[0].int()      # benchmark.py feeds .int()
+    if load_reference() is not None:
+        net = reference_backbone(workload, state_dict).to(device)
+        x = x.to(device)
+        fwd = lambda: net(x, None, None)                                          # noqa: E731
+        which = "reference"
+    else:
+        if device != "cpu":
+            raise SystemExit("bench.py --impl reference --device cuda needs baseline/_ref (python baseline/make_ref.py)")
+        from oracle import sast_oracle as O
+        cfg = oracle_cfg(workload)
+        fwd = lambda: O.backbone_forward(x, None, state_dict, cfg)                # noqa: E731
+        which = "port"
+
+    def sync():
+        if device != "cpu":
+            torch.cuda.synchronize()
+
     with torch.no_grad():
         for _ in range(warm):
-            O.backbone_forward(x, None, state_dict, cfg)
+            fwd()
+        sync()
         t0 = time.perf_counter()
         for _ in range(iters):
-            _, _, counts = O.backbone_forward(x, None, state_dict, cfg)
+            counts = fwd()[2]
+        sync()
         dt = (time.perf_counter() - t0) / iters
-    return frames / dt, dt, counts
+    return frames / dt, dt, [int(c) for c in counts], which
 
 
 def run_reference(args, workload):
@@ -143,15 +197,20 @@ def run_reference(args, workload):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     frames = workload["batch"]
-    fps, dt, counts = cpu_baseline(workload, args.sparsity, frames, max(args.steps, 1), max(args.warmup, 1), kind=args.input)
+    dev = args.device
+    fps, dt, counts, which = cpu_baseline(workload, args.sparsity, frames, max(args.steps, 1), max(args.warmup, 1),
+                                          kind=args.input, device=dev)
+    what = ("unmodified reference (baseline/_ref) build_recurrent_backbone(cfg).forward" if which == "reference"
+            else "oracle port of the reference PyTorch path")
+    where = f"torch CPU fp32, {torch.get_num_threads()} threads" if dev == "cpu" else "stock PyTorch eager on the GPU, fp32 (TF32 off)"
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "f32", "data": "synthetic", "device": dev,
         "config": {"workload": args.workload, "desc": workload["desc"], "batch_per_step": frames, "sparsity": args.sparsity,
-                   "selected_tokens_per_stage": [int(c) for c in counts]},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{frames} frames per step (full batch), oracle port of the reference PyTorch CPU path, fp32"},
+                   "selected_tokens_per_stage": counts},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads() if dev == "cpu" else 0, "kind": which,
+                         "sample": f"{frames} frames per step (full batch), {what}, {where}, benchmark.py:33-42 loop"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -290,10 +349,11 @@ def run_ours(args, workload):
             threads = os.cpu_count() or 1
             torch.set_num_threads(threads)
             sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-            fps_cpu, dt_cpu, _ = cpu_baseline(workload, args.sparsity, B, 3, 1, sd, kind=args.input)
-            cpu = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"{B} frames x 3 timed iterations (1 warm-up) of the same workload, oracle port of the "
-                             f"reference PyTorch CPU path, fp32, {dt_cpu * 1e3:.0f} ms per iteration"}
+            fps_cpu, dt_cpu, _, which = cpu_baseline(workload, args.sparsity, B, 3, 1, sd, kind=args.input)
+            cpu = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": which,
+                   "sample": f"{B} frames x 3 timed iterations (1 warm-up) of the same workload, "
+                             + ("unmodified reference (baseline/_ref)" if which == "reference" else "oracle port of the reference")
+                             + f" PyTorch CPU path, fp32, {dt_cpu * 1e3:.0f} ms per iteration"}
         line = {
             "metric": METRIC, "value": frames / t_res, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True,
@@ -326,6 +386,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu (the reference arm) or cuda (the same unmodified code, stock PyTorch eager on the GPU)")
     ap.add_argument("--workload", default="1mpx_b8", choices=sorted(WORKLOADS))
     ap.add_argument("--sparsity", type=float, default=0.0, help="benchmark.py default 0.0 (every pixel active)")
     ap.add_argument("--input", default="binary", choices=["binary", "poisson"],

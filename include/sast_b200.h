@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SAST_ABI_VERSION 1
+#define SAST_ABI_VERSION 2
 
 enum sast_error {
   SAST_OK = 0,
@@ -50,7 +50,9 @@ enum sast_flavor {       /* how (window w, token t) maps to a pixel of the NHWC 
 
 enum sast_precision {
   SAST_FP32 = 0,         /* CUDA-core fp32 FMA everywhere (validation grade)        */
-  SAST_BF16 = 1          /* tcgen05 bf16 operands / fp32 accumulate for GEMMs+attention */
+  SAST_BF16 = 1,         /* tcgen05 bf16 operands / fp32 accumulate for GEMMs+attention: the fused one-kernel
+                            layer where sast_layer_is_fused() says so, else the multi-kernel chain          */
+  SAST_BF16_CHAIN = 2    /* same arithmetic, always the multi-kernel chain (A/B comparisons, tests)          */
 };
 
 enum sast_dtype { SAST_U8 = 0, SAST_I32 = 1, SAST_F32 = 2, SAST_I64 = 3, SAST_F16 = 4, SAST_BF16_T = 5 };
@@ -68,7 +70,7 @@ typedef struct sast_geom {
  * [index_window, index_token, padding_index, asy_index, K] of SAST.py:123.
  */
 typedef struct sast_selection {
-  int32_t* counts;    /* [8]  0:M  1:S  2:Kmax  3..7 reserved                                   */
+  int32_t* counts;    /* [8]  0:M  1:S  2:Kmax  3:number of entries of tile_list  4..7 reserved */
   int32_t* win_K;     /* [NW]   selected tokens in window w (0 when the window is dropped)  */
   int32_t* win_rank;  /* [NW]   rank m of window w among selected windows, or -1            */
   int32_t* win_row0;  /* [NW+1] first compacted row of window w (exclusive prefix of win_K) */
@@ -81,6 +83,8 @@ typedef struct sast_selection {
   int32_t* tiles;     /* [NW*2] attention tiles (consecutive windows of one frame, <= 128 rows): the j-th tile
                                 of frame b is slot b*N + j: tiles[2 slot] = its first window (-1 = unused slot),
                                 tiles[2 slot + 1] = one past its last window                   */
+  int32_t* tile_list; /* [NW*2] the same tiles as one dense work list (any order): entry k < counts[3] is
+                                {first compacted row, number of rows}; a tile holds whole windows        */
 } sast_selection;
 
 /* Bytes of one int32 pool able to hold a sast_selection for (NW, P, B); see sast_selection_bind. */
@@ -190,6 +194,10 @@ typedef struct sast_layer_args {
 } sast_layer_args;
 size_t sast_layer_workspace_bytes(int64_t P, int32_t C, int32_t I, int32_t B, int32_t precision);
 int sast_layer_fwd(const sast_layer_args* a, void* stream);
+/* 1 if sast_layer_fwd runs this configuration as ONE fused kernel (SAST_BF16, C = 64 or 128 with the mlp_ratio-4
+ * GLU width, no context broadcast): the whole layer per 128-row tile with qkv / attention / MLP intermediates kept
+ * in shared and tensor memory.  Such calls need no workspace (workspace may be NULL).  0: the multi-kernel chain. */
+int32_t sast_layer_is_fused(int32_t C, int32_t I, int32_t precision, int32_t enable_cb);
 
 /* Standalone gather / scatter of the selected tokens (a9 / a13), for tests and the
  * HBM-roofline microbenchmark: rows [S,C] <-> map tokens, through sel.row_tok. */

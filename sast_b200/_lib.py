@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SAST_B200_LIB") or os.path.join(_HERE, "libsast_b200.
 
 # enums (mirror include/sast_b200.h)
 WINDOW, GRID, FLAT = 0, 1, 2
-FP32, BF16 = 0, 1
+FP32, BF16, BF16_CHAIN = 0, 1, 2
 U8, I32, F32 = 0, 1, 2
 SEL_SCORES, SEL_PROBS, SEL_FLAGS = 0, 1, 2
 
@@ -32,7 +32,7 @@ class Selection(C.Structure):
     _fields_ = [("counts", C.c_void_p), ("win_K", C.c_void_p), ("win_rank", C.c_void_p),
                 ("win_row0", C.c_void_p), ("sel_win", C.c_void_p), ("tok_row", C.c_void_p),
                 ("row_tok", C.c_void_p), ("row_pix", C.c_void_p), ("win_logit", C.c_void_p),
-                ("tok_keep", C.c_void_p), ("tiles", C.c_void_p)]
+                ("tok_keep", C.c_void_p), ("tiles", C.c_void_p), ("tile_list", C.c_void_p)]
 
 
 class ScoreArgs(C.Structure):
@@ -83,6 +83,7 @@ def _load():
         "sast_select2": (C.c_int, [C.POINTER(SelectArgs), i32, C.POINTER(Selection), vp]),
         "sast_layer_workspace_bytes": (sz, [i64, i32, i32, i32, i32]),
         "sast_layer_fwd": (C.c_int, [C.POINTER(LayerArgs), vp]),
+        "sast_layer_is_fused": (i32, [i32, i32, i32, i32]),
         "sast_gather": (C.c_int, [C.POINTER(Geom), i32, vp, C.POINTER(Selection), vp, vp]),
         "sast_scatter": (C.c_int, [C.POINTER(Geom), i32, vp, C.POINTER(Selection), vp, vp]),
         "sast_gemm_bf16": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
@@ -97,7 +98,7 @@ def _load():
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.sast_abi_version() != 1:
+    if lib.sast_abi_version() != 2:
         raise RuntimeError("libsast_b200.so ABI version mismatch")
     for which, cls in enumerate((Geom, Selection, ScoreArgs, SelectArgs, LayerWeights, LayerArgs)):
         if lib.sast_struct_size(which) != C.sizeof(cls):
@@ -108,7 +109,7 @@ def _load():
 
 EXPORTS = ("sast_abi_version", "sast_build_info", "sast_struct_size", "sast_launch_count", "sast_selection_bytes", "sast_selection_bind",
            "sast_nonzero_ratio", "sast_score_fwd", "sast_select", "sast_select2", "sast_layer_workspace_bytes",
-           "sast_layer_fwd", "sast_gather", "sast_scatter", "sast_gemm_bf16", "sast_gemm_bf16_glu", "sast_pad_input", "sast_pad_nhwc",
+           "sast_layer_fwd", "sast_layer_is_fused", "sast_gather", "sast_scatter", "sast_gemm_bf16", "sast_gemm_bf16_glu", "sast_pad_input", "sast_pad_nhwc",
            "sast_layernorm", "sast_lstm_gates", "sast_lstm_fwd", "sast_stem_fwd", "sast_debug_trace")
 
 _lib = None
@@ -127,6 +128,14 @@ def check(rc: int, what: str):
     if rc < 0:
         raise RuntimeError(f"{what}: {_ERR.get(rc, rc)}")
     raise RuntimeError(f"{what}: CUDA error {rc}")
+
+
+def run(device, name: str, *args):
+    """Call entry point `name` with `args` + the current stream of `device`, with that device current (the
+    library launches on the current CUDA device; per-device kernel attributes are set inside each call)."""
+    with torch.cuda.device(device):
+        rc = getattr(lib(), name)(*args, torch.cuda.current_stream(device).cuda_stream)
+    check(rc, name)
 
 
 def stream_ptr(device) -> int:

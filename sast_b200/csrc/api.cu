@@ -10,7 +10,7 @@ extern "C" uint64_t sast_launch_count(void) { return g_launches.load(std::memory
 extern "C" int sast_abi_version(void) { return SAST_ABI_VERSION; }
 
 extern "C" const char* sast_build_info(void) {
-  return "libsast_b200 abi " "1" " sm_100a nvcc " __DATE__;
+  return "libsast_b200 abi " "2" " sm_100a nvcc " __DATE__;
 }
 
 // sizeof() of the ABI structs as this library was compiled, so that a binding can verify its mirror.

@@ -59,14 +59,7 @@ __device__ __forceinline__ float ex2_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
+using ptx::tmem_ld_32x16;
 
 // 256 threads: warps w and w+4 own TMEM lanes 32*(w%4)..+31 (= tile rows); the low warp of a pair works on key
 // columns [0,64), the high warp on [64,128) -- two threads per row halve the softmax latency chain and double
@@ -394,12 +387,11 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
   CUtensorMap mq;
   int rc = make_tmap_bf16_box(&mq, qkv, max_rows, 3 * C, 3 * C, 32, 128, 64);
   if (rc) return rc;
-  static bool attr_done = false;
   const size_t smem = 1024 + 5 * AT_TILE + 1024 + sizeof(AttnSmem);
-  if (!attr_done) {
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
   // enough CTAs to fill the chip (4 per SM): all heads in one CTA when there are many tile slots, fewer otherwise
   int hpc = heads;

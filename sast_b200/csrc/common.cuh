@@ -44,6 +44,18 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through SAST_LAUNCH_CHECK
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE attribute: a launcher keeps one
+// `static thread_local uint64_t` mask per kernel instantiation and sets the attribute the first time each device is
+// used by each host thread (idempotent; no cross-thread state).
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

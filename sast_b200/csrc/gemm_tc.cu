@@ -382,13 +382,10 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, long long rows, int cols,
   return make_tmap_bf16_box(m, ptr, rows, cols, ld, TC_BK, box_rows, 128);
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
+static int sm_count() {   // of the CURRENT device (no process-wide cache: one process may drive several GPUs)
+  int n = 0, dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   return n;
 }
 
@@ -398,11 +395,10 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const float* 
                      const CUtensorMap* ma2 = nullptr, int k_split = 1 << 30) {
   const int stages = BN > 128 ? 3 : TC_STAGES;                          // 3 x 48 KB or 4 x <=32 KB of operand ring
   const size_t smem = 1024 + (size_t)stages * (TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2) + 128;
-  static bool attr_done = false;   // per-instantiation; the attribute is idempotent
-  if (!attr_done) {
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024);   // + <= 34 KB static
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
   const long long tiles = ((max_rows + TC_BM - 1) / TC_BM) * (N / BN);       // worst case; the kernel clips to counts[1]
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());

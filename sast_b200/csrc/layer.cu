@@ -436,14 +436,24 @@ static int launch_gather_ln(const sast_layer_args& a, const Geom& g, const Layer
 }  // namespace sast
 
 extern "C" size_t sast_layer_workspace_bytes(int64_t P, int32_t C, int32_t I, int32_t B, int32_t precision) {
+  if (precision == SAST_BF16_CHAIN) precision = SAST_BF16;
   return sast::layer_workspace_layout(P, C, I, B, precision, nullptr, nullptr);
+}
+
+extern "C" int32_t sast_layer_is_fused(int32_t C, int32_t I, int32_t precision, int32_t enable_cb) {
+  sast_layer_args a{};
+  a.g.C = C; a.w.I = I; a.precision = precision; a.enable_cb = enable_cb;
+  return sast::fused_layer_supported(a) ? 1 : 0;
 }
 
 extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
   using namespace sast;
   SAST_CHECK_PTR(ap);
-  const sast_layer_args& a = *ap;
-  SAST_CHECK_PTR(a.x); SAST_CHECK_PTR(a.out); SAST_CHECK_PTR(a.workspace);
+  sast_layer_args a_ = *ap;
+  const bool chain = a_.precision == SAST_BF16_CHAIN;
+  if (chain) a_.precision = SAST_BF16;
+  const sast_layer_args& a = a_;
+  SAST_CHECK_PTR(a.x); SAST_CHECK_PTR(a.out);
   if (a.x == a.out) return SAST_E_UNSUPPORTED;
   int rc = check_geom(a.g, a.flavor);
   if (rc) return rc;
@@ -459,6 +469,8 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
   if (a.precision == SAST_BF16) {
     SAST_CHECK_PTR(w.qkv_w_bf16); SAST_CHECK_PTR(w.proj_w_bf16); SAST_CHECK_PTR(w.mlp1_w_bf16); SAST_CHECK_PTR(w.mlp2_w_bf16);
   }
+  if (!chain && fused_layer_supported(a)) return launch_layer_fused(a, g, (cudaStream_t)stream);      // one kernel, no workspace
+  SAST_CHECK_PTR(a.workspace);
   LayerWorkspace ws;
   const size_t need = layer_workspace_layout(g.P, C, I, g.B, a.precision, a.workspace, &ws);
   if (need > a.workspace_bytes) return SAST_E_WORKSPACE;

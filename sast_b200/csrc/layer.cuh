@@ -48,4 +48,8 @@ int launch_gemm_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, cons
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, const sast_selection& sel, int NW, int B, int T,
                         long long max_rows, int variant, cudaStream_t st);
 
+// fused one-kernel layer (fused_layer.cu): bf16 path, C = 64 / 128, no context broadcast
+bool fused_layer_supported(const sast_layer_args& a);
+int launch_layer_fused(const sast_layer_args& a, const Geom& g, cudaStream_t st);
+
 }  // namespace sast

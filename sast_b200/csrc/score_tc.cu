@@ -299,11 +299,10 @@ int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv
   if (P * C >= (1ll << 31)) return SAST_E_UNSUPPORTED;        // 32-bit element offsets inside the kernel
   const size_t smem = (size_t)SC_STAGES * (2 * SC_BM * SC_BK * 4 + 2 * (size_t)BN * SC_BK * 4) + 256 +
                       (size_t)4 * SC_GROUPS * 32 * 33 * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kSelThreads) select_flags_kernel(SelectParams 
   const sast_select_args& a = p.a;
   const Geom g = make_geom(a.g, flavor);
   __shared__ float red[kSelWarps];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) sel.counts[3] = 0;   // tile_list fill count (select_scan adds)
   const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n = blockIdx.x * kSelWarps + wid;
   const int w = b * g.N + n;
@@ -226,29 +227,36 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
     if (threadIdx.x == 0) {
       int k = 0;
       for (int i = 0; i < kSelWarps; ++i) k = max(k, red3[i][2]);
-      sel.counts[0] = run_m; sel.counts[1] = run_s; sel.counts[2] = k; sel.counts[3] = 0;
+      sel.counts[0] = run_m; sel.counts[1] = run_s; sel.counts[2] = k;
       sel.win_row0[g.NW] = run_s;
     }
   }
   __syncthreads();
-  // greedy packing of consecutive windows of this frame into attention tiles of <= 128 rows.  The j-th tile of
-  // frame b goes to slot b*N + j: tiles[2 slot] = first window, tiles[2 slot + 1] = one past its last window
-  // (first window -1: slot unused).  Slots are dense from j = 0, so a tile-major grid has its idle CTAs last.
+  // greedy packing of consecutive windows of this frame into attention tiles of <= 128 rows and <= 128 windows
+  // (a tile starts at a selected window; empty windows never open one).  The j-th tile of frame b goes to slot
+  // b*N + j: tiles[2 slot] = first window, tiles[2 slot + 1] = one past its last selected window (first window -1:
+  // slot unused).  Slots are dense from j = 0, so a tile-major grid has its idle CTAs last.  The same tiles are
+  // appended to the dense work list tile_list as {first compacted row, rows} (counts[3] entries, order arbitrary).
   if (threadIdx.x == 0) {
-    int start = 0, rows = 0, j = 0;
+    int start = 0, last = 0, rows = 0, j = 0;
+    auto emit = [&]() {
+      const int slot = b * g.N + j;
+      sel.tiles[2 * slot] = b * g.N + start;
+      sel.tiles[2 * slot + 1] = b * g.N + last;
+      const int k = atomicAdd(&sel.counts[3], 1);
+      sel.tile_list[2 * k] = sel.win_row0[b * g.N + start];
+      sel.tile_list[2 * k + 1] = rows;
+      ++j;
+    };
     for (int n = 0; n < g.N; ++n) {
       const int K = kbuf[n];
-      if (rows + K > 128) {
-        sel.tiles[2 * (b * g.N + j)] = b * g.N + start;
-        sel.tiles[2 * (b * g.N + j) + 1] = b * g.N + n;
-        ++j; start = n; rows = 0;
-      }
+      if (K == 0) continue;
+      if (rows > 0 && (rows + K > 128 || n - start >= 128)) { emit(); rows = 0; }
+      if (rows == 0) start = n;
       rows += K;
+      last = n + 1;
     }
-    if (rows > 0) {
-      sel.tiles[2 * (b * g.N + j)] = b * g.N + start;
-      sel.tiles[2 * (b * g.N + j) + 1] = b * g.N + g.N;
-    }
+    if (rows > 0) emit();
   }
 }
 
@@ -291,7 +299,7 @@ extern "C" size_t sast_selection_bytes(int32_t B, int32_t NW, int32_t P) {
   n += align_up(((size_t)NW + 1) * 4, 16);      // win_row0
   n += 3 * align_up((size_t)P * 4, 16);         // tok_row, row_tok, row_pix
   n += align_up((size_t)P, 16);                 // tok_keep
-  n += align_up((size_t)NW * 8, 16);            // tiles
+  n += 2 * align_up((size_t)NW * 8, 16);        // tiles, tile_list
   return n;
 }
 
@@ -312,13 +320,14 @@ extern "C" int sast_selection_bind(void* pool, int32_t B, int32_t NW, int32_t P,
   out->row_pix = (int32_t*)take((size_t)P * 4);
   out->tok_keep = (uint8_t*)take((size_t)P);
   out->tiles = (int32_t*)take((size_t)NW * 8);
+  out->tile_list = (int32_t*)take((size_t)NW * 8);
   return SAST_OK;
 }
 
 static int check_sel(const sast_selection& s) {
   SAST_CHECK_PTR(s.counts); SAST_CHECK_PTR(s.win_K); SAST_CHECK_PTR(s.win_rank); SAST_CHECK_PTR(s.win_row0);
   SAST_CHECK_PTR(s.sel_win); SAST_CHECK_PTR(s.tok_row); SAST_CHECK_PTR(s.row_tok); SAST_CHECK_PTR(s.row_pix);
-  SAST_CHECK_PTR(s.win_logit); SAST_CHECK_PTR(s.tok_keep); SAST_CHECK_PTR(s.tiles);
+  SAST_CHECK_PTR(s.win_logit); SAST_CHECK_PTR(s.tok_keep); SAST_CHECK_PTR(s.tiles); SAST_CHECK_PTR(s.tile_list);
   return SAST_OK;
 }
 

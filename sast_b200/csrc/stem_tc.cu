@@ -266,11 +266,10 @@ extern "C" int sast_stem_fwd(const uint8_t* x, int32_t B, int32_t Cin, int32_t H
   rc = make_tmap_bf16_box(&ml, w_lo, Cout, Kp, Kp, 64, Cout, 128);
   if (rc) return rc;
   const size_t smem = (size_t)ST_STAGES * (ST_BM * 128 + 2 * (size_t)Cout * 128) + sizeof(StSmem) + 64;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
   }
   if (smem > 200 * 1024) return SAST_E_UNSUPPORTED;
   int sms = 148, dev = 0;

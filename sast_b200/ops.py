@@ -53,8 +53,7 @@ def nonzero_ratio(x: Tensor) -> Tensor:
     B, Cin, H, W = x.shape
     r = torch.empty(4, B, Cin, device=x.device, dtype=torch.float32)          # level-major: r[:, i] below is contiguous
     scratch = torch.zeros(B * Cin * 4, device=x.device, dtype=torch.int32)
-    L.check(L.lib().sast_nonzero_ratio(x.data_ptr(), dt, B, Cin, H, W, r.data_ptr(), scratch.data_ptr(),
-                                       L.stream_ptr(x.device)), "sast_nonzero_ratio")
+    L.run(x.device, "sast_nonzero_ratio", x.data_ptr(), dt, B, Cin, H, W, r.data_ptr(), scratch.data_ptr())
     return r.permute(1, 0, 2)                                                   # the reference's [B, 4, Cin]
 
 
@@ -82,11 +81,12 @@ def score_fwd(x: Tensor, pos: Tensor, r: Tensor, ctrl_w: Tensor, score_w: Tensor
     xw = torch.empty_like(x)
     tok = torch.empty(B, H, W, device=x.device, dtype=torch.float32)
     scratch = torch.empty(2 * B * Cc + (Cc // 32) * B * H * W, device=x.device, dtype=torch.float32)
+    # converted copies (non-fp32 / non-contiguous parameters) must stay alive until after the launch
+    ctrl_w, score_w, score_b = _f32c(ctrl_w, "ctrl_w"), _f32c(score_w, "score_w"), _f32c(score_b, "score_b")
     a = L.ScoreArgs(_geom(B, H, W, Cc, 1, 1), x.data_ptr(), pos.data_ptr(), pstride, r.data_ptr(), r.shape[1],
-                    _f32c(ctrl_w, "ctrl_w").data_ptr(), _f32c(score_w, "score_w").data_ptr(),
-                    _f32c(score_b, "score_b").data_ptr(), float(amp), xw.data_ptr(), tok.data_ptr(),
+                    ctrl_w.data_ptr(), score_w.data_ptr(), score_b.data_ptr(), float(amp), xw.data_ptr(), tok.data_ptr(),
                     scratch.data_ptr(), L.ptr(score_w_hi), L.ptr(score_w_lo))
-    L.check(L.lib().sast_score_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_score_fwd")
+    L.run(x.device, "sast_score_fwd", C.byref(a))
     return xw, tok
 
 
@@ -117,7 +117,7 @@ def add_pos(x: Tensor, pos: Tensor) -> Tensor:
     out = torch.empty_like(x)
     a = L.ScoreArgs(_geom(B, H, W, Cc, 1, 1), x.data_ptr(), pos.data_ptr(), pstride, 0, 0, 0, 0, 0, 0.0,
                     out.data_ptr(), 0, 0, 0, 0)
-    L.check(L.lib().sast_score_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_score_fwd(add_pos)")
+    L.run(x.device, "sast_score_fwd", C.byref(a))
     return out
 
 
@@ -155,7 +155,7 @@ def _select_impl(mode: int, B, H, W, p0, p1, flavor, thr_win, thr_tok, device, t
     a = L.SelectArgs(_geom(B, H, W, 32, p0, p1), int(flavor), mode, L.ptr(tok_score), L.ptr(win_prob),
                      L.ptr(tok_prob), L.ptr(win_flag), L.ptr(tok_flag), float(thr_win), float(thr_tok),
                      L.ptr(wp), L.ptr(tp), sel)
-    L.check(L.lib().sast_select(C.byref(a), L.stream_ptr(device)), "sast_select")
+    L.run(device, "sast_select", C.byref(a))
     return pool, wp, tp
 
 
@@ -186,7 +186,7 @@ def select_pair(tok_score: Tensor, p0: int, p1: int, thr_win: float, thr_tok: fl
     sel_a, sel_b = _bind(pool_a, B, NW, P), _bind(pool_b, B, NW, P)
     a = L.SelectArgs(_geom(B, H, W, 32, p0, p1), L.WINDOW, L.SEL_SCORES, tok_score.data_ptr(), 0, 0, 0, 0,
                      float(thr_win), float(thr_tok), 0, 0, sel_a)
-    L.check(L.lib().sast_select2(C.byref(a), L.GRID, C.byref(sel_b), L.stream_ptr(dev)), "sast_select2")
+    L.run(dev, "sast_select2", C.byref(a), L.GRID, C.byref(sel_b))
     return pool_a, pool_b
 
 
@@ -330,6 +330,14 @@ WEIGHT_ORDER = ("ln1_w", "ln1_b", "ln2_w", "ln2_b", "qkv_w", "qkv_b", "proj_w", 
                 "mlp1_w", "mlp1_b", "mlp2_w", "mlp2_b", "qkv_w_bf16", "proj_w_bf16", "mlp1_w_bf16", "mlp2_w_bf16")
 
 
+def _layer_workspace(lib, P, Cc, mlp_inner, B, precision, enable_cb, device):
+    """Scratch of the multi-kernel chain; the fused one-kernel layer (sast_layer_is_fused) needs none."""
+    if lib.sast_layer_is_fused(int(Cc), int(mlp_inner), int(precision), int(bool(enable_cb))):
+        return None, 0
+    nbytes = lib.sast_layer_workspace_bytes(P, Cc, mlp_inner, B, precision)
+    return torch.empty(nbytes, device=device, dtype=torch.uint8), nbytes
+
+
 @torch.library.custom_op("sast::layer_fwd", mutates_args=())
 def layer_fwd(x: Tensor, pool: Tensor, weights: List[Tensor], p0: int, p1: int, flavor: int, precision: int,
               enable_cb: bool, mlp_inner: int, ln_eps: float) -> Tensor:
@@ -342,16 +350,15 @@ def layer_fwd(x: Tensor, pool: Tensor, weights: List[Tensor], p0: int, p1: int, 
     P = x.numel() // Cc
     lib = L.lib()
     sel = _bind(pool, g.B, (g.H * g.W // (g.p0 * g.p1)) * g.B, P)
-    nbytes = lib.sast_layer_workspace_bytes(P, Cc, mlp_inner, g.B, precision)
-    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    ws, nbytes = _layer_workspace(lib, P, Cc, mlp_inner, g.B, precision, enable_cb, x.device)
     w = L.LayerWeights()
     assert len(weights) == len(WEIGHT_ORDER)
     for name, t in zip(WEIGHT_ORDER, weights):
         setattr(w, name, t.data_ptr() if t.numel() else 0)
     w.I, w.ln_eps = int(mlp_inner), float(ln_eps)
     a = L.LayerArgs(g, int(flavor), int(precision), int(bool(enable_cb)), x.data_ptr(), out.data_ptr(), w, sel,
-                    ws.data_ptr(), nbytes)
-    L.check(lib.sast_layer_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_layer_fwd")
+                    L.ptr(ws), nbytes)
+    L.run(x.device, "sast_layer_fwd", C.byref(a))
     return out
 
 
@@ -368,15 +375,14 @@ def layer_fwd_flat(x: Tensor, sel: Selection, weights, precision, enable_cb, mlp
     lib = L.lib()
     N = NWn // B
     g = _geom(B, N, T, Cc, 1, T)   # FLAT: a "frame" is N rows of T tokens, window n = row n
-    nbytes = lib.sast_layer_workspace_bytes(NWn * T, Cc, mlp_inner, B, precision)
-    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    ws, nbytes = _layer_workspace(lib, NWn * T, Cc, mlp_inner, B, precision, enable_cb, x.device)
     w = L.LayerWeights()
     for name, t in zip(WEIGHT_ORDER, weights):
         setattr(w, name, t.data_ptr() if t.numel() else 0)
     w.I, w.ln_eps = int(mlp_inner), float(ln_eps)
     a = L.LayerArgs(g, L.FLAT, int(precision), int(bool(enable_cb)), x.data_ptr(), out.data_ptr(), w,
-                    sel.struct, ws.data_ptr(), nbytes)
-    L.check(lib.sast_layer_fwd(C.byref(a), L.stream_ptr(x.device)), "sast_layer_fwd")
+                    sel.struct, L.ptr(ws), nbytes)
+    L.run(x.device, "sast_layer_fwd", C.byref(a))
     return out
 
 
@@ -388,8 +394,7 @@ def gather_rows(x: Tensor, sel: Selection, flavor: int) -> Tensor:
     Cc = x.shape[-1]
     rows = torch.zeros(sel.P, Cc, device=x.device, dtype=torch.float32)
     g = _geom(sel.B, sel.H, sel.W, Cc, sel.p0, sel.p1)
-    L.check(L.lib().sast_gather(C.byref(g), flavor, x.data_ptr(), C.byref(sel.struct), rows.data_ptr(),
-                                L.stream_ptr(x.device)), "sast_gather")
+    L.run(x.device, "sast_gather", C.byref(g), flavor, x.data_ptr(), C.byref(sel.struct), rows.data_ptr())
     return rows
 
 
@@ -398,8 +403,7 @@ def scatter_rows(rows: Tensor, sel: Selection, flavor: int, x: Tensor) -> Tensor
     rows = _f32c(rows, "rows")
     Cc = x.shape[-1]
     g = _geom(sel.B, sel.H, sel.W, Cc, sel.p0, sel.p1)
-    L.check(L.lib().sast_scatter(C.byref(g), flavor, rows.data_ptr(), C.byref(sel.struct), x.data_ptr(),
-                                 L.stream_ptr(x.device)), "sast_scatter")
+    L.run(x.device, "sast_scatter", C.byref(g), flavor, rows.data_ptr(), C.byref(sel.struct), x.data_ptr())
     return x
 
 
@@ -410,8 +414,7 @@ def gemm_bf16(A: Tensor, Wt: Tensor, bias: Optional[Tensor] = None, out_bf16: bo
     M, K = A.shape
     N = Wt.shape[0]
     D = torch.empty(M, N, device=A.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
-    L.check(L.lib().sast_gemm_bf16(A.data_ptr(), Wt.data_ptr(), L.ptr(bias), D.data_ptr(), int(out_bf16), M, N, K,
-                                   L.stream_ptr(A.device)), "sast_gemm_bf16")
+    L.run(A.device, "sast_gemm_bf16", A.data_ptr(), Wt.data_ptr(), L.ptr(bias), D.data_ptr(), int(out_bf16), M, N, K)
     return D
 
 
@@ -434,8 +437,7 @@ def pad_input(x: Tensor, pad: int) -> Tensor:
     x = x.contiguous()
     B, Cin, H, W = x.shape
     out = torch.empty(B, H + 2 * pad, W + 2 * pad, Cin, device=x.device, dtype=torch.float32)
-    L.check(L.lib().sast_pad_input(x.data_ptr(), dt, B, Cin, H, W, pad, out.data_ptr(), L.stream_ptr(x.device)),
-            "sast_pad_input")
+    L.run(x.device, "sast_pad_input", x.data_ptr(), dt, B, Cin, H, W, pad, out.data_ptr())
     return out
 
 
@@ -455,8 +457,8 @@ def pad_nhwc(x: Tensor, pad: int) -> Tensor:
         x = x.contiguous()
     B, H, W, Cc = x.shape
     out = torch.empty(B, H + 2 * pad, W + 2 * pad, Cc, device=x.device, dtype=torch.float32)
-    L.check(L.lib().sast_pad_nhwc(x.data_ptr(), B, H, W, Cc, pad, x.stride(0), x.stride(1), x.stride(2),
-                                  out.data_ptr(), L.stream_ptr(x.device)), "sast_pad_nhwc")
+    L.run(x.device, "sast_pad_nhwc", x.data_ptr(), B, H, W, Cc, pad, x.stride(0), x.stride(1), x.stride(2),
+                                  out.data_ptr())
     return out
 
 
@@ -471,9 +473,10 @@ def layernorm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps: 
     x = _f32c(x, "x")
     Cc = x.shape[-1]
     out = torch.empty_like(x)
-    L.check(L.lib().sast_layernorm(x.data_ptr(), L.ptr(None if weight is None else _f32c(weight, "weight")),
-                                   L.ptr(None if bias is None else _f32c(bias, "bias")), float(eps),
-                                   x.numel() // Cc, Cc, out.data_ptr(), L.stream_ptr(x.device)), "sast_layernorm")
+    weight = None if weight is None else _f32c(weight, "weight")     # keep converted copies alive past the launch
+    bias = None if bias is None else _f32c(bias, "bias")
+    L.run(x.device, "sast_layernorm", x.data_ptr(), L.ptr(weight), L.ptr(bias), float(eps),
+                                   x.numel() // Cc, Cc, out.data_ptr())
     return out
 
 
@@ -492,9 +495,10 @@ def lstm_gates(mix: Tensor, bias: Optional[Tensor], c_prev: Optional[Tensor]) ->
         c_prev = _f32c(c_prev, "c_prev")
     h = torch.empty(shape, device=mix.device, dtype=torch.float32)
     c = torch.empty(shape, device=mix.device, dtype=torch.float32)
-    L.check(L.lib().sast_lstm_gates(mix.data_ptr(), L.ptr(None if bias is None else _f32c(bias, "bias")), L.ptr(c_prev),
+    bias = None if bias is None else _f32c(bias, "bias")             # keep the converted copy alive past the launch
+    L.run(mix.device, "sast_lstm_gates", mix.data_ptr(), L.ptr(bias), L.ptr(c_prev),
                                     mix.numel() // (4 * Cc), Cc, h.data_ptr(),
-                                    c.data_ptr(), L.stream_ptr(mix.device)), "sast_lstm_gates")
+                                    c.data_ptr())
     return h, c
 
 
@@ -513,8 +517,8 @@ def lstm_fwd(x: Tensor, h_prev: Optional[Tensor], c_prev: Optional[Tensor], w_pa
     if h_prev is not None:
         h_prev, c_prev = _f32c(h_prev, "h_prev"), _f32c(c_prev, "c_prev")
     h, c = torch.empty_like(x), torch.empty_like(x)
-    L.check(L.lib().sast_lstm_fwd(x.data_ptr(), L.ptr(h_prev), L.ptr(c_prev), w_packed.data_ptr(), L.ptr(bias_packed),
-                                  x.numel() // Cc, Cc, h.data_ptr(), c.data_ptr(), L.stream_ptr(x.device)), "sast_lstm_fwd")
+    L.run(x.device, "sast_lstm_fwd", x.data_ptr(), L.ptr(h_prev), L.ptr(c_prev), w_packed.data_ptr(), L.ptr(bias_packed),
+                                  x.numel() // Cc, Cc, h.data_ptr(), c.data_ptr())
     return h, c
 
 
@@ -530,8 +534,7 @@ def gemm_bf16_glu(A: Tensor, Wt_interleaved: Tensor, bias_interleaved: Optional[
     M, K = A.shape
     N = Wt.shape[0]
     D = torch.empty(M, N // 2, device=A.device, dtype=torch.bfloat16)
-    L.check(L.lib().sast_gemm_bf16_glu(A.data_ptr(), Wt.data_ptr(), L.ptr(bias_interleaved), D.data_ptr(), M, N, K,
-                                       L.stream_ptr(A.device)), "sast_gemm_bf16_glu")
+    L.run(A.device, "sast_gemm_bf16_glu", A.data_ptr(), Wt.data_ptr(), L.ptr(bias_interleaved), D.data_ptr(), M, N, K)
     return D
 
 
@@ -560,9 +563,8 @@ def stem_fwd(x: Tensor, w_hi: Tensor, w_lo: Tensor, n_groups_pad: int, ln_w: Opt
     B, Cin, H, W = x.shape
     Cout = w_hi.shape[0]
     out = torch.empty(B, H // 4, W // 4, Cout, device=x.device, dtype=torch.float32)
-    L.check(L.lib().sast_stem_fwd(x.data_ptr(), B, Cin, H, W, w_hi.data_ptr(), w_lo.data_ptr(), Cout, n_groups_pad,
-                                  L.ptr(ln_w), L.ptr(ln_b), float(eps), out.data_ptr(), L.stream_ptr(x.device)),
-            "sast_stem_fwd")
+    L.run(x.device, "sast_stem_fwd", x.data_ptr(), B, Cin, H, W, w_hi.data_ptr(), w_lo.data_ptr(), Cout, n_groups_pad,
+                                  L.ptr(ln_w), L.ptr(ln_b), float(eps), out.data_ptr())
     return out
 
 

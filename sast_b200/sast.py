@@ -26,8 +26,10 @@ Tensor = torch.Tensor
 
 
 def default_precision() -> int:
-    """SAST_B200_PRECISION=fp32 selects the CUDA-core validation path; default bf16 tensor cores."""
-    return L.FP32 if os.environ.get("SAST_B200_PRECISION", "bf16").lower() == "fp32" else L.BF16
+    """SAST_B200_PRECISION=fp32 selects the CUDA-core validation path, bf16_chain the unfused tensor-core
+    kernel chain; default bf16 tensor cores (fused one-kernel layers where the library supports the shape)."""
+    v = os.environ.get("SAST_B200_PRECISION", "bf16").lower()
+    return L.FP32 if v == "fp32" else L.BF16_CHAIN if v == "bf16_chain" else L.BF16
 
 
 # ------------------------------------------------------------------------------------------
@@ -248,7 +250,7 @@ class MS_WSA(nn.Module):
         ws = [f(self.norm1.weight), f(self.norm1.bias), f(self.norm2.weight), f(self.norm2.bias), f(self.qkv.weight),
               f(self.qkv.bias), f(self.proj.weight), f(self.proj.bias), f(srcs[8]), f(srcs[9]), w1i, b1i,
               f(out.weight), f(out.bias)]
-        if self.precision == L.BF16:
+        if self.precision != L.FP32:
             ws += [ws[4].to(torch.bfloat16), ws[6].to(torch.bfloat16), w1i.to(torch.bfloat16), ws[12].to(torch.bfloat16)]
         else:
             ws += [empty, empty, empty, empty]

@@ -16,7 +16,10 @@ BLOCKS = ["block_c64_w6x10", "block_c128_w8x10_b1", "block_c64_cb", "block_c64_d
 # tolerance on the block output (LayerNorm-scaled activations, LayerScale gamma ~0.5 so the
 # attention/MLP branch is fully visible): fp32 path = summation-order noise; bf16 path = bf16
 # operand rounding through 4 GEMMs + attention per layer, two layers.
-TOL = {L.FP32: 2e-4, L.BF16: 6e-2}
+# SURVEY tier C: bf16-operand path <= 2e-2 abs on LN-scaled activations (observed ~1.3e-2).
+TOL = {L.FP32: 2e-4, L.BF16: 2e-2, L.BF16_CHAIN: 2e-2}
+PRECS = [L.FP32, L.BF16, L.BF16_CHAIN]
+PREC_IDS = ["fp32", "bf16", "bf16chain"]
 
 
 def _compare_lists(lists, g, li):
@@ -28,7 +31,7 @@ def _compare_lists(lists, g, li):
     assert set(pad.tolist()) == set(it.tolist()) - set(asy.tolist())
 
 
-@pytest.mark.parametrize("precision", [L.FP32, L.BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECS, ids=PREC_IDS)
 @pytest.mark.parametrize("name", BLOCKS)
 def test_block_golden(golden, name, precision):
     g = golden(name)
@@ -55,7 +58,7 @@ def test_block_golden(golden, name, precision):
         assert torch.equal(y2, y2b)
 
 
-@pytest.mark.parametrize("precision", [L.FP32, L.BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECS, ids=PREC_IDS)
 def test_ms_wsa_reference_signature(golden, precision):
     """MS_WSA.forward(x, index_window, index_token, padding_index, asy_index, M, B, enable_CB) on a
     partitioned tensor (ref: SAST.py:199-201) against the oracle's sparse form."""
@@ -79,7 +82,7 @@ def test_ms_wsa_reference_signature(golden, precision):
     assert (got.cpu() - ref).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("precision", [L.FP32, L.BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECS, ids=PREC_IDS)
 @pytest.mark.parametrize("name", ["backbone_e32", "backbone_e32_nb2_mask_cb"])
 def test_backbone_golden(golden, name, precision):
     """RNNDetector: two recurrent steps with carried LSTM state against the reference."""
@@ -147,17 +150,18 @@ def test_block_bf16_against_fp32_path(C, part, B, H, W, amp, r_scale):
     r = (torch.rand(B, 20, generator=gen) * r_scale).to(DEV)
     pos = PositionEmbeddingSine(C // 2, normalize=True, input_size=(1, H, W))
     outs = {}
-    for prec in (L.FP32, L.BF16):
+    for prec in (L.FP32, L.BF16, L.BF16_CHAIN):
         blk.win_attn.precision = blk.grid_attn.precision = prec
         with torch.no_grad():
             y, cnt, lists = blk(x, pos, r, None)
         outs[prec] = (y, int(cnt), [(l.tok_row >= 0).clone() for l in lists])
-    assert outs[L.FP32][1] == outs[L.BF16][1] > 0
-    for a, b in zip(outs[L.FP32][2], outs[L.BF16][2]):
-        assert torch.equal(a, b)
-    assert torch.isfinite(outs[L.BF16][0]).all()
-    err = (outs[L.FP32][0] - outs[L.BF16][0]).abs().max().item()
-    assert err < 6e-2, err
+    for prec in (L.BF16, L.BF16_CHAIN):      # fused one-kernel layer (C = 64 / 128) and the multi-kernel chain
+        assert outs[L.FP32][1] == outs[prec][1] > 0
+        for a, b in zip(outs[L.FP32][2], outs[prec][2]):
+            assert torch.equal(a, b)
+        assert torch.isfinite(outs[prec][0]).all()
+        err = (outs[L.FP32][0] - outs[prec][0]).abs().max().item()
+        assert err < 2e-2, (prec, err)
 
 
 def test_block_training_gradients_match_oracle(golden):
@@ -195,7 +199,7 @@ def test_block_training_gradients_match_oracle(golden):
 
 
 @pytest.mark.parametrize("case", ["single_window", "T128", "empty_scene", "dense_B1", "many_frames"])
-@pytest.mark.parametrize("precision", [L.FP32, L.BF16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("precision", PRECS, ids=PREC_IDS)
 def test_block_edge_cases_against_oracle(case, precision):
     """Edge geometries and scenes the domain has: one window per frame (N=1: always selected, SAST.py:260-262
     comment / Gen1 stage 4), the largest window the kernels take (T=128), an empty scene (r=0: the control
@@ -251,3 +255,69 @@ def test_block_edge_cases_against_oracle(case, precision):
     if flips == 0:
         assert int(cnt) == cnt_ref
         assert (y.cpu() - y_ref).abs().max().item() < TOL[precision]
+
+
+def _dense_layer_reference(x, sel_mask_map, params, prefix, C, part, flavor):
+    """oracle.ms_wsa_dense (the dense-equivalent statement, SURVEY 8a, pinned against the reference) on the map."""
+    B, H, W, _ = x.shape
+    part_fn, rev_fn = (O.window_partition, O.window_reverse) if flavor == L.WINDOW else (O.grid_partition, O.grid_reverse)
+    T = part[0] * part[1]
+    xp = part_fn(x, part).reshape(-1, T, C)
+    mp = part_fn(sel_mask_map.view(B, H, W, 1), part).reshape(-1, T) > 0.5
+    out = O.ms_wsa_dense(xp, mp, O.sub(params, prefix.rstrip(".")), B)
+    return rev_fn(out.view(-1, part[0], part[1], C), part, (H, W))
+
+
+@pytest.mark.parametrize("precision", PRECS, ids=PREC_IDS)
+@pytest.mark.parametrize("case", ["late_windows", "sparse_mixed", "one_token", "nothing", "gen1_T80", "c128_grid"])
+def test_layer_explicit_selection(case, precision):
+    """One MS-WSA layer on an explicit (flag-given) selection against the fp64 dense-equivalent statement.
+    late_windows: N = 256 windows per frame with only windows >= 128 selected (a tile must not span more than 128
+    windows / must start at a selected window: the bf16 attention kernel used to write NaN here); sparse_mixed: few
+    tokens per window, many windows per tile; one_token / nothing: degenerate counts."""
+    from sast_b200.config import attention_config
+    from oracle.golden_common import make_params, with_aliases
+    C, part, B, H, W, flavor = 64, (6, 10), 2, 96, 160, L.WINDOW
+    if case == "gen1_T80":
+        part, B, H, W = (8, 10), 3, 32, 40
+    if case == "c128_grid":
+        C, B, H, W, flavor = 128, 2, 48, 80, L.GRID
+    T = part[0] * part[1]
+    N = H * W // T
+    gen = torch.Generator().manual_seed(len(case) + C)
+    wf = torch.zeros(B, N, dtype=torch.uint8)
+    tf = torch.zeros(B, N, T, dtype=torch.uint8)
+    if case == "late_windows":
+        wf[0, 200] = 1; wf[0, 131] = 1; wf[1, 255] = 1
+        tf[:] = (torch.rand(B, N, T, generator=gen) < 0.5).to(torch.uint8)
+    elif case == "sparse_mixed":
+        wf[:] = (torch.rand(B, N, generator=gen) < 0.7).to(torch.uint8)
+        tf[:] = (torch.rand(B, N, T, generator=gen) < 0.05).to(torch.uint8)
+    elif case == "one_token":
+        wf[1, 3] = 1; tf[1, 3, 7] = 1
+    elif case == "nothing":
+        pass
+    else:
+        wf[:] = (torch.rand(B, N, generator=gen) < 0.8).to(torch.uint8)
+        tf[:] = (torch.rand(B, N, T, generator=gen) < 0.6).to(torch.uint8)
+    tf = tf * wf[:, :, None]
+    wf = (tf.sum(-1) > 0).to(torch.uint8)            # every kept window holds >= 1 token, as in the reference
+    blk = sast_b200.SAST_block(C, attention_config(part), first_block=True)
+    shapes = {k: tuple(v.shape) for k, v in blk.state_dict().items() if ".sub_layers." not in k}
+    params = make_params(shapes, seed=5)
+    blk.load_state_dict(with_aliases(params, blk.state_dict().keys()))
+    blk = blk.to(DEV).eval()
+    layer, prefix = (blk.win_attn, "win_attn.") if flavor == L.WINDOW else (blk.grid_attn, "grid_attn.")
+    layer.precision = precision
+    x = torch.randn(B, H, W, C, generator=gen) * torch.linspace(0.3, 1.7, W).view(1, 1, W, 1)
+    sel = ops.Selection(ops.select_from_flags(wf.view(-1).to(DEV), tf.view(-1).to(DEV), B, H, W, part[0], part[1], flavor),
+                        B, H, W, part[0], part[1])
+    with torch.no_grad():
+        y = layer.run(x.to(DEV), sel, flavor, False)
+    assert torch.isfinite(y).all()
+    rev = O.window_reverse if flavor == L.WINDOW else O.grid_reverse
+    mask_map = rev(tf.view(B * N, part[0], part[1], 1).float(), part, (H, W)).view(B, H, W) > 0.5
+    assert int(sel.counts[1]) == int(mask_map.sum())
+    ref = _dense_layer_reference(x, mask_map.float(), params, prefix, C, part, flavor)
+    err = (y.cpu() - ref).abs().max().item()
+    assert err < TOL[precision], err

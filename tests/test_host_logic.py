@@ -26,7 +26,7 @@ def test_header_symbols_exported():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/sast_b200.h but not exported"
     assert declared == set(L.EXPORTS)
-    assert L.lib().sast_abi_version() == 1
+    assert L.lib().sast_abi_version() == 2
     assert b"sm_100a" in L.lib().sast_build_info()
 
 
@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
     lib = L.lib()   # _load() already raises on a mismatch; spell it out here
     for which, cls in enumerate((L.Geom, L.Selection, L.ScoreArgs, L.SelectArgs, L.LayerWeights, L.LayerArgs)):
         assert lib.sast_struct_size(which) == ctypes.sizeof(cls), cls.__name__
-    assert ctypes.sizeof(L.Geom) == 24 and ctypes.sizeof(L.Selection) == 88
+    assert ctypes.sizeof(L.Geom) == 24 and ctypes.sizeof(L.Selection) == 96
 
 
 def test_selection_pool_layout():
