@@ -80,6 +80,7 @@ struct Params {
   const int *counts, *tile_list, *row_tok, *row_pix, *win_row0, *tok_row;
   Geom g;
   int flavor;
+  long long* trace;      // debug stamps (sast_debug_trace which = 4), normally null; trace build only
 };
 
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -134,6 +135,10 @@ __device__ __forceinline__ void mma_kblock(bool leader, uint32_t tmem_d, uint32_
     if (k < nks && leader) ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), id, (k > 0 || !fresh) ? 1u : 0u);
 }
 
+// trace build only: [CTA][32] clock64 stamps of thread 0: 0..14 phase boundaries of the CTA's SECOND tile (steady state),
+// 15 kernel entry, 16 set-up done, 17 tiles done, 18 unselected pass done, 19 SM id, 20 tiles of this CTA
+#define FL_STAMP(i) SAST_STAMP(trc, tid == 0 && ti == 1, (i))
+
 template <int C>
 __global__ void __launch_bounds__(Cfg<C>::kThreads, 1)
 layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_proj,
@@ -150,6 +155,8 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(kFull, tid >> 5, 0), lane = tid & 31;
+  [[maybe_unused]] long long* const trc = p.trace ? p.trace + (size_t)blockIdx.x * 32 : nullptr;
+  SAST_STAMP(trc, tid == 0, 15);
 
   if (tid == 0) {
     ptx::tma_prefetch_desc(&map_qkv); ptx::tma_prefetch_desc(&map_proj);
@@ -178,6 +185,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 
   pdl_entry();                                             // selection + input map are read from here on
   const int n_tiles = p.counts[3];
+  SAST_STAMP(trc, tid == 0, 16);
 
   if (K::kRing && warp == 16) {
     // ---------------- weight producer (ring mode): 23 chunks of 16 KB per tile, in consumption order ----------------
@@ -231,7 +239,10 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 
     if (!K::kRing && mma_warp) ptx::mbar_wait(&ctl->w_full[0], 0);     // resident weights have landed
 
+    [[maybe_unused]] int ti = -1;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      ++ti;
+      FL_STAMP(0);
       const int row0 = p.tile_list[2 * t], rows = p.tile_list[2 * t + 1];
 
       // ---- tile bookkeeping (consumed after later barriers) + gather / LN1 / LN2 -------------------------------
@@ -297,6 +308,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       compute_sync();
+      FL_STAMP(1);
 
       // ---- QKV = n2 Wqkv^T ----------------------------------------------------------------------------------------
       if (mma_warp) {
@@ -322,6 +334,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         y[4 * j] = f.x; y[4 * j + 1] = f.y; y[4 * j + 2] = f.z; y[4 * j + 3] = f.w;
       }
       wait_mma();
+      FL_STAMP(2);
       compute_sync();                                        // every shortcut read is done: the Q,K,V tiles may overwrite it
 
       // ---- QKV epilogue: + bias, bf16, operand tiles of the attention MMAs ------------------------------------
@@ -350,6 +363,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       compute_sync();
+      FL_STAMP(3);
 
       // ---- attention, two heads at a time -------------------------------------------------------------------------
       const int lo = ctl->lo[row], hi = ctl->hi[row];
@@ -370,6 +384,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           if (leader) ptx::umma_commit(&ctl->mma_bar);
         }
         wait_mma();
+        FL_STAMP(4);
         // pass 1: row maximum over the keys of the row's own window, this thread's 64 columns
         float mx = -INFINITY;
         bool need[2];
@@ -388,6 +403,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
         ctl->pmax[hh][half][row] = mx;
         compute_sync();
+        FL_STAMP(5);
         mx = fmaxf(ctl->pmax[hh][0][row], ctl->pmax[hh][1][row]);
         const float mxs = mx * sc;
         // pass 2: p = 2^((s - max) scale log2e) as bf16 pairs into TMEM -- the A operand of P V
@@ -416,6 +432,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         compute_sync();
+        FL_STAMP(6);
         if (mma_warp) {
           ptx::tc_fence_after();
           const uint64_t d1 = desc_sw64_k(sOnes);
@@ -434,6 +451,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           if (leader) ptx::umma_commit(&ctl->mma_bar);
         }
         wait_mma();
+        FL_STAMP(7);
         {
           uint32_t raw[16];
           ptx::tmem_ld_32x16(tm + lane_sel + TM_O + (uint32_t)(32 * hh + 16 * half), raw);
@@ -454,6 +472,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         ptx::fence_proxy_async();
         ptx::tc_fence_before();
         compute_sync();
+        FL_STAMP(8);
       }
 
       // ---- proj + LayerScale + shortcut: y = n2 + g1 (o Wp^T + b) ---------------------------------------------
@@ -472,6 +491,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         if (leader) ptx::umma_commit(&ctl->mma_bar);
       }
       wait_mma();
+      FL_STAMP(9);
       {
         const int col0 = sub * CPT;
         uint32_t raw[CPT];
@@ -498,6 +518,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       compute_sync();
+      FL_STAMP(10);
 
       // ---- GLU: hid = val * gelu(gate) of y W1^T + b  (ops.py:135-137; weight rows interleaved value_j, gate_j) ----
       for (int rd = 0; rd < K::GLU_ROUNDS; ++rd) {
@@ -518,6 +539,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           if (leader) ptx::umma_commit(&ctl->mma_bar);
         }
         wait_mma();
+        FL_STAMP(11);
         for (int u = sub; u < ncols / 16; u += 4) {            // 16 accumulator columns -> 8 hid columns = one 16-byte chunk
           uint32_t raw[16];
           ptx::tmem_ld_32x16(tm + lane_sel + TM_GLU + (uint32_t)(16 * u), raw);
@@ -537,6 +559,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         ptx::fence_proxy_async();
         ptx::tc_fence_before();
         compute_sync();
+        FL_STAMP(12);
       }
 
       // ---- MLP out + LayerScale + residual + scatter-back: out[pix] = y + g2 (hid W2^T + b) ---------------------
@@ -555,6 +578,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         if (leader) ptx::umma_commit(&ctl->mma_bar);
       }
       wait_mma();
+      FL_STAMP(13);
       {
         const int col0 = sub * CPT;
         uint32_t raw[CPT];
@@ -574,7 +598,12 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       }
       ptx::tc_fence_before();
       compute_sync();                                        // TMEM, the A tile and ctl->pix/lo/hi are free for the next tile
+      FL_STAMP(14);
     }
+    SAST_STAMP(trc, tid == 0, 17);
+#ifdef SAST_TRACE
+    if (trc && tid == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); trc[19] = smid; trc[20] = ti + 1; }
+#endif
 
     // ---- unselected tokens keep norm1(x)  (SAST.py:251-254): this CTA's share, 4 lanes per token ------------------
     {
@@ -613,6 +642,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
       }
     }
+    SAST_STAMP(trc, tid == 0, 18);
   }
 
   ptx::tc_fence_before();
@@ -642,6 +672,7 @@ static int launch_fused_t(const sast_layer_args& a, const Geom& g, cudaStream_t 
   p.counts = a.sel.counts; p.tile_list = a.sel.tile_list; p.row_tok = a.sel.row_tok; p.row_pix = a.sel.row_pix;
   p.win_row0 = a.sel.win_row0; p.tok_row = a.sel.tok_row;
   p.g = g; p.flavor = a.flavor;
+  p.trace = g_trace_which == 4 ? g_trace : nullptr;
   const size_t smem = 1024 + (size_t)K::W_BYTES + K::A_BYTES + K::R_BYTES + 1024 + sizeof(Ctl);
   static thread_local unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {

@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
   __syncthreads();
   int run_m = 0, run_s = 0, kmax = 0;
   for (int i = 0; i < kSelWarps; ++i) { run_m += red3[i][0]; run_s += red3[i][1]; kmax = max(kmax, red3[i][2]); }
+  const int frame_base = run_s;            // first compacted row of this frame
 
   for (int n0 = 0; n0 < g.N; n0 += blockDim.x) {
     const int n = n0 + threadIdx.x;
@@ -237,26 +238,35 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
   // b*N + j: tiles[2 slot] = first window, tiles[2 slot + 1] = one past its last selected window (first window -1:
   // slot unused).  Slots are dense from j = 0, so a tile-major grid has its idle CTAs last.  The same tiles are
   // appended to the dense work list tile_list as {first compacted row, rows} (counts[3] entries, order arbitrary).
+  // Sequential but cheap: one thread walks the frame's K values in shared memory twice -- first to count its tiles
+  // (ONE atomicAdd then reserves the frame's range of tile_list), then to store them; no load depends on a store.
   if (threadIdx.x == 0) {
-    int start = 0, last = 0, rows = 0, j = 0;
-    auto emit = [&]() {
-      const int slot = b * g.N + j;
-      sel.tiles[2 * slot] = b * g.N + start;
-      sel.tiles[2 * slot + 1] = b * g.N + last;
-      const int k = atomicAdd(&sel.counts[3], 1);
-      sel.tile_list[2 * k] = sel.win_row0[b * g.N + start];
-      sel.tile_list[2 * k + 1] = rows;
-      ++j;
-    };
-    for (int n = 0; n < g.N; ++n) {
-      const int K = kbuf[n];
-      if (K == 0) continue;
-      if (rows > 0 && (rows + K > 128 || n - start >= 128)) { emit(); rows = 0; }
-      if (rows == 0) start = n;
-      rows += K;
-      last = n + 1;
+    int list_base = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      int start = 0, last = 0, rows = 0, j = 0, row0 = 0, acc = 0;
+      auto emit = [&]() {
+        if (pass == 1) {
+          const int slot = b * g.N + j;
+          sel.tiles[2 * slot] = b * g.N + start;
+          sel.tiles[2 * slot + 1] = b * g.N + last;
+          sel.tile_list[2 * (list_base + j)] = frame_base + row0;
+          sel.tile_list[2 * (list_base + j) + 1] = rows;
+        }
+        ++j;
+      };
+#pragma unroll 8
+      for (int n = 0; n < g.N; ++n) {
+        const int K = kbuf[n];
+        if (K == 0) continue;
+        if (rows > 0 && (rows + K > 128 || n - start >= 128)) { emit(); rows = 0; }
+        if (rows == 0) { start = n; row0 = acc; }
+        rows += K; acc += K;
+        last = n + 1;
+      }
+      if (rows > 0) emit();
+      if (pass == 0 && j > 0) list_base = atomicAdd(&sel.counts[3], j);
+      if (pass == 0 && j == 0) break;
     }
-    if (rows > 0) emit();
   }
 }
 

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Phase timeline of layer_fused_kernel CTAs (debug aid): runs one MS-WSA layer at a stage shape of the 1 Mpx B=8
+workload with sast_debug_trace(which=4) armed and prints, per phase of each CTA's SECOND tile, the median / p90 clock
+deltas, plus the per-CTA totals.  Usage: fused_trace.py [stage 1|2] [keep 0..1]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("SAST_B200_LIB", os.path.join(ROOT, "sast_b200", "libsast_b200_trace.so"))
+if not os.path.exists(os.environ["SAST_B200_LIB"]):
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "sast_b200", "csrc"), "trace"])
+sys.path.insert(0, ROOT)
+import sast_b200  # noqa: E402
+from sast_b200 import _lib as L, ops  # noqa: E402
+from sast_b200.config import backbone_config  # noqa: E402
+
+stage = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+keep = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+dev = torch.device("cuda:0")
+B, C = 8, 64 << (stage - 1)
+H, W = 96 >> (stage - 1), 160 >> (stage - 1)
+p0, p1 = 6, 10
+NW = B * (H // p0) * (W // p1)
+net = sast_b200.build_recurrent_backbone(backbone_config((384, 640))).to(dev).eval()
+layer = net.stages[stage - 1].att_blocks[0].att.win_attn
+x = torch.randn(B, H, W, C, device=dev)
+g = torch.Generator().manual_seed(3)
+rho = keep ** 0.5
+wf = (torch.rand(NW, generator=g) < rho).to(torch.uint8) if keep < 1 else torch.ones(NW, dtype=torch.uint8)
+tf = (torch.rand(NW * p0 * p1, generator=g) < rho).to(torch.uint8) if keep < 1 else torch.ones(NW * p0 * p1, dtype=torch.uint8)
+sel = ops.Selection(ops.select_from_flags(wf.to(dev), tf.to(dev), B, H, W, p0, p1, L.WINDOW), B, H, W, p0, p1)
+with torch.no_grad():
+    for _ in range(3):
+        layer.run(x, sel, L.WINDOW, False)
+    torch.cuda.synchronize()
+    buf = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
+    L.lib().sast_debug_trace(buf.data_ptr(), 4)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush.zero_()
+    layer.run(x, sel, L.WINDOW, False)
+    torch.cuda.synchronize()
+    L.lib().sast_debug_trace(None, 0)
+t = buf.view(-1, 32).cpu()
+t = t[t[:, 14] != 0]
+cnt = sel.counts.tolist()
+print(f"stage {stage}: C={C} keep={keep} S={cnt[1]} tiles={cnt[3]} traced CTAs={len(t)} (tiles per CTA {t[:, 20].float().mean():.2f})")
+names = ["gather + LN1/LN2 + sync", "QKV mma -> done (+ shortcut regs)", "sync + QKV epilogue + sync", "S mma -> done",
+         "softmax pass 1 + sync", "softmax pass 2 (P -> TMEM) + sync", "PV mma -> done", "O epilogue + sync", "proj mma -> done",
+         "proj epilogue + sync", "GLU mma -> done", "GLU epilogue + sync", "out mma -> done", "out epilogue + sync"]
+d = (t[:, 1:15] - t[:, 0:14]).float()
+for i, n in enumerate(names):
+    col = d[:, i]
+    print(f"  {n:40s} median {col.median():8.0f}  p90 {col.quantile(0.9):8.0f} clk")
+tot = (t[:, 14] - t[:, 0]).float()
+print(f"  second tile total: median {tot.median():.0f} clk, p90 {tot.quantile(0.9):.0f}")
+for a, b, n in ((15, 16, "entry -> set-up done (incl. PDL wait)"), (16, 17, "all tiles"), (17, 18, "unselected pass"), (15, 18, "kernel total")):
+    col = (t[:, b] - t[:, a]).float()
+    print(f"  [{n:38s}] median {col.median():9.0f}  max {col.max():9.0f} clk")
