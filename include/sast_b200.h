@@ -85,6 +85,8 @@ typedef struct sast_selection {
                                 tiles[2 slot + 1] = one past its last window                   */
   int32_t* tile_list; /* [NW*2] the same tiles as one dense work list (any order): entry k < counts[3] is
                                 {first compacted row, number of rows}; a tile holds whole windows        */
+  int32_t* row_win;   /* [P]    first S entries: (first compacted row of row r's window) << 8 | (K of that window):
+                                the keys a row attends to, without a dependent look-up (needs P < 2^23)        */
 } sast_selection;
 
 /* Bytes of one int32 pool able to hold a sast_selection for (NW, P, B); see sast_selection_bind. */

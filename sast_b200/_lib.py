@@ -32,7 +32,7 @@ class Selection(C.Structure):
     _fields_ = [("counts", C.c_void_p), ("win_K", C.c_void_p), ("win_rank", C.c_void_p),
                 ("win_row0", C.c_void_p), ("sel_win", C.c_void_p), ("tok_row", C.c_void_p),
                 ("row_tok", C.c_void_p), ("row_pix", C.c_void_p), ("win_logit", C.c_void_p),
-                ("tok_keep", C.c_void_p), ("tiles", C.c_void_p), ("tile_list", C.c_void_p)]
+                ("tok_keep", C.c_void_p), ("tiles", C.c_void_p), ("tile_list", C.c_void_p), ("row_win", C.c_void_p)]
 
 
 class ScoreArgs(C.Structure):

@@ -80,7 +80,7 @@ inline int check_geom(const sast_geom& g, int flavor) {
   if (flavor != SAST_FLAT && (g.H % g.p0 != 0 || g.W % g.p1 != 0)) return SAST_E_SHAPE;
   if (flavor == SAST_FLAT && ((long long)g.H * g.W) % (g.p0 * g.p1) != 0) return SAST_E_SHAPE;
   if (g.p0 * g.p1 > 128) return SAST_E_UNSUPPORTED;   // a window's tokens must fit one 128-row tile
-  if ((long long)g.B * g.H * g.W >= (1ll << 31) / 4) return SAST_E_UNSUPPORTED;
+  if ((long long)g.B * g.H * g.W >= (1ll << 23)) return SAST_E_UNSUPPORTED;     // row_win packs a compacted row into 23 bits
   return SAST_OK;
 }
 

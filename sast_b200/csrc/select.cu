@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(kSelThreads) select_tokens_kernel(SelectParams
     if (keep) {
       sel.row_tok[row0 + run + pre] = (int)(q0 + t);
       sel.row_pix[row0 + run + pre] = b * g.H * g.W + frame_pixel(n, t, g.H, g.W, g.p0, g.p1, flavor);
+      sel.row_win[row0 + run + pre] = (row0 << 8) | K;
     }
     run += __popc(bal);
   }
@@ -307,7 +308,7 @@ extern "C" size_t sast_selection_bytes(int32_t B, int32_t NW, int32_t P) {
   n += align_up(8 * 4, 16);                     // counts
   n += 4 * align_up((size_t)NW * 4, 16);        // win_K, win_rank, sel_win, win_logit
   n += align_up(((size_t)NW + 1) * 4, 16);      // win_row0
-  n += 3 * align_up((size_t)P * 4, 16);         // tok_row, row_tok, row_pix
+  n += 4 * align_up((size_t)P * 4, 16);         // tok_row, row_tok, row_pix, row_win
   n += align_up((size_t)P, 16);                 // tok_keep
   n += 2 * align_up((size_t)NW * 8, 16);        // tiles, tile_list
   return n;
@@ -331,13 +332,14 @@ extern "C" int sast_selection_bind(void* pool, int32_t B, int32_t NW, int32_t P,
   out->tok_keep = (uint8_t*)take((size_t)P);
   out->tiles = (int32_t*)take((size_t)NW * 8);
   out->tile_list = (int32_t*)take((size_t)NW * 8);
+  out->row_win = (int32_t*)take((size_t)P * 4);
   return SAST_OK;
 }
 
 static int check_sel(const sast_selection& s) {
   SAST_CHECK_PTR(s.counts); SAST_CHECK_PTR(s.win_K); SAST_CHECK_PTR(s.win_rank); SAST_CHECK_PTR(s.win_row0);
   SAST_CHECK_PTR(s.sel_win); SAST_CHECK_PTR(s.tok_row); SAST_CHECK_PTR(s.row_tok); SAST_CHECK_PTR(s.row_pix);
-  SAST_CHECK_PTR(s.win_logit); SAST_CHECK_PTR(s.tok_keep); SAST_CHECK_PTR(s.tiles); SAST_CHECK_PTR(s.tile_list);
+  SAST_CHECK_PTR(s.win_logit); SAST_CHECK_PTR(s.tok_keep); SAST_CHECK_PTR(s.tiles); SAST_CHECK_PTR(s.tile_list); SAST_CHECK_PTR(s.row_win);
   return SAST_OK;
 }
 

@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
     lib = L.lib()   # _load() already raises on a mismatch; spell it out here
     for which, cls in enumerate((L.Geom, L.Selection, L.ScoreArgs, L.SelectArgs, L.LayerWeights, L.LayerArgs)):
         assert lib.sast_struct_size(which) == ctypes.sizeof(cls), cls.__name__
-    assert ctypes.sizeof(L.Geom) == 24 and ctypes.sizeof(L.Selection) == 96
+    assert ctypes.sizeof(L.Geom) == 24 and ctypes.sizeof(L.Selection) == 104
 
 
 def test_selection_pool_layout():

@@ -44,17 +44,20 @@ with torch.no_grad():
     torch.cuda.synchronize()
     L.lib().sast_debug_trace(None, 0)
 t = buf.view(-1, 32).cpu()
-t = t[t[:, 14] != 0]
+t = t[t[:, 17] != 0]
+t2 = t[t[:, 14] != 0]
 cnt = sel.counts.tolist()
 print(f"stage {stage}: C={C} keep={keep} S={cnt[1]} tiles={cnt[3]} traced CTAs={len(t)} (tiles per CTA {t[:, 20].float().mean():.2f})")
 names = ["gather + LN1/LN2 + sync", "QKV mma -> done (+ shortcut regs)", "sync + QKV epilogue + sync", "S mma -> done",
          "softmax pass 1 + sync", "softmax pass 2 (P -> TMEM) + sync", "PV mma -> done", "O epilogue + sync", "proj mma -> done",
          "proj epilogue + sync", "GLU mma -> done", "GLU epilogue + sync", "out mma -> done", "out epilogue + sync"]
-d = (t[:, 1:15] - t[:, 0:14]).float()
+d = (t2[:, 1:15] - t2[:, 0:14]).float()
+if len(t2) == 0:
+    d = torch.zeros(1, 14)
 for i, n in enumerate(names):
     col = d[:, i]
     print(f"  {n:40s} median {col.median():8.0f}  p90 {col.quantile(0.9):8.0f} clk")
-tot = (t[:, 14] - t[:, 0]).float()
+tot = (t2[:, 14] - t2[:, 0]).float() if len(t2) else torch.zeros(1)
 print(f"  second tile total: median {tot.median():.0f} clk, p90 {tot.quantile(0.9):.0f}")
 for a, b, n in ((15, 16, "entry -> set-up done (incl. PDL wait)"), (16, 17, "all tiles"), (17, 18, "unselected pass"), (15, 18, "kernel total")):
     col = (t[:, b] - t[:, a]).float()
