@@ -242,13 +242,19 @@ def run_ours(args, workload):
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    numa = parallel.bind_to_gpu_numa(local)          # before the pinned buffers below are allocated
     parallel.init("nccl", device)
 
     B, res = workload["batch"], workload["res"]
     seq = workload.get("seq", 1)                    # frames per stream and step (1: benchmark.py protocol; 21: streaming)
     net = build_net(workload, args.precision, device)
     n_buf = 4
-    host = [t.pin_memory() for t in make_inputs(B, res, args.sparsity, n_buf, seed=1 + rank, kind=args.input)]   # every rank: its own frames
+    raw = make_inputs(B, res, args.sparsity, n_buf, seed=1 + rank, kind=args.input)        # every rank: its own frames
+    # Host side of the product API: the event histogram bit-packed (1 bit per bin for the binary benchmark input, 4 bits
+    # for counts clipped at 10), packed once OUTSIDE the timed region (a data loader's job); unpacked on the device INSIDE it.
+    bits = {"auto": 1 if args.input == "binary" else 4, "0": 0, "1": 1, "4": 4}[args.pack]
+    import sast_b200
+    host = [(sast_b200.pack_events(t, bits) if bits else t).pin_memory() for t in raw]
     dev_in = [t.to(device) for t in host]
     lib = L.lib()
 
@@ -309,7 +315,7 @@ def run_ours(args, workload):
     nrun = len(runners)
     ev_copied = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
-    stage_in = [runners[k].x for k in range(2)] if nrun == 2 else [torch.empty_like(dev_in[0]) for _ in range(2)]
+    stage_in = [runners[k].x for k in range(2)] if nrun == 2 else [dev_in[0].clone() for _ in range(2)]
     main = torch.cuda.current_stream(device)
     for e in ev_done:
         e.record(main)
@@ -343,7 +349,7 @@ def run_ours(args, workload):
 
     if rank == 0:
         from roofline import roofline_block            # measured live, same process
-        roof = roofline_block(net, workload, args, device)
+        roof = roofline_block(net, workload, args, device, ms_per_step=t_res / args.steps * 1e3)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -361,13 +367,18 @@ def run_ours(args, workload):
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": workload["desc"], "batch_per_gpu": B, "global_batch": B * world,
                        "frames_per_step_per_gpu": B * seq, "sparsity": args.sparsity,
-                       "input": "uint8 (rand > sparsity), benchmark.py:58-60" if args.input == "binary" else "uint8 Poisson counts clipped at 10, 1 - sparsity of the bins non-empty",
+                       "input": ("(rand > sparsity), benchmark.py:58-60" if args.input == "binary" else "Poisson counts clipped at 10, 1 - sparsity of the bins non-empty")
+                                + (f", {bits} bit/bin packed" if bits else ", uint8"),
                        "selected_tokens_per_stage": counts, "cuda_graph": not args.no_graph,
                        "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": f"inputs rotate over {n_buf} buffers; per-step working set (activations + workspaces) exceeds the 126 MB L2"},
             "e2e": {"value": frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": host[0].numel() * seq * world,
                     "d2h_bytes_per_step": 64 * seq * world, "ms_per_step": t_e2e / args.steps * 1e3,
-                    "pipeline": "H2D on a copy stream, double buffered against the compute stream"},
+                    "pipeline": "H2D on a copy stream, double buffered against the compute stream",
+                    "host_format": (f"event histogram bit-packed {bits} bit/bin (sast_b200.pack_events, outside the timed region); "
+                                    "unpacked on the device inside it" if bits else "uint8, 1 byte/bin"),
+                    "d2h": "per-layer selected-token counts (the backbone protocol's only host-visible result, benchmark.py:33-42)",
+                    "numa": numa},
             "gpu_launches": int(launches_per_frame_batch) * seq * args.steps,
             "gpu_launches_per_frame_batch": int(launches_per_frame_batch),
             "clocks": clocks,
@@ -393,6 +404,8 @@ def main():
     ap.add_argument("--input", default="binary", choices=["binary", "poisson"],
                     help="binary: (rand > sparsity) as benchmark.py does; poisson: event counts clipped at 10, 1 - sparsity non-empty")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--pack", default="auto", choices=["auto", "0", "1", "4"],
+                    help="bits per bin of the host / device input (0: plain uint8; auto: 1 for --input binary, 4 for poisson)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -104,6 +104,16 @@ int sast_nonzero_ratio(const void* x, int32_t dtype, int32_t B, int32_t Cin, int
                        float* r, int32_t* scratch /* [B*Cin*4] ints, zero on entry, left zero on exit */, void* stream);
 
 /*
+ * Bit-packed input: the event histogram as BITS (1 or 4) bits per bin, packed along x, little endian (bits = 1: bit k of
+ * byte j is column 8 j + k; bits = 4: low nibble of byte j = column 2 j) -- [B,Cin,H,W*bits/8] bytes.  Event histograms are
+ * binary in benchmark.py:58-60 and clipped at count_cutoff 10 in the datasets (representations.py), so 1 / 4 bits are
+ * lossless; the host->device copy shrinks 8x / 2x.  One pass unpacks to uint8 [B,Cin,H,W] (x_out, the stem's input) and
+ * produces r exactly as sast_nonzero_ratio does.  W % 8 == 0.
+ */
+int sast_unpack_nonzero_ratio(const uint8_t* packed, int32_t bits, int32_t B, int32_t Cin, int32_t H, int32_t W,
+                              uint8_t* x_out, float* r, int32_t* scratch, void* stream);
+
+/*
  * a4  scoring module + STP weighting.  ref: SAST.py:105-119, 305-328.
  *   x0 = x + pos;  ctrl = exp(Wc) (r + 1e-6);  s = relu(x0 Ws^T + bs)
  *   xw = sigmoid(ctrl) sigmoid(s) x0   (NHWC, same layout as x)

@@ -10,6 +10,7 @@ from .sast import (SAST_block, MS_WSA, PositiveLinear, LayerScale, MLP, GLU, Laz
                    get_score_index_with_padding)
 from .backbone import (RNNDetector, RNNDetectorStage, SASTAttentionPairCl, PositionEmbeddingSine,
                        ConvDownsampling_Cf2Cl, DWSConvLSTM2d, non_zero_ratio, build_recurrent_backbone)
+from .ops import PackedEvents, pack_events
 from .config import Config, attention_config, backbone_config
 from .yolox import YoloXDetector, YOLOPAFPN, YOLOXHead, postprocess, detector_config
 

@@ -78,6 +78,7 @@ def _load():
         "sast_selection_bytes": (sz, [i32, i32, i32]),
         "sast_selection_bind": (C.c_int, [vp, i32, i32, i32, C.POINTER(Selection)]),
         "sast_nonzero_ratio": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+        "sast_unpack_nonzero_ratio": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "sast_score_fwd": (C.c_int, [C.POINTER(ScoreArgs), vp]),
         "sast_select": (C.c_int, [C.POINTER(SelectArgs), vp]),
         "sast_select2": (C.c_int, [C.POINTER(SelectArgs), i32, C.POINTER(Selection), vp]),
@@ -108,7 +109,7 @@ def _load():
 
 
 EXPORTS = ("sast_abi_version", "sast_build_info", "sast_struct_size", "sast_launch_count", "sast_selection_bytes", "sast_selection_bind",
-           "sast_nonzero_ratio", "sast_score_fwd", "sast_select", "sast_select2", "sast_layer_workspace_bytes",
+           "sast_nonzero_ratio", "sast_unpack_nonzero_ratio", "sast_score_fwd", "sast_select", "sast_select2", "sast_layer_workspace_bytes",
            "sast_layer_fwd", "sast_layer_is_fused", "sast_gather", "sast_scatter", "sast_gemm_bf16", "sast_gemm_bf16_glu", "sast_pad_input", "sast_pad_nhwc",
            "sast_layernorm", "sast_lstm_gates", "sast_lstm_fwd", "sast_stem_fwd", "sast_debug_trace")
 

@@ -344,7 +344,10 @@ class RNNDetector(BaseDetector):
         assert len(prev_states) == self.num_stages
         states: List[Tuple[Tensor, Tensor]] = []
         output: Dict[int, Tensor] = {}
-        r = non_zero_ratio(x)
+        if isinstance(x, ops.PackedEvents):      # bit-packed histogram: unpacked in the pass that computes r
+            x, r = ops.unpack_nonzero_ratio(x.data, x.bits, x.width)
+        else:
+            r = non_zero_ratio(x)
         P = []            # (the stem casts its own input: no separate x.float() pass, ref sast_rnn.py:153)
         for stage_idx, stage in enumerate(self.stages):
             x, state, p = stage(x, prev_states[stage_idx], token_mask if stage_idx == 0 else None, r[:, stage_idx])

@@ -97,6 +97,83 @@ __global__ void __launch_bounds__(256) nonzero_count_kernel(const T* __restrict_
   }
 }
 
+
+// Bit-packed event histograms (sast_unpack_nonzero_ratio): the same band decomposition, reading BITS (1 or 4) bits per
+// bin and writing the bins back as uint8 for the stem -- the unpack rides on the pass that has to read the input anyway.
+// Packing runs along x, little endian: BITS = 1: bit k of byte j is column 8 j + k; BITS = 4: the low nibble of byte j is
+// column 2 j, the high nibble column 2 j + 1.
+template <int BITS>
+__global__ void __launch_bounds__(256) unpack_count_kernel(const uint8_t* __restrict__ packed, int H, int W,
+                                                            uint8_t* __restrict__ out, int* __restrict__ counts) {
+  pdl_entry();
+  extern __shared__ float cell0[];        // [8][w0] level-0 maxima of this band
+  __shared__ int red[4][8];
+  const int plane = blockIdx.x, band = blockIdx.y;
+  const int pitch = W * BITS / 8;         // bytes per packed row
+  const uint8_t* xp = packed + (size_t)plane * H * pitch;
+  uint8_t* op = out + (size_t)plane * H * W;
+  const int h0 = H / 4, w0 = W / 4;
+  int cnt[4] = {0, 0, 0, 0};
+  const int rows0 = min(8, h0 - band * 8);
+  for (int i = threadIdx.x; i < rows0 * w0; i += blockDim.x) {
+    const int cy = i / w0, cx = i - cy * w0;
+    const int y0 = (band * 8 + cy) * 4;
+    uint32_t w[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {        // 4 independent row loads in flight; 4 bins -> one uchar4
+      const uint8_t* row = xp + (size_t)(y0 + rr) * pitch;
+      if (BITS == 1) {
+        const uint32_t nib = (row[cx >> 1] >> ((cx & 1) * 4)) & 15u;
+        w[rr] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+      } else {
+        const uint32_t h = *reinterpret_cast<const uint16_t*>(row + cx * 2);
+        w[rr] = (h & 15u) | ((h & 0xF0u) << 4) | ((h & 0xF00u) << 8) | ((h & 0xF000u) << 12);
+      }
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      *reinterpret_cast<uint32_t*>(op + (size_t)(y0 + rr) * W + cx * 4) = w[rr];
+      any |= w[rr];
+    }
+    const float m = any ? 1.0f : 0.0f;      // bins are >= 0: "max != 0" is "any bin set"
+    cell0[cy * w0 + cx] = m;
+    cnt[0] += any != 0;
+  }
+  // rows of the plane below the last complete 4-row cell (H % 4) hold no cell but must still be unpacked
+  if (band == gridDim.y - 1) {
+    for (int y = h0 * 4; y < H; ++y)
+      for (int x = threadIdx.x; x < W; x += blockDim.x)
+        op[(size_t)y * W + x] = BITS == 1 ? ((xp[(size_t)y * pitch + (x >> 3)] >> (x & 7)) & 1u)
+                                          : ((xp[(size_t)y * pitch + (x >> 1)] >> ((x & 1) * 4)) & 15u);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int lvl = 1; lvl < 4; ++lvl) {
+    const int s = 1 << lvl;
+    const int rows = rows0 / s, cols = w0 / s;
+    for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+      const int cy = i / cols, cx = i - cy * cols;
+      float m = 0.f;
+      for (int yy = 0; yy < s; ++yy)
+        for (int xx = 0; xx < s; ++xx) m = fmaxf(m, cell0[(cy * s + yy) * w0 + cx * s + xx]);
+      cnt[lvl] += (m != 0.0f);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int lvl = 0; lvl < 4; ++lvl) {
+    const int v = warp_sum_i(cnt[lvl]);
+    if (lane == 0) red[lvl][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    int tot = 0;
+    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) tot += red[threadIdx.x][w2];
+    if (tot) atomicAdd(&counts[plane * 4 + threadIdx.x], tot);
+  }
+}
+
 __global__ void nonzero_finalize_kernel(int* __restrict__ counts, int planes, int B, int Cin, float f0, float f1, float f2, float f3,
                                         float* __restrict__ r) {
   pdl_entry();
@@ -132,6 +209,32 @@ extern "C" int sast_nonzero_ratio(const void* x, int32_t dtype, int32_t B, int32
     case SAST_F32: sast::launch_k(sast::nonzero_count_kernel<float>, grid, block, smem, st, (const float*)x, H, W, scratch); break;
     default: return SAST_E_UNSUPPORTED;
   }
+  SAST_LAUNCH_CHECK();
+  sast::launch_k(sast::nonzero_finalize_kernel, dim3((planes * 4 + 127) / 128), dim3(128), 0, st, scratch, planes, B, Cin, f[0], f[1], f[2],
+                 f[3], r);
+  SAST_LAUNCH_CHECK();
+  return SAST_OK;
+}
+
+// Bit-packed twin of sast_nonzero_ratio: unpacks to uint8 [B,Cin,H,W] (the stem's input) and computes r in the same pass.
+extern "C" int sast_unpack_nonzero_ratio(const uint8_t* packed, int32_t bits, int32_t B, int32_t Cin, int32_t H, int32_t W,
+                                         uint8_t* x_out, float* r, int32_t* scratch, void* stream) {
+  SAST_CHECK_PTR(packed); SAST_CHECK_PTR(x_out); SAST_CHECK_PTR(r); SAST_CHECK_PTR(scratch);
+  if (B <= 0 || Cin <= 0 || H < 32 || W < 32 || W % 8 != 0) return SAST_E_SHAPE;
+  if (bits != 1 && bits != 4) return SAST_E_UNSUPPORTED;
+  float f[4];
+  for (int l = 0; l < 4; ++l) {
+    const long long cs = 4ll << l;
+    const double numel = (double)B * Cin * (H / cs) * (W / cs);
+    f[l] = (float)((double)B / numel);
+  }
+  const size_t smem = (size_t)8 * (W / 4) * sizeof(float);
+  if (smem > 48 * 1024) return SAST_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int planes = B * Cin;
+  const dim3 grid(planes, (H / 4 + 7) / 8), block(256);
+  if (bits == 1) sast::launch_k(sast::unpack_count_kernel<1>, grid, block, smem, st, packed, H, W, x_out, scratch);
+  else sast::launch_k(sast::unpack_count_kernel<4>, grid, block, smem, st, packed, H, W, x_out, scratch);
   SAST_LAUNCH_CHECK();
   sast::launch_k(sast::nonzero_finalize_kernel, dim3((planes * 4 + 127) / 128), dim3(128), 0, st, scratch, planes, B, Cin, f[0], f[1], f[2],
                  f[3], r);

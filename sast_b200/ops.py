@@ -62,6 +62,93 @@ def _(x):
     return x.new_empty(4, x.shape[0], x.shape[1], dtype=torch.float32).permute(1, 0, 2)
 
 
+class PackedEvents:
+    """Event histogram packed ``bits`` (1 or 4) bits per bin along x, little endian: ``data`` is uint8
+    [B, Cin, H, W * bits // 8].  Binary histograms (benchmark.py:58-60) fit 1 bit, dataset histograms (clipped at
+    count_cutoff = 10, data/utils/representations.py) 4 bits, so the host->device copy shrinks 8x / 2x without loss;
+    ``RNNDetector.forward`` accepts it in place of the [B, Cin, H, W] tensor and unpacks on the device in the pass
+    that computes the scene sparsity ratio.  Tensor-like enough for the runners (clone / copy_ / to / pin_memory)."""
+
+    def __init__(self, data: Tensor, bits: int, width: int):
+        assert bits in (1, 4) and data.dtype == torch.uint8 and data.dim() == 4
+        assert width % 8 == 0 and data.shape[-1] == width * bits // 8
+        self.data, self.bits, self.width = data, bits, width
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape[:3]) + (self.width,)
+
+    @property
+    def device(self):
+        return self.data.device
+
+    @property
+    def is_cuda(self):
+        return self.data.is_cuda
+
+    def numel(self):
+        """bytes actually held (what a host->device copy moves)"""
+        return self.data.numel()
+
+    def data_ptr(self):
+        return self.data.data_ptr()
+
+    def clone(self):
+        return PackedEvents(self.data.clone(), self.bits, self.width)
+
+    def to(self, *a, **k):
+        return PackedEvents(self.data.to(*a, **k), self.bits, self.width)
+
+    def pin_memory(self):
+        return PackedEvents(self.data.pin_memory(), self.bits, self.width)
+
+    def copy_(self, other, non_blocking=False):
+        assert isinstance(other, PackedEvents) and (other.bits, other.width) == (self.bits, self.width)
+        self.data.copy_(other.data, non_blocking=non_blocking)
+        return self
+
+    def unpack_reference(self) -> Tensor:
+        """uint8 [B, Cin, H, W] by plain torch ops (tests; works on CPU)."""
+        d = self.data.to(torch.int32)
+        if self.bits == 1:
+            out = torch.stack([(d >> k) & 1 for k in range(8)], dim=-1)
+        else:
+            out = torch.stack([d & 15, (d >> 4) & 15], dim=-1)
+        return out.reshape(*self.data.shape[:3], self.width).to(torch.uint8)
+
+
+def pack_events(x: Tensor, bits: int) -> PackedEvents:
+    """[B, Cin, H, W] integer histogram (values < 2**bits, W % 8 == 0) -> :class:`PackedEvents` on x's device."""
+    assert bits in (1, 4) and x.dim() == 4 and x.shape[-1] % 8 == 0
+    assert int(x.max()) < (1 << bits) and int(x.min()) >= 0, f"values do not fit {bits} bit(s)"
+    n = 8 // bits
+    d = x.to(torch.int32).reshape(*x.shape[:3], x.shape[-1] // n, n)
+    w = torch.zeros(d.shape[:-1], dtype=torch.int32, device=x.device)
+    for k in range(n):
+        w |= d[..., k] << (k * bits)
+    return PackedEvents(w.to(torch.uint8).contiguous(), bits, x.shape[-1])
+
+
+@torch.library.custom_op("sast::unpack_nonzero_ratio", mutates_args=())
+def unpack_nonzero_ratio(data: Tensor, bits: int, width: int) -> Tuple[Tensor, Tensor]:
+    """packed uint8 [B,Cin,H,W*bits/8] -> (x uint8 [B,Cin,H,W], r [B,4,Cin]); see sast_unpack_nonzero_ratio."""
+    L.require_cuda(data, "data")
+    data = data.contiguous()
+    B, Cin, H, _ = data.shape
+    x = torch.empty(B, Cin, H, width, device=data.device, dtype=torch.uint8)
+    r = torch.empty(4, B, Cin, device=data.device, dtype=torch.float32)
+    scratch = torch.zeros(B * Cin * 4, device=data.device, dtype=torch.int32)
+    L.run(data.device, "sast_unpack_nonzero_ratio", data.data_ptr(), int(bits), B, Cin, H, int(width), x.data_ptr(),
+          r.data_ptr(), scratch.data_ptr())
+    return x, r.permute(1, 0, 2)
+
+
+@unpack_nonzero_ratio.register_fake
+def _(data, bits, width):
+    B, Cin, H, _ = data.shape
+    return (data.new_empty(B, Cin, H, width), data.new_empty(4, B, Cin, dtype=torch.float32).permute(1, 0, 2))
+
+
 # --------------------------------------------------------------------------------------------
 # a4  scoring + STP weighting
 # --------------------------------------------------------------------------------------------

@@ -26,6 +26,43 @@ def init(backend: str, device=None):
     return rank, world, local
 
 
+def parse_cpulist(text: str) -> List[int]:
+    """'0-15,32-47' -> [0..15, 32..47] (the sysfs cpulist format)."""
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin this process to the CPUs that are NUMA-local to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE
+    any pinned host buffer is allocated: page-locked memory is then placed on the GPU's own NUMA node, and with one rank
+    per GPU the ranks' host->device copies stop sharing one socket's memory controllers.  Best effort: returns what it
+    did; never raises."""
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(f"{base}/local_cpulist") as f:
+            cpus = parse_cpulist(f.read())
+        try:
+            with open(f"{base}/numa_node") as f:
+                info["numa_node"] = int(f.read().strip())
+        except OSError:
+            pass
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed), pci=bdf)
+    except Exception as exc:      # noqa: BLE001 -- containers may hide sysfs; the run goes on unbound
+        info["error"] = f"{type(exc).__name__}: {exc}"
+    return info
+
+
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous shard [start, stop) of n_items for `rank`; the first n_items % world ranks get one more."""
     base, rem = divmod(n_items, world)

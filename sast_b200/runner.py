@@ -17,7 +17,7 @@ Tensor = torch.Tensor
 
 class GraphedBackbone:
     def __init__(self, net, example_x: Tensor, recurrent: bool = False, warmup: int = 3):
-        assert example_x.is_cuda, "GraphedBackbone needs CUDA tensors"
+        assert example_x.is_cuda, "GraphedBackbone needs CUDA tensors"     # a Tensor or a sast_b200.PackedEvents
         self.net = net
         self.recurrent = recurrent
         self.x = example_x.clone()

@@ -122,3 +122,20 @@ def test_gemm_glu_epilogue(M, I, K):
     bi = torch.stack((b[:I], b[I:]), dim=1).reshape(-1)
     got = ops.gemm_bf16_glu(A.to(DEV), Wi.to(DEV), bi.to(DEV)).float().cpu()
     assert ((got - ref).abs() / (ref.abs() + 1.0)).max() < 1e-2      # bf16 output: 2^-8 relative
+
+
+@pytest.mark.parametrize("bits,B,H,W", [(1, 8, 384, 640), (4, 8, 384, 640), (1, 2, 66, 72), (4, 3, 240, 304)])
+def test_unpack_nonzero_ratio(bits, B, H, W):
+    """Bit-packed input path: unpacked histogram and r bit-identical to the uint8 path (and hence to the reference)."""
+    import sast_b200
+    from sast_b200 import ops
+    g = torch.Generator().manual_seed(bits + H)
+    if bits == 1:
+        x = (torch.rand(B, 20, H, W, generator=g) > 0.97).to(torch.uint8)
+    else:
+        x = torch.poisson(torch.full((B, 20, H, W), 0.05), generator=g).clamp_(max=10).to(torch.uint8)
+    x[0, 3] = 0                                            # an empty bin plane
+    pk = sast_b200.pack_events(x, bits).to("cuda:0")
+    xu, r = ops.unpack_nonzero_ratio(pk.data, pk.bits, pk.width)
+    assert torch.equal(xu.cpu(), x)
+    assert torch.equal(r, ops.nonzero_ratio(x.to("cuda:0")))

@@ -173,3 +173,19 @@ def test_dropin_shadows_reference_modules():
     mods = line[0].split()
     assert mods[0] == "sast_b200.backbone" and mods[1] == "sast_b200.sast" and mods[2] == "sast_b200.backbone"
     assert mods[3].startswith("models.detection.yolox_extension")
+
+
+def test_pack_events_round_trip():
+    """Bit-packed histograms (PackedEvents): lossless for binary / clipped counts, byte layout as the header states."""
+    import sast_b200
+    g = torch.Generator().manual_seed(4)
+    xb = (torch.rand(2, 3, 8, 32, generator=g) > 0.7).to(torch.uint8)
+    xc = torch.randint(0, 11, (2, 3, 8, 32), generator=g, dtype=torch.uint8)
+    pb, pc = sast_b200.pack_events(xb, 1), sast_b200.pack_events(xc, 4)
+    assert pb.data.shape == (2, 3, 8, 4) and pc.data.shape == (2, 3, 8, 16) and pb.shape == pc.shape == (2, 3, 8, 32)
+    assert torch.equal(pb.unpack_reference(), xb) and torch.equal(pc.unpack_reference(), xc)
+    # little endian along x: bit k of byte j = column 8j + k; low nibble = even column
+    assert int(pb.data[0, 0, 0, 1]) == sum(int(xb[0, 0, 0, 8 + k]) << k for k in range(8))
+    assert int(pc.data[1, 2, 3, 5]) == int(xc[1, 2, 3, 10]) | (int(xc[1, 2, 3, 11]) << 4)
+    with pytest.raises(AssertionError):
+        sast_b200.pack_events(xc, 1)            # counts do not fit one bit
