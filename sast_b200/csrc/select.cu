@@ -180,8 +180,10 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
   const int flavor = pick_flavor(p, blockIdx.z);
   const sast_selection& sel = pick_sel(p, blockIdx.z);
   const Geom g = make_geom(p.a.g, flavor);
-  extern __shared__ int kbuf[];          // [N] K of this frame's windows (for the tile packer)
+  extern __shared__ int pre[];           // [N+1] exclusive prefix of K inside this frame, then [N] next-tile pointers
+  int* const nxt = pre + g.N + 1;
   __shared__ int ws[kSelWarps][2];
+  __shared__ int pack_n, pack_base;
   __shared__ int red3[kSelWarps][3];
   const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
@@ -204,12 +206,12 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
     const bool in = n < g.N;
     const int kept = in ? (sel.win_rank[w] >= 0) : 0;
     const int K = in ? sel.win_K[w] : 0;
-    if (in) kbuf[n] = K;
     kmax = max(kmax, K);
     int em, es, tm, ts;
     block_excl_scan2(kept, K, em, es, tm, ts, ws);
     if (in) {
       sel.win_row0[w] = run_s + es;
+      pre[n] = run_s + es - frame_base;
       if (kept) {
         sel.win_rank[w] = run_m + em;
         sel.sel_win[run_m + em] = w;
@@ -233,40 +235,47 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
     }
   }
   __syncthreads();
-  // greedy packing of consecutive windows of this frame into attention tiles of <= 128 rows and <= 128 windows
-  // (a tile starts at a selected window; empty windows never open one).  The j-th tile of frame b goes to slot
-  // b*N + j: tiles[2 slot] = first window, tiles[2 slot + 1] = one past its last selected window (first window -1:
-  // slot unused).  Slots are dense from j = 0, so a tile-major grid has its idle CTAs last.  The same tiles are
-  // appended to the dense work list tile_list as {first compacted row, rows} (counts[3] entries, order arbitrary).
-  // Sequential but cheap: one thread walks the frame's K values in shared memory twice -- first to count its tiles
-  // (ONE atomicAdd then reserves the frame's range of tile_list), then to store them; no load depends on a store.
-  if (threadIdx.x == 0) {
-    int list_base = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      int start = 0, last = 0, rows = 0, j = 0, row0 = 0, acc = 0;
-      auto emit = [&]() {
-        if (pass == 1) {
-          const int slot = b * g.N + j;
-          sel.tiles[2 * slot] = b * g.N + start;
-          sel.tiles[2 * slot + 1] = b * g.N + last;
-          sel.tile_list[2 * (list_base + j)] = frame_base + row0;
-          sel.tile_list[2 * (list_base + j) + 1] = rows;
-        }
-        ++j;
-      };
-#pragma unroll 8
-      for (int n = 0; n < g.N; ++n) {
-        const int K = kbuf[n];
-        if (K == 0) continue;
-        if (rows > 0 && (rows + K > 128 || n - start >= 128)) { emit(); rows = 0; }
-        if (rows == 0) { start = n; row0 = acc; }
-        rows += K; acc += K;
-        last = n + 1;
-      }
-      if (rows > 0) emit();
-      if (pass == 0 && j > 0) list_base = atomicAdd(&sel.counts[3], j);
-      if (pass == 0 && j == 0) break;
+  // Greedy packing of consecutive windows of this frame into attention tiles of <= 128 rows and <= 128 windows.  The
+  // j-th tile of frame b goes to slot b*N + j: tiles[2 slot] = first window, tiles[2 slot + 1] = one past its last
+  // window (first window -1: slot unused); slots are dense from j = 0, so a tile-major grid has its idle CTAs last.
+  // The same tiles are appended to the dense work list tile_list as {first compacted row, rows} (counts[3] entries,
+  // order arbitrary).  Parallel in three steps: (1) every window n finds by binary search on the prefix sums where a
+  // tile STARTING at n would end; (2) one thread follows those pointers from window 0 -- one shared-memory load per
+  // tile instead of a walk over all windows -- and claims the slots; (3) one atomicAdd reserves the frame's range of
+  // tile_list, which all threads then fill.
+  if (threadIdx.x == 0) pre[g.N] = run_s - frame_base;
+  __syncthreads();
+  for (int n = threadIdx.x; n < g.N; n += blockDim.x) {
+    int lo = n + 1, hi = min(n + 128, g.N);          // largest m in [lo, hi] with pre[m] - pre[n] <= 128 (m = n + 1 always fits: K <= T <= 128)
+    const int p0 = pre[n];
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (pre[mid] - p0 <= 128) lo = mid; else hi = mid - 1;
     }
+    nxt[n] = lo;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int j = 0;
+    for (int n = 0; n < g.N;) {
+      const int m = nxt[n];
+      if (pre[m] > pre[n]) {                          // tiles made of dropped windows only are not emitted
+        const int slot = b * g.N + j;
+        sel.tiles[2 * slot] = b * g.N + n;
+        sel.tiles[2 * slot + 1] = b * g.N + m;
+        ++j;
+      }
+      n = m;
+    }
+    pack_n = j;
+    pack_base = j ? atomicAdd(&sel.counts[3], j) : 0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < pack_n; j += blockDim.x) {
+    const int slot = b * g.N + j;
+    const int n = sel.tiles[2 * slot] - b * g.N, m = sel.tiles[2 * slot + 1] - b * g.N;
+    sel.tile_list[2 * (pack_base + j)] = frame_base + pre[n];
+    sel.tile_list[2 * (pack_base + j) + 1] = pre[m] - pre[n];
   }
 }
 
@@ -359,7 +368,7 @@ extern "C" int sast_select2(const sast_select_args* a, int32_t flavor_b, const s
   else if (a->mode == SAST_SEL_FLAGS) { SAST_CHECK_PTR(a->win_flag); SAST_CHECK_PTR(a->tok_flag); }
   else return SAST_E_UNSUPPORTED;
   const sast::Geom g = sast::make_geom(a->g, a->flavor);
-  const size_t smem = (size_t)g.N * 4;
+  const size_t smem = ((size_t)g.N * 2 + 1) * 4;
   if (smem > 40 * 1024) return SAST_E_UNSUPPORTED;
   sast::SelectParams p;
   p.a = *a;

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       // input words of one k-block: 4 groups x {left, centre, right} aligned words; the NEXT k-block's words are
       // requested before the current ones are converted (software pipelining: the loads never sit on the
       // critical path of the conversion)
-      uint32_t w0[4], w1[4], w2[4], n0[4], n1[4], n2[4];
+      uint32_t w0[4], w1[4], w2[4], n0[4], n1[4], n2[4], m0[4], m1[4], m2[4];
       auto load_block = [&](int kb, uint32_t (&a0)[4], uint32_t (&a1)[4], uint32_t (&a2)[4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -113,10 +113,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
           a2[j] = row[ox + 1 < Wo ? ox + 1 : ox];               // only tap 7 (zero weight) reads it
         }
       };
+      // prefetch distance 2: the producers are bound by the latency of these loads (first touch of the input comes from
+      // DRAM), not by instruction issue, so two k-blocks of words are kept in flight behind the one being converted
       load_block(0, w0, w1, w2);
+      if (nkb > 1) load_block(1, n0, n1, n2);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t s = it % ST_STAGES, round = it / ST_STAGES;
-        if (kb + 1 < nkb) load_block(kb + 1, n0, n1, n2);
+        if (kb + 2 < nkb) load_block(kb + 2, m0, m1, m2);
         ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
         uint8_t* st = base + (size_t)s * stage_bytes;
         if (warp == 0 && ptx::elect_one()) {     // warp-uniform operands, elected lane: no R2UR waterfall per TMA
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&sm->full[s]);        // one arrive per warp: 256 serialized smem atomics per k-block otherwise
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { w0[j] = n0[j]; w1[j] = n1[j]; w2[j] = n2[j]; }
+        for (int j = 0; j < 4; ++j) { w0[j] = n0[j]; w1[j] = n1[j]; w2[j] = n2[j]; n0[j] = m0[j]; n1[j] = m1[j]; n2[j] = m2[j]; }
       }
     }
   } else if (warp == 8) {
