@@ -211,6 +211,29 @@ int sast_layer_fwd(const sast_layer_args* a, void* stream);
  * in shared and tensor memory.  Such calls need no workspace (workspace may be NULL).  0: the multi-kernel chain. */
 int32_t sast_layer_is_fused(int32_t C, int32_t I, int32_t precision, int32_t enable_cb);
 
+/*
+ * Backward twins for the training configuration (the reference trains through stock autograd: train.py,
+ * modules/detection.py:113-221).  Recompute based: nothing is saved by the forward; fp32 throughout.
+ * The selection is a constant of the backward (SAST.py's index tensors carry no gradient).
+ *
+ * sast_layer_bwd: a = the forward's arguments (x, selection, fp32 weights; a.out unused; a.workspace >=
+ *   sast_layer_bwd_workspace_bytes); d_out [B,H,W,C] -> dx [B,H,W,C] and the parameter gradients, ACCUMULATED into the
+ *   buffers of `grads` (zero them first; same shapes / row order as sast_layer_weights, mlp1 rows interleaved; an
+ *   entry may be NULL where the weight is).  enable_cb is not supported (SAST_E_UNSUPPORTED); needs 2 I >= 3 C.
+ * sast_score_bwd: a = the forward's arguments (xw / tok_score / scratch unused); d_xw -> dx and, for a first block,
+ *   d to_scores.weight [C,C] / .bias [C] (accumulated, zero them first) and d to_controls.weight [C,n_bins] (written).
+ *   tok_score is not differentiable (selection), as in the reference.
+ */
+typedef struct sast_layer_grads {
+  float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  float *qkv_w, *qkv_b, *proj_w, *proj_b, *gamma1, *gamma2, *mlp1_w, *mlp1_b, *mlp2_w, *mlp2_b;
+} sast_layer_grads;
+size_t sast_layer_bwd_workspace_bytes(int64_t P, int32_t C, int32_t I);
+int sast_layer_bwd(const sast_layer_args* a, const float* d_out, float* dx, const sast_layer_grads* grads, void* stream);
+size_t sast_score_bwd_workspace_bytes(int64_t P, int32_t C, int32_t B);
+int sast_score_bwd(const sast_score_args* a, const float* d_xw, float* dx, float* d_score_w, float* d_score_b,
+                   float* d_ctrl_w, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Standalone gather / scatter of the selected tokens (a9 / a13), for tests and the
  * HBM-roofline microbenchmark: rows [S,C] <-> map tokens, through sel.row_tok. */
 int sast_gather(const sast_geom* g, int32_t flavor, const float* x, const sast_selection* sel,
@@ -282,7 +305,7 @@ void sast_debug_trace(long long* buf, int32_t which /* 1 attention, 2 GEMM, 3 sc
 /* Library / build info. */
 int sast_abi_version(void);
 /* sizeof of an ABI struct: 0 sast_geom, 1 sast_selection, 2 sast_score_args, 3 sast_select_args,
- * 4 sast_layer_weights, 5 sast_layer_args (lets a foreign-language binding verify its mirror). */
+ * 4 sast_layer_weights, 5 sast_layer_args, 6 sast_layer_grads (lets a foreign-language binding verify its mirror). */
 size_t sast_struct_size(int32_t which);
 const char* sast_build_info(void);
 

@@ -62,6 +62,12 @@ class LayerArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class LayerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_w", "ln1_b", "ln2_w", "ln2_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "gamma1", "gamma2",
+        "mlp1_w", "mlp1_b", "mlp2_w", "mlp2_b")]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
@@ -85,6 +91,10 @@ def _load():
         "sast_layer_workspace_bytes": (sz, [i64, i32, i32, i32, i32]),
         "sast_layer_fwd": (C.c_int, [C.POINTER(LayerArgs), vp]),
         "sast_layer_is_fused": (i32, [i32, i32, i32, i32]),
+        "sast_layer_bwd_workspace_bytes": (sz, [i64, i32, i32]),
+        "sast_layer_bwd": (C.c_int, [C.POINTER(LayerArgs), vp, vp, C.POINTER(LayerGrads), vp]),
+        "sast_score_bwd_workspace_bytes": (sz, [i64, i32, i32]),
+        "sast_score_bwd": (C.c_int, [C.POINTER(ScoreArgs), vp, vp, vp, vp, vp, vp, sz, vp]),
         "sast_gather": (C.c_int, [C.POINTER(Geom), i32, vp, C.POINTER(Selection), vp, vp]),
         "sast_scatter": (C.c_int, [C.POINTER(Geom), i32, vp, C.POINTER(Selection), vp, vp]),
         "sast_gemm_bf16": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
@@ -101,7 +111,7 @@ def _load():
         fn.restype, fn.argtypes = res, args
     if lib.sast_abi_version() != 2:
         raise RuntimeError("libsast_b200.so ABI version mismatch")
-    for which, cls in enumerate((Geom, Selection, ScoreArgs, SelectArgs, LayerWeights, LayerArgs)):
+    for which, cls in enumerate((Geom, Selection, ScoreArgs, SelectArgs, LayerWeights, LayerArgs, LayerGrads)):
         if lib.sast_struct_size(which) != C.sizeof(cls):
             raise RuntimeError(f"ctypes mirror of {cls.__name__} is {C.sizeof(cls)} bytes, library says "
                                f"{lib.sast_struct_size(which)}")
@@ -110,7 +120,8 @@ def _load():
 
 EXPORTS = ("sast_abi_version", "sast_build_info", "sast_struct_size", "sast_launch_count", "sast_selection_bytes", "sast_selection_bind",
            "sast_nonzero_ratio", "sast_unpack_nonzero_ratio", "sast_score_fwd", "sast_select", "sast_select2", "sast_layer_workspace_bytes",
-           "sast_layer_fwd", "sast_layer_is_fused", "sast_gather", "sast_scatter", "sast_gemm_bf16", "sast_gemm_bf16_glu", "sast_pad_input", "sast_pad_nhwc",
+           "sast_layer_fwd", "sast_layer_is_fused", "sast_layer_bwd_workspace_bytes", "sast_layer_bwd",
+           "sast_score_bwd_workspace_bytes", "sast_score_bwd", "sast_gather", "sast_scatter", "sast_gemm_bf16", "sast_gemm_bf16_glu", "sast_pad_input", "sast_pad_nhwc",
            "sast_layernorm", "sast_lstm_gates", "sast_lstm_fwd", "sast_stem_fwd", "sast_debug_trace")
 
 _lib = None

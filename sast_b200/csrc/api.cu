@@ -22,6 +22,7 @@ extern "C" size_t sast_struct_size(int32_t which) {
     case 3: return sizeof(sast_select_args);
     case 4: return sizeof(sast_layer_weights);
     case 5: return sizeof(sast_layer_args);
+    case 6: return sizeof(sast_layer_grads);
   }
   return 0;
 }

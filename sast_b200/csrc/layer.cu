@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(256) gather_ln_kernel(const float* __restrict_
     rstd = rsqrtf(group_sum<LPT>(ss) * inv_c + eps);
     if (!ok) continue;
     if (row[j] < 0) {   // unselected: keeps norm1(x)   (SAST.py:251-254)
+      if (out == nullptr) continue;                       // recompute pass of the backward: only the compacted rows matter
       float* op = out + pix[j] * C;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -431,6 +432,25 @@ static int launch_gather_ln(const sast_layer_args& a, const Geom& g, const Layer
   if (C <= 512) return launch_gather_ln_t<32, 4, 2>(a, g, ws, st);
   if (C <= 1024) return launch_gather_ln_t<32, 8, 1>(a, g, ws, st);
   return SAST_E_UNSUPPORTED;
+}
+
+// pieces of the fp32 forward reused by the recompute pass of sast_layer_bwd (layer_bwd.cu)
+int launch_gather_ln_f32(const float* x, float* out_unselected, const sast_layer_weights& w, const sast_selection& sel, const Geom& g,
+                         int flavor, float* n2f, cudaStream_t st) {
+  sast_layer_args a{};
+  a.x = x; a.out = out_unselected; a.w = w; a.sel = sel; a.flavor = flavor;
+  LayerWorkspace ws{};
+  ws.n2f = n2f; ws.n2h = nullptr;
+  return launch_gather_ln(a, g, ws, st);
+}
+int launch_attention_f32(const float* qkv, float* att, int C, int heads, int T, int NW, const sast_selection& sel, cudaStream_t st) {
+  const size_t smem = (size_t)T * 64 * sizeof(float);
+  sast::launch_k(attention_f32_kernel, dim3(NW, heads), 128, smem, st, qkv, att, C, sel.win_K, sel.win_row0);
+  SAST_LAUNCH_CHECK();
+  return SAST_OK;
+}
+int launch_rows_gather(const float* map, float* rows, const sast_selection* sel, int C, cudaStream_t st) {
+  return launch_rows_copy<true>(const_cast<float*>(map), rows, sel, C, st);
 }
 
 }  // namespace sast

@@ -193,6 +193,52 @@ def _(x, pos, r, ctrl_w, score_w, score_b, amp, score_w_hi=None, score_w_lo=None
     return torch.empty_like(x, dtype=torch.float32), x.new_empty(x.shape[:3], dtype=torch.float32)
 
 
+@torch.library.custom_op("sast::score_bwd", mutates_args=())
+def score_bwd(d_xw: Tensor, x: Tensor, pos: Tensor, r: Tensor, ctrl_w: Tensor, score_w: Tensor, score_b: Tensor
+              ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Gradient of the STP weighting xw = sig(ctrl) sig(relu(x0 Ws^T + bs)) x0 (SAST.py:105-114): (dx, dWs, dbs, dWc).
+    Hand-written kernels (sast_score_bwd), fp32, recompute based; tok_score carries no gradient (selection)."""
+    x, d_xw = _f32c(x, "x"), _f32c(d_xw, "d_xw")
+    B, H, W, Cc = x.shape
+    pos = _f32c(pos, "pos")
+    if pos.dim() == 4 and pos.shape[0] == 1:
+        pos = pos[0]
+    pstride = 0 if pos.dim() == 3 else H * W * Cc
+    r, ctrl_w, score_w, score_b = _f32c(r, "r"), _f32c(ctrl_w, "ctrl_w"), _f32c(score_w, "score_w"), _f32c(score_b, "score_b")
+    dx = torch.empty_like(x)
+    d_sw, d_sb, d_cw = torch.zeros_like(score_w), torch.zeros_like(score_b), torch.empty_like(ctrl_w)
+    lib = L.lib()
+    nbytes = lib.sast_score_bwd_workspace_bytes(B * H * W, Cc, B)
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    a = L.ScoreArgs(_geom(B, H, W, Cc, 1, 1), x.data_ptr(), pos.data_ptr(), pstride, r.data_ptr(), r.shape[1],
+                    ctrl_w.data_ptr(), score_w.data_ptr(), score_b.data_ptr(), 0.0, 0, 0, 0, 0, 0)
+    with torch.cuda.device(x.device):
+        rc = lib.sast_score_bwd(C.byref(a), d_xw.data_ptr(), dx.data_ptr(), d_sw.data_ptr(), d_sb.data_ptr(), d_cw.data_ptr(),
+                                ws.data_ptr(), nbytes, L.stream_ptr(x.device))
+    L.check(rc, "sast_score_bwd")
+    return dx, d_sw, d_sb, d_cw
+
+
+@score_bwd.register_fake
+def _(d_xw, x, pos, r, ctrl_w, score_w, score_b):
+    return torch.empty_like(x), torch.empty_like(score_w), torch.empty_like(score_b), torch.empty_like(ctrl_w)
+
+
+def _score_setup(ctx, inputs, output):
+    x, pos, r, ctrl_w, score_w, score_b = inputs[:6]
+    ctx.save_for_backward(x, pos, r, ctrl_w, score_w, score_b)
+    ctx.set_materialize_grads(True)
+
+
+def _score_backward(ctx, d_xw, d_tok):
+    x, pos, r, ctrl_w, score_w, score_b = ctx.saved_tensors
+    dx, d_sw, d_sb, d_cw = score_bwd(d_xw, x, pos, r, ctrl_w, score_w, score_b)
+    return dx, None, None, d_cw, d_sw, d_sb, None, None, None
+
+
+torch.library.register_autograd("sast::score_fwd", _score_backward, setup_context=_score_setup)
+
+
 @torch.library.custom_op("sast::add_pos", mutates_args=())
 def add_pos(x: Tensor, pos: Tensor) -> Tensor:
     x = _f32c(x, "x")
@@ -211,6 +257,9 @@ def add_pos(x: Tensor, pos: Tensor) -> Tensor:
 @add_pos.register_fake
 def _(x, pos):
     return torch.empty_like(x, dtype=torch.float32)
+
+
+torch.library.register_autograd("sast::add_pos", lambda ctx, g: (g, None))
 
 
 # --------------------------------------------------------------------------------------------
@@ -452,6 +501,63 @@ def layer_fwd(x: Tensor, pool: Tensor, weights: List[Tensor], p0: int, p1: int, 
 @layer_fwd.register_fake
 def _(x, pool, weights, p0, p1, flavor, precision, enable_cb, mlp_inner, ln_eps):
     return torch.empty_like(x, dtype=torch.float32)
+
+
+GRAD_ORDER = WEIGHT_ORDER[:14]        # the fp32 entries; the bf16 copies carry no gradient
+
+
+@torch.library.custom_op("sast::layer_bwd", mutates_args=())
+def layer_bwd(d_out: Tensor, x: Tensor, pool: Tensor, weights: List[Tensor], p0: int, p1: int, flavor: int,
+              mlp_inner: int, ln_eps: float) -> List[Tensor]:
+    """Gradient of one MS-WSA layer: [dx] + one gradient per fp32 entry of `weights` (WEIGHT_ORDER[:14]; an empty
+    tensor where the weight is absent).  Hand-written kernels (sast_layer_bwd): fp32 recompute of the layer on the
+    compacted rows, then the chain rule backwards; the selection is a constant (as in the reference)."""
+    x, d_out = _f32c(x, "x"), _f32c(d_out, "d_out")
+    B, H, W, Cc = x.shape
+    g = _geom(B, H, W, Cc, p0, p1)
+    P = x.numel() // Cc
+    lib = L.lib()
+    sel = _bind(pool, g.B, (g.H * g.W // (g.p0 * g.p1)) * g.B, P)
+    w = L.LayerWeights()
+    for name, t in zip(WEIGHT_ORDER, weights):
+        setattr(w, name, t.data_ptr() if t.numel() else 0)
+    w.I, w.ln_eps = int(mlp_inner), float(ln_eps)
+    grads = [torch.zeros_like(t, dtype=torch.float32) for t in weights[:14]]
+    gs = L.LayerGrads()
+    for name, t in zip(GRAD_ORDER, grads):
+        setattr(gs, name, t.data_ptr() if t.numel() else 0)
+    dx = torch.empty_like(x)
+    nbytes = lib.sast_layer_bwd_workspace_bytes(P, Cc, mlp_inner)
+    ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    a = L.LayerArgs(g, int(flavor), L.FP32, 0, x.data_ptr(), 0, w, sel, ws.data_ptr(), nbytes)
+    with torch.cuda.device(x.device):
+        rc = lib.sast_layer_bwd(C.byref(a), d_out.data_ptr(), dx.data_ptr(), C.byref(gs), L.stream_ptr(x.device))
+    L.check(rc, "sast_layer_bwd")
+    return [dx] + grads
+
+
+@layer_bwd.register_fake
+def _(d_out, x, pool, weights, p0, p1, flavor, mlp_inner, ln_eps):
+    return [torch.empty_like(x)] + [torch.empty_like(t, dtype=torch.float32) for t in weights[:14]]
+
+
+def _layer_setup(ctx, inputs, output):
+    x, pool, weights, p0, p1, flavor, precision, enable_cb, mlp_inner, ln_eps = inputs
+    if enable_cb:
+        raise NotImplementedError("sast::layer_fwd backward: context broadcast (enable_CB) is not differentiable here")
+    ctx.save_for_backward(x, pool, *weights)
+    ctx.meta = (p0, p1, flavor, mlp_inner, ln_eps)
+
+
+def _layer_backward(ctx, d_out):
+    x, pool, *weights = ctx.saved_tensors
+    p0, p1, flavor, mlp_inner, ln_eps = ctx.meta
+    out = layer_bwd(d_out, x, pool, list(weights), p0, p1, flavor, mlp_inner, ln_eps)
+    wg = [gq if weights[i].numel() else None for i, gq in enumerate(out[1:])] + [None] * (len(weights) - 14)
+    return out[0], None, wg, None, None, None, None, None, None, None
+
+
+torch.library.register_autograd("sast::layer_fwd", _layer_backward, setup_context=_layer_setup)
 
 
 def layer_fwd_flat(x: Tensor, sel: Selection, weights, precision, enable_cb, mlp_inner, ln_eps, B: int) -> Tensor:

@@ -115,6 +115,16 @@ def grid_reverse(windows: Tensor, grid_size: Tuple[int, int], img_size: Tuple[in
 
 
 # ------------------------------------------------------------------------------------------
+_warned = set()
+
+
+def _warn_once(msg: str):
+    if msg not in _warned:
+        _warned.add(msg)
+        import warnings
+        warnings.warn(msg, stacklevel=3)
+
+
 class LazyCount:
     """Selected-token count kept on the device; turns into a Python number when used as one.
 
@@ -257,6 +267,30 @@ class MS_WSA(nn.Module):
         self._pack_key, self._packed = key, ws
         return ws
 
+    def packed_weights_autograd(self) -> List[Tensor]:
+        """The same list as :meth:`packed_weights`, built with differentiable ops straight from the parameters (no
+        cache, no detach), so gradients of ``torch.ops.sast.layer_fwd`` reach them -- the training path."""
+        glu, out = self.mlp.net[0].proj, self.mlp.net[2]
+        dev = self.qkv.weight.device
+        empty = torch.empty(0, device=dev)
+        I = self.mlp.inner_dim
+
+        def f(t):
+            return empty if t is None else t.float().contiguous()
+
+        w1 = glu.weight.float()
+        w1i = torch.stack((w1[:I], w1[I:]), dim=1).reshape(2 * I, -1)
+        b1i = empty if glu.bias is None else torch.stack((glu.bias.float()[:I], glu.bias.float()[I:]), dim=1).reshape(-1)
+        ws = [f(self.norm1.weight), f(self.norm1.bias), f(self.norm2.weight), f(self.norm2.bias), f(self.qkv.weight),
+              f(self.qkv.bias), f(self.proj.weight), f(self.proj.bias), f(getattr(self.ls1, "gamma", None)),
+              f(getattr(self.ls2, "gamma", None)), w1i, b1i, f(out.weight), f(out.bias)]
+        if self.precision != L.FP32:
+            ws += [ws[4].detach().to(torch.bfloat16), ws[6].detach().to(torch.bfloat16), w1i.detach().to(torch.bfloat16),
+                   ws[12].detach().to(torch.bfloat16)]
+        else:
+            ws += [empty, empty, empty, empty]
+        return ws
+
     def run_autograd(self, xw: Tensor, sel_mask: Tensor, B: int, enable_CB: bool) -> Tensor:
         """Differentiable form for training (xw [B*N,T,C] partitioned, sel_mask [B*N,T] bool): the dense-equivalent
         statement of the layer in plain torch ops, so autograd provides the backward.  Selection
@@ -281,8 +315,11 @@ class MS_WSA(nn.Module):
         return torch.where(sel_mask[..., None], out, n1)
 
     def run(self, x: Tensor, sel: ops.Selection, flavor: int, enable_CB: bool) -> Tensor:
-        """x [B,H,W,C] NHWC with a window/grid selection -> [B,H,W,C]."""
-        return ops.layer_fwd(x, sel.pool, self.packed_weights(), sel.p0, sel.p1, flavor, self.precision,
+        """x [B,H,W,C] NHWC with a window/grid selection -> [B,H,W,C].  With gradients enabled the weights are packed
+        differentiably and ``sast::layer_fwd``'s registered backward (sast_layer_bwd kernels) provides the gradient."""
+        grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        ws = self.packed_weights_autograd() if grad else self.packed_weights()
+        return ops.layer_fwd(x, sel.pool, ws, sel.p0, sel.p1, flavor, self.precision,
                              bool(enable_CB), self.mlp.inner_dim, float(self.norm1.eps))
 
     def forward(self, x: Tensor, index_window: Tensor, index_token: Tensor, padding_index: Tensor,
@@ -375,12 +412,19 @@ class SAST_block(nn.Module):
         self.B, self.N = B, N
         pos = self._position(pos_emb, x)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            return self._partition_attn_autograd(x, pos, r, index_list)
+            # training: the custom ops carry their own hand-written backward (sast_layer_bwd / sast_score_bwd); the dense
+            # torch-autograd statement remains for context broadcast and as an A/B reference (SAST_B200_TRAIN=torch)
+            if self.enable_CB or os.environ.get("SAST_B200_TRAIN", "kernels") == "torch":
+                return self._partition_attn_autograd(x, pos, r, index_list)
+            if not self.training:
+                _warn_once("sast_b200: gradients are enabled on a module in eval() mode -- running the training path "
+                           "(custom-op backward); wrap inference in torch.no_grad()")
         if self.first_block:
             w_hi, w_lo = self._score_split()
             xw, tok = ops.score_fwd(x, pos, r, self.to_controls.weight, self.to_scores.weight, self.to_scores.bias,
                                     float(self.amp_value), w_hi, w_lo)
             thr_w, thr_t = ops.thresholds(N, T, self.bounce_value)
+            tok = tok.detach()                                   # selection carries no gradient (SAST.py:120-123)
             pool1, pool2 = ops.select_pair(tok, p0, p1, thr_w, thr_t)
             sel1 = ops.Selection(pool1, B, H, W, p0, p1)
             sel2 = ops.Selection(pool2, B, H, W, p0, p1)

@@ -164,10 +164,15 @@ def test_block_bf16_against_fp32_path(C, part, B, H, W, amp, r_scale):
         assert err < 2e-2, (prec, err)
 
 
-def test_block_training_gradients_match_oracle(golden):
-    """Training path (selection by the kernels, differentiable torch ops for everything that carries
-    gradient): loss and every parameter gradient against autograd through the CPU oracle."""
-    g = golden("block_c64_w6x10")
+@pytest.mark.parametrize("path", ["kernels", "torch"])
+@pytest.mark.parametrize("name", ["block_c64_w6x10", "block_c128_w8x10_b1", "block_c64_dense"])
+def test_block_training_gradients_match_oracle(golden, monkeypatch, name, path):
+    """Training path: loss and EVERY parameter gradient (and d/dx) against autograd through the CPU oracle.
+    path "kernels": torch.ops.sast.score_fwd / layer_fwd with their registered hand-written backward
+    (sast_score_bwd / sast_layer_bwd: fp32 recompute on the compacted rows); path "torch": the dense-equivalent
+    statement in differentiable torch ops (A/B reference, SAST_B200_TRAIN=torch).  Selection by the kernels in both."""
+    monkeypatch.setenv("SAST_B200_TRAIN", path)
+    g = golden(name)
     m = g.meta
     blk, params = build_block(m, L.FP32)
     blk.train()
@@ -185,7 +190,10 @@ def test_block_training_gradients_match_oracle(golden):
     y, cnt, _ = blk(x_gpu, pos, g.t("r").to(DEV), None)
     assert int(cnt) == cnt_ref
     assert (y.detach().cpu() - y_ref.detach()).abs().max() < 2e-4
+    n0 = L.lib().sast_launch_count()
     (y * wgt.to(DEV)).sum().backward()
+    n_bwd = L.lib().sast_launch_count() - n0          # kernels of libsast_b200 launched by the backward pass
+    assert (n_bwd > 40) if path == "kernels" else (n_bwd == 0), n_bwd
     assert (x_gpu.grad.cpu() - x_ref.grad).abs().max() < 2e-3 * x_ref.grad.abs().max()
     sd = dict(blk.named_parameters())
     checked = 0

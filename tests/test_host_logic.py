@@ -32,7 +32,7 @@ def test_header_symbols_exported():
 
 def test_struct_sizes_match_header():
     lib = L.lib()   # _load() already raises on a mismatch; spell it out here
-    for which, cls in enumerate((L.Geom, L.Selection, L.ScoreArgs, L.SelectArgs, L.LayerWeights, L.LayerArgs)):
+    for which, cls in enumerate((L.Geom, L.Selection, L.ScoreArgs, L.SelectArgs, L.LayerWeights, L.LayerArgs, L.LayerGrads)):
         assert lib.sast_struct_size(which) == ctypes.sizeof(cls), cls.__name__
     assert ctypes.sizeof(L.Geom) == 24 and ctypes.sizeof(L.Selection) == 104
 
