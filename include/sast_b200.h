@@ -190,6 +190,8 @@ typedef struct sast_layer_weights {
   const uint16_t *qkv_w_bf16, *proj_w_bf16, *mlp1_w_bf16, *mlp2_w_bf16; /* SAST_BF16 only */
   int32_t I;                    /* GLU width */
   float ln_eps;
+  int32_t dim_head;             /* 0 or 32: the default (all precisions); 8, 16, 24: SAST_FP32 only (the reference's
+                                   "small" configs use 24, config/experiment/gen1/small.yaml:10); C % dim_head == 0 */
 } sast_layer_weights;
 
 typedef struct sast_layer_args {

@@ -53,7 +53,7 @@ class LayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "ln1_w", "ln1_b", "ln2_w", "ln2_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "gamma1", "gamma2",
         "mlp1_w", "mlp1_b", "mlp2_w", "mlp2_b", "qkv_w_bf16", "proj_w_bf16", "mlp1_w_bf16", "mlp2_w_bf16")] + \
-        [("I", C.c_int32), ("ln_eps", C.c_float)]
+        [("I", C.c_int32), ("ln_eps", C.c_float), ("dim_head", C.c_int32)]
 
 
 class LayerArgs(C.Structure):

@@ -21,6 +21,8 @@
 
 namespace sast {
 
+int launch_attention_f32(const float* qkv, float* att, int C, int heads, int T, int NW, const sast_selection& sel, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------
 // gather + LN1 (+ LN2)
 // ------------------------------------------------------------------------------------------
@@ -221,51 +223,53 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------
 // fp32 attention over the compacted rows of one window and one head (SAST_FP32 path)
 // ------------------------------------------------------------------------------------------
+template <int DH>
 __global__ void __launch_bounds__(128) attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ att, int C,
                                                             const int* __restrict__ win_K, const int* __restrict__ win_row0) {
   pdl_entry();
-  extern __shared__ __align__(16) float kv[];      // k [K][32] then v [K][32]
+  extern __shared__ __align__(16) float kv[];      // k [K][DH] then v [K][DH]
   const int w = blockIdx.x, h = blockIdx.y;
   const int K = win_K[w];
   if (K == 0) return;
   const int row0 = win_row0[w];
   const int ld = 3 * C;
+  constexpr int Q4 = DH / 4;                       // float4 per row of q, k or v (head-major qkv rows: [h][q,k,v][DH])
   float* ks = kv;
-  float* vs = kv + (size_t)K * 32;
-  for (int i = threadIdx.x; i < K * 16; i += blockDim.x) {     // 16 float4 per row: 8 of k, 8 of v
-    const int r = i >> 4, c = i & 15;
-    const float4 t = *reinterpret_cast<const float4*>(qkv + (size_t)(row0 + r) * ld + h * 96 + 32 + c * 4);
-    *reinterpret_cast<float4*>((c < 8 ? ks + r * 32 + c * 4 : vs + r * 32 + (c - 8) * 4)) = t;
+  float* vs = kv + (size_t)K * DH;
+  for (int i = threadIdx.x; i < K * 2 * Q4; i += blockDim.x) {
+    const int r = i / (2 * Q4), c = i % (2 * Q4);
+    const float4 t = *reinterpret_cast<const float4*>(qkv + (size_t)(row0 + r) * ld + h * 3 * DH + DH + c * 4);
+    *reinterpret_cast<float4*>((c < Q4 ? ks + r * DH + c * 4 : vs + r * DH + (c - Q4) * 4)) = t;
   }
   __syncthreads();
   const int i = threadIdx.x;
   if (i >= K) return;
-  float q[32], o[32];
-  const float scale = 0.17677669529663688110f;   // 32^-0.5
+  float q[DH], o[DH];
+  const float scale = rsqrtf((float)DH);           // dim_head ** -0.5 (SAST.py:176)
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float4 t = *reinterpret_cast<const float4*>(qkv + (size_t)(row0 + i) * ld + h * 96 + c * 4);
+  for (int c = 0; c < Q4; ++c) {
+    const float4 t = *reinterpret_cast<const float4*>(qkv + (size_t)(row0 + i) * ld + h * 3 * DH + c * 4);
     q[c * 4] = t.x; q[c * 4 + 1] = t.y; q[c * 4 + 2] = t.z; q[c * 4 + 3] = t.w;
   }
 #pragma unroll
-  for (int d = 0; d < 32; ++d) o[d] = 0.f;
+  for (int d = 0; d < DH; ++d) o[d] = 0.f;
   float mx = -INFINITY, l = 0.f;
   for (int j = 0; j < K; ++j) {
     float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) s = fmaf(q[d], ks[j * 32 + d], s);
+    for (int d = 0; d < DH; ++d) s = fmaf(q[d], ks[j * DH + d], s);
     s *= scale;
     const float mn = fmaxf(mx, s);
     const float corr = expf(mx - mn), p = expf(s - mn);
     l = l * corr + p;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) o[d] = fmaf(p, vs[j * 32 + d], o[d] * corr);
+    for (int d = 0; d < DH; ++d) o[d] = fmaf(p, vs[j * DH + d], o[d] * corr);
     mx = mn;
   }
   const float il = 1.0f / l;
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<float4*>(att + (size_t)(row0 + i) * C + h * 32 + c * 4) =
+  for (int c = 0; c < Q4; ++c)
+    *reinterpret_cast<float4*>(att + (size_t)(row0 + i) * C + h * DH + c * 4) =
         make_float4(o[c * 4] * il, o[c * 4 + 1] * il, o[c * 4 + 2] * il, o[c * 4 + 3] * il);
 }
 
@@ -444,8 +448,16 @@ int launch_gather_ln_f32(const float* x, float* out_unselected, const sast_layer
   return launch_gather_ln(a, g, ws, st);
 }
 int launch_attention_f32(const float* qkv, float* att, int C, int heads, int T, int NW, const sast_selection& sel, cudaStream_t st) {
-  const size_t smem = (size_t)T * 64 * sizeof(float);
-  sast::launch_k(attention_f32_kernel, dim3(NW, heads), 128, smem, st, qkv, att, C, sel.win_K, sel.win_row0);
+  const int dh = C / heads;
+  const size_t smem = (size_t)T * 2 * dh * sizeof(float);
+  const dim3 grid(NW, heads);
+  switch (dh) {
+    case 32: sast::launch_k(attention_f32_kernel<32>, grid, 128, smem, st, qkv, att, C, sel.win_K, sel.win_row0); break;
+    case 24: sast::launch_k(attention_f32_kernel<24>, grid, 128, smem, st, qkv, att, C, sel.win_K, sel.win_row0); break;
+    case 16: sast::launch_k(attention_f32_kernel<16>, grid, 128, smem, st, qkv, att, C, sel.win_K, sel.win_row0); break;
+    case 8: sast::launch_k(attention_f32_kernel<8>, grid, 128, smem, st, qkv, att, C, sel.win_K, sel.win_row0); break;
+    default: return SAST_E_UNSUPPORTED;
+  }
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }
@@ -484,8 +496,11 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
   SAST_CHECK_PTR(a.sel.win_K); SAST_CHECK_PTR(a.sel.win_row0); SAST_CHECK_PTR(a.sel.tiles);
   const Geom g = make_geom(a.g, a.flavor);
   const int C = g.C, I = w.I;
-  if (C % 32 != 0 || I % 32 != 0 || I <= 0 || C > 1024) return SAST_E_SHAPE;
+  const int dh = w.dim_head > 0 ? w.dim_head : 32;
+  if (C % 8 != 0 || I % 8 != 0 || I <= 0 || C > 1024 || C % dh != 0) return SAST_E_SHAPE;
   if (a.precision != SAST_FP32 && a.precision != SAST_BF16) return SAST_E_UNSUPPORTED;
+  if (dh != 32 && (a.precision != SAST_FP32 || (dh != 8 && dh != 16 && dh != 24))) return SAST_E_UNSUPPORTED;   // tcgen05 kernels: dim_head 32
+  if (a.precision == SAST_BF16 && (C % 32 != 0 || I % 32 != 0)) return SAST_E_SHAPE;
   if (a.precision == SAST_BF16) {
     SAST_CHECK_PTR(w.qkv_w_bf16); SAST_CHECK_PTR(w.proj_w_bf16); SAST_CHECK_PTR(w.mlp1_w_bf16); SAST_CHECK_PTR(w.mlp2_w_bf16);
   }
@@ -496,7 +511,7 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
   if (need > a.workspace_bytes) return SAST_E_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(a.workspace) & 255) != 0) return SAST_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  const int heads = C / 32;
+  const int heads = C / dh;
 
   rc = launch_gather_ln(a, g, ws, st);
   if (rc) return rc;
@@ -510,9 +525,8 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
     rc = launch_gemm_f32<EPI_STORE>(ws.n2f, C, w.qkv_w, w.qkv_b, 3 * C, C, a.sel.counts, g.P, ep, st);
     if (rc) return rc;
     // attention
-    const size_t smem = (size_t)g.T * 64 * sizeof(float);
-    sast::launch_k(attention_f32_kernel, dim3(g.NW, heads), 128, smem, st, (const float*)ws.qkv, (float*)ws.att, C, a.sel.win_K, a.sel.win_row0);
-    SAST_LAUNCH_CHECK();
+    rc = launch_attention_f32((const float*)ws.qkv, (float*)ws.att, C, heads, g.T, g.NW, a.sel, st);
+    if (rc) return rc;
     // proj + LayerScale + shortcut
     ep.out_f32 = ws.yf; ep.ldo = C; ep.resid = ws.n2f; ep.ldr = C; ep.gamma = w.gamma1;
     rc = launch_gemm_f32<EPI_RESID>((const float*)ws.att, C, w.proj_w, w.proj_b, C, C, a.sel.counts, g.P, ep, st);

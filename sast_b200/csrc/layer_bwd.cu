@@ -211,84 +211,85 @@ __global__ void glu_bwd_kernel(float* __restrict__ u, const float* __restrict__ 
 // attention backward over the compacted rows of one window and one head (fp32):  qkv, d(att) -> d(qkv)
 // phase 1 (thread = query i): m_i, l_i, D_i = do_i . o_i, dq_i;   phase 2 (thread = key j): dk_j, dv_j.  No atomics.
 // ------------------------------------------------------------------------------------------------------------------
+template <int DH>
 __global__ void __launch_bounds__(128) attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ datt,
                                                             float* __restrict__ dqkv, int C, const int* __restrict__ win_K,
                                                             const int* __restrict__ win_row0) {
   pdl_entry();
-  extern __shared__ __align__(16) float sm[];       // q, k, v, do: [K][32] each; then m, l, D: [K] each
+  extern __shared__ __align__(16) float sm[];       // q, k, v, do: [K][DH] each; then m, l, D: [K] each
   const int w = blockIdx.x, h = blockIdx.y;
   const int K = win_K[w];
   if (K == 0) return;
   const int row0 = win_row0[w];
   const int ld = 3 * C;
-  float *qs = sm, *ks = sm + K * 32, *vs = sm + 2 * K * 32, *ds = sm + 3 * K * 32;
-  float *ms = sm + 4 * K * 32, *ls = ms + K, *Ds = ls + K;
-  for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
-    const int r = i >> 5, c = i & 31;
-    const float* src = qkv + (size_t)(row0 + r) * ld + h * 96 + c;
-    qs[i] = src[0]; ks[i] = src[32]; vs[i] = src[64];
-    ds[i] = datt[(size_t)(row0 + r) * C + h * 32 + c];
+  float *qs = sm, *ks = sm + K * DH, *vs = sm + 2 * K * DH, *ds = sm + 3 * K * DH;
+  float *ms = sm + 4 * K * DH, *ls = ms + K, *Ds = ls + K;
+  for (int i = threadIdx.x; i < K * DH; i += blockDim.x) {
+    const int r = i / DH, c = i % DH;
+    const float* src = qkv + (size_t)(row0 + r) * ld + h * 3 * DH + c;
+    qs[i] = src[0]; ks[i] = src[DH]; vs[i] = src[2 * DH];
+    ds[i] = datt[(size_t)(row0 + r) * C + h * DH + c];
   }
   __syncthreads();
-  const float scale = 0.17677669529663688110f;
+  const float scale = rsqrtf((float)DH);
   const int i = threadIdx.x;
   if (i < K) {
-    float q[32], dq[32], o[32];
+    float q[DH], dq[DH], o[DH];
 #pragma unroll
-    for (int d = 0; d < 32; ++d) { q[d] = qs[i * 32 + d]; dq[d] = 0.f; o[d] = 0.f; }
+    for (int d = 0; d < DH; ++d) { q[d] = qs[i * DH + d]; dq[d] = 0.f; o[d] = 0.f; }
     float mx = -INFINITY;
     for (int j = 0; j < K; ++j) {
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) s = fmaf(q[d], ks[j * 32 + d], s);
+      for (int d = 0; d < DH; ++d) s = fmaf(q[d], ks[j * DH + d], s);
       mx = fmaxf(mx, s * scale);
     }
     float l = 0.f;
     for (int j = 0; j < K; ++j) {
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) s = fmaf(q[d], ks[j * 32 + d], s);
+      for (int d = 0; d < DH; ++d) s = fmaf(q[d], ks[j * DH + d], s);
       const float p = expf(s * scale - mx);
       l += p;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) o[d] = fmaf(p, vs[j * 32 + d], o[d]);
+      for (int d = 0; d < DH; ++d) o[d] = fmaf(p, vs[j * DH + d], o[d]);
     }
     const float il = 1.0f / l;
     float D = 0.f;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) D = fmaf(ds[i * 32 + d], o[d] * il, D);
+    for (int d = 0; d < DH; ++d) D = fmaf(ds[i * DH + d], o[d] * il, D);
     for (int j = 0; j < K; ++j) {
       float s = 0.f, dp = 0.f;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) { s = fmaf(q[d], ks[j * 32 + d], s); dp = fmaf(ds[i * 32 + d], vs[j * 32 + d], dp); }
+      for (int d = 0; d < DH; ++d) { s = fmaf(q[d], ks[j * DH + d], s); dp = fmaf(ds[i * DH + d], vs[j * DH + d], dp); }
       const float p = expf(s * scale - mx) * il;
       const float dsij = p * (dp - D) * scale;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) dq[d] = fmaf(dsij, ks[j * 32 + d], dq[d]);
+      for (int d = 0; d < DH; ++d) dq[d] = fmaf(dsij, ks[j * DH + d], dq[d]);
     }
     ms[i] = mx; ls[i] = il; Ds[i] = D;
-    float* dst = dqkv + (size_t)(row0 + i) * ld + h * 96;
+    float* dst = dqkv + (size_t)(row0 + i) * ld + h * 3 * DH;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) dst[d] = dq[d];
+    for (int d = 0; d < DH; ++d) dst[d] = dq[d];
   }
   __syncthreads();
   const int j = threadIdx.x;
   if (j < K) {
-    float kk[32], vv[32], dk[32], dv[32];
+    float kk[DH], vv[DH], dk[DH], dv[DH];
 #pragma unroll
-    for (int d = 0; d < 32; ++d) { kk[d] = ks[j * 32 + d]; vv[d] = vs[j * 32 + d]; dk[d] = 0.f; dv[d] = 0.f; }
+    for (int d = 0; d < DH; ++d) { kk[d] = ks[j * DH + d]; vv[d] = vs[j * DH + d]; dk[d] = 0.f; dv[d] = 0.f; }
     for (int r = 0; r < K; ++r) {
       float s = 0.f, dp = 0.f;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) { s = fmaf(qs[r * 32 + d], kk[d], s); dp = fmaf(ds[r * 32 + d], vv[d], dp); }
+      for (int d = 0; d < DH; ++d) { s = fmaf(qs[r * DH + d], kk[d], s); dp = fmaf(ds[r * DH + d], vv[d], dp); }
       const float p = expf(s * scale - ms[r]) * ls[r];
       const float dsij = p * (dp - Ds[r]) * scale;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) { dk[d] = fmaf(dsij, qs[r * 32 + d], dk[d]); dv[d] = fmaf(p, ds[r * 32 + d], dv[d]); }
+      for (int d = 0; d < DH; ++d) { dk[d] = fmaf(dsij, qs[r * DH + d], dk[d]); dv[d] = fmaf(p, ds[r * DH + d], dv[d]); }
     }
-    float* dst = dqkv + (size_t)(row0 + j) * ld + h * 96;
+    float* dst = dqkv + (size_t)(row0 + j) * ld + h * 3 * DH;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) { dst[32 + d] = dk[d]; dst[64 + d] = dv[d]; }
+    for (int d = 0; d < DH; ++d) { dst[DH + d] = dk[d]; dst[2 * DH + d] = dv[d]; }
   }
 }
 
@@ -467,7 +468,9 @@ extern "C" int sast_layer_bwd(const sast_layer_args* ap, const float* d_out, flo
   SAST_CHECK_PTR(gr.qkv_w); SAST_CHECK_PTR(gr.proj_w); SAST_CHECK_PTR(gr.mlp1_w); SAST_CHECK_PTR(gr.mlp2_w);
   const Geom g = make_geom(a.g, a.flavor);
   const int C = g.C, I = w.I;
-  if (C % 32 != 0 || I % 32 != 0 || I <= 0 || C > 1024 || g.T > 128) return SAST_E_SHAPE;
+  const int dh = w.dim_head > 0 ? w.dim_head : 32;
+  if (C % 8 != 0 || I % 8 != 0 || I <= 0 || C > 1024 || g.T > 128 || C % dh != 0) return SAST_E_SHAPE;
+  if (dh != 8 && dh != 16 && dh != 24 && dh != 32) return SAST_E_UNSUPPORTED;
   if (2 * I < 3 * C) return SAST_E_UNSUPPORTED;          // d(qkv) re-uses the GLU pre-activation buffer
   if (a.workspace_bytes < sast_layer_bwd_workspace_bytes(g.P, C, I)) return SAST_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -485,7 +488,7 @@ extern "C" int sast_layer_bwd(const sast_layer_args* ap, const float* d_out, flo
   float* m = take((size_t)P * C);
   float* gy = take((size_t)P * C);
   float* t1 = take((size_t)P * C);
-  const int heads = C / 32;
+  const int heads = C / dh;
   const unsigned eb = 148 * 8;
 
   // ---- recompute the forward on the compacted rows (fp32) ----
@@ -514,14 +517,20 @@ extern "C" int sast_layer_bwd(const sast_layer_args* ap, const float* d_out, flo
   if ((rc = bw::gemm_tn(t1, att, gr.proj_w, C, C, counts, P, st))) return rc;                      // dWp = dpo^T att
   if ((rc = bw::gemm_nn(t1, w.proj_w, m, C, C, 0, counts, P, st))) return rc;                      // datt = dpo Wp     (over m)
   {
-    const size_t smem = ((size_t)4 * g.T * 32 + 3 * g.T) * sizeof(float);
+    const size_t smem = ((size_t)4 * g.T * dh + 3 * g.T) * sizeof(float);
     static thread_local unsigned long long attr_mask = 0;
-    if (first_use_on_device(attr_mask)) {
-      cudaError_t e = cudaFuncSetAttribute(bw::attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * 128 * 32 + 3 * 128) * 4);
-      if (e != cudaSuccess) return (int)e;
+    const bool first = first_use_on_device(attr_mask);
+#define SAST_ATT_BWD(DH)                                                                                                      \
+    {                                                                                                                         \
+      if (first) {                                                                                                            \
+        cudaError_t e = cudaFuncSetAttribute(bw::attention_bwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 * 128 * DH + 3 * 128) * 4); \
+        if (e != cudaSuccess) return (int)e;                                                                                  \
+      }                                                                                                                       \
+      sast::launch_k(bw::attention_bwd_kernel<DH>, dim3(g.NW, heads), 128, smem, st, (const float*)qkv, (const float*)m, u, C, a.sel.win_K, \
+                     a.sel.win_row0);                                                              /* dqkv (over u) */       \
     }
-    sast::launch_k(bw::attention_bwd_kernel, dim3(g.NW, heads), 128, smem, st, (const float*)qkv, (const float*)m, u, C, a.sel.win_K,
-                   a.sel.win_row0);                                                                // dqkv             (over u)
+    if (dh == 32) SAST_ATT_BWD(32) else if (dh == 24) SAST_ATT_BWD(24) else if (dh == 16) SAST_ATT_BWD(16) else SAST_ATT_BWD(8)
+#undef SAST_ATT_BWD
     SAST_LAUNCH_CHECK();
   }
   if ((rc = bw::colreduce(u, nullptr, nullptr, nullptr, nullptr, gr.qkv_b, 3 * C, counts, P, st))) return rc;

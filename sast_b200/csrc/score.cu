@@ -142,7 +142,8 @@ int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv
 extern "C" int sast_score_fwd(const sast_score_args* a, void* stream) {
   SAST_CHECK_PTR(a); SAST_CHECK_PTR(a->x); SAST_CHECK_PTR(a->pos); SAST_CHECK_PTR(a->xw);
   const sast_geom& g = a->g;
-  if (g.B <= 0 || g.H <= 0 || g.W <= 0 || g.C <= 0 || g.C % 32 != 0) return SAST_E_SHAPE;
+  if (g.B <= 0 || g.H <= 0 || g.W <= 0 || g.C <= 0 || g.C % 16 != 0) return SAST_E_SHAPE;
+  if (a->score_w_hi && a->score_w_lo && g.C % 32 != 0) return SAST_E_SHAPE;        // tcgen05 scoring: C % 32
   if (a->pos_batch_stride % 4 != 0) return SAST_E_SHAPE;
   if (a->xw == a->x) return SAST_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;

@@ -476,7 +476,7 @@ def _layer_workspace(lib, P, Cc, mlp_inner, B, precision, enable_cb, device):
 
 @torch.library.custom_op("sast::layer_fwd", mutates_args=())
 def layer_fwd(x: Tensor, pool: Tensor, weights: List[Tensor], p0: int, p1: int, flavor: int, precision: int,
-              enable_cb: bool, mlp_inner: int, ln_eps: float) -> Tensor:
+              enable_cb: bool, mlp_inner: int, ln_eps: float, dim_head: int) -> Tensor:
     """x [B,H,W,C] fp32 NHWC -> same shape (flavor WINDOW or GRID)."""
     x = _f32c(x, "x")
     L.require_cuda(pool, "pool")
@@ -491,7 +491,7 @@ def layer_fwd(x: Tensor, pool: Tensor, weights: List[Tensor], p0: int, p1: int, 
     assert len(weights) == len(WEIGHT_ORDER)
     for name, t in zip(WEIGHT_ORDER, weights):
         setattr(w, name, t.data_ptr() if t.numel() else 0)
-    w.I, w.ln_eps = int(mlp_inner), float(ln_eps)
+    w.I, w.ln_eps, w.dim_head = int(mlp_inner), float(ln_eps), int(dim_head)
     a = L.LayerArgs(g, int(flavor), int(precision), int(bool(enable_cb)), x.data_ptr(), out.data_ptr(), w, sel,
                     L.ptr(ws), nbytes)
     L.run(x.device, "sast_layer_fwd", C.byref(a))
@@ -499,7 +499,7 @@ def layer_fwd(x: Tensor, pool: Tensor, weights: List[Tensor], p0: int, p1: int, 
 
 
 @layer_fwd.register_fake
-def _(x, pool, weights, p0, p1, flavor, precision, enable_cb, mlp_inner, ln_eps):
+def _(x, pool, weights, p0, p1, flavor, precision, enable_cb, mlp_inner, ln_eps, dim_head):
     return torch.empty_like(x, dtype=torch.float32)
 
 
@@ -508,7 +508,7 @@ GRAD_ORDER = WEIGHT_ORDER[:14]        # the fp32 entries; the bf16 copies carry 
 
 @torch.library.custom_op("sast::layer_bwd", mutates_args=())
 def layer_bwd(d_out: Tensor, x: Tensor, pool: Tensor, weights: List[Tensor], p0: int, p1: int, flavor: int,
-              mlp_inner: int, ln_eps: float) -> List[Tensor]:
+              mlp_inner: int, ln_eps: float, dim_head: int) -> List[Tensor]:
     """Gradient of one MS-WSA layer: [dx] + one gradient per fp32 entry of `weights` (WEIGHT_ORDER[:14]; an empty
     tensor where the weight is absent).  Hand-written kernels (sast_layer_bwd): fp32 recompute of the layer on the
     compacted rows, then the chain rule backwards; the selection is a constant (as in the reference)."""
@@ -521,7 +521,7 @@ def layer_bwd(d_out: Tensor, x: Tensor, pool: Tensor, weights: List[Tensor], p0:
     w = L.LayerWeights()
     for name, t in zip(WEIGHT_ORDER, weights):
         setattr(w, name, t.data_ptr() if t.numel() else 0)
-    w.I, w.ln_eps = int(mlp_inner), float(ln_eps)
+    w.I, w.ln_eps, w.dim_head = int(mlp_inner), float(ln_eps), int(dim_head)
     grads = [torch.zeros_like(t, dtype=torch.float32) for t in weights[:14]]
     gs = L.LayerGrads()
     for name, t in zip(GRAD_ORDER, grads):
@@ -537,30 +537,30 @@ def layer_bwd(d_out: Tensor, x: Tensor, pool: Tensor, weights: List[Tensor], p0:
 
 
 @layer_bwd.register_fake
-def _(d_out, x, pool, weights, p0, p1, flavor, mlp_inner, ln_eps):
+def _(d_out, x, pool, weights, p0, p1, flavor, mlp_inner, ln_eps, dim_head):
     return [torch.empty_like(x)] + [torch.empty_like(t, dtype=torch.float32) for t in weights[:14]]
 
 
 def _layer_setup(ctx, inputs, output):
-    x, pool, weights, p0, p1, flavor, precision, enable_cb, mlp_inner, ln_eps = inputs
+    x, pool, weights, p0, p1, flavor, precision, enable_cb, mlp_inner, ln_eps, dim_head = inputs
     if enable_cb:
         raise NotImplementedError("sast::layer_fwd backward: context broadcast (enable_CB) is not differentiable here")
     ctx.save_for_backward(x, pool, *weights)
-    ctx.meta = (p0, p1, flavor, mlp_inner, ln_eps)
+    ctx.meta = (p0, p1, flavor, mlp_inner, ln_eps, dim_head)
 
 
 def _layer_backward(ctx, d_out):
     x, pool, *weights = ctx.saved_tensors
-    p0, p1, flavor, mlp_inner, ln_eps = ctx.meta
-    out = layer_bwd(d_out, x, pool, list(weights), p0, p1, flavor, mlp_inner, ln_eps)
+    p0, p1, flavor, mlp_inner, ln_eps, dim_head = ctx.meta
+    out = layer_bwd(d_out, x, pool, list(weights), p0, p1, flavor, mlp_inner, ln_eps, dim_head)
     wg = [gq if weights[i].numel() else None for i, gq in enumerate(out[1:])] + [None] * (len(weights) - 14)
-    return out[0], None, wg, None, None, None, None, None, None, None
+    return out[0], None, wg, None, None, None, None, None, None, None, None
 
 
 torch.library.register_autograd("sast::layer_fwd", _layer_backward, setup_context=_layer_setup)
 
 
-def layer_fwd_flat(x: Tensor, sel: Selection, weights, precision, enable_cb, mlp_inner, ln_eps, B: int) -> Tensor:
+def layer_fwd_flat(x: Tensor, sel: Selection, weights, precision, enable_cb, mlp_inner, ln_eps, B: int, dim_head: int = 32) -> Tensor:
     """MS_WSA on an already partitioned [B*N,T,C] tensor (frames matter only for context broadcast)."""
     x = _f32c(x, "x")
     NWn, T, Cc = x.shape
@@ -572,7 +572,7 @@ def layer_fwd_flat(x: Tensor, sel: Selection, weights, precision, enable_cb, mlp
     w = L.LayerWeights()
     for name, t in zip(WEIGHT_ORDER, weights):
         setattr(w, name, t.data_ptr() if t.numel() else 0)
-    w.I, w.ln_eps = int(mlp_inner), float(ln_eps)
+    w.I, w.ln_eps, w.dim_head = int(mlp_inner), float(ln_eps), int(dim_head)
     a = L.LayerArgs(g, L.FLAT, int(precision), int(bool(enable_cb)), x.data_ptr(), out.data_ptr(), w,
                     sel.struct, L.ptr(ws), nbytes)
     L.run(x.device, "sast_layer_fwd", C.byref(a))

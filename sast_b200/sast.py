@@ -208,8 +208,9 @@ class MS_WSA(nn.Module):
     def __init__(self, dim: int, dim_head: int = 32, bias: bool = True,
                  sub_layer_params: Optional[Sequence] = None, norms: Sequence[nn.Module] = None):
         super().__init__()
-        if dim_head != 32 or dim % 32 != 0:
-            raise NotImplementedError("libsast_b200 attention kernels are built for dim_head == 32")
+        if dim_head not in (8, 16, 24, 32) or dim % dim_head != 0 or dim % 8 != 0:
+            raise NotImplementedError(f"dim={dim}, dim_head={dim_head}: libsast_b200 takes dim_head 32 (tensor-core kernels) or "
+                                      "8 / 16 / 24 (fp32 CUDA-core kernels), dim a multiple of dim_head and of 8")
         self.num_heads = dim // dim_head
         self.dim_head = dim_head
         self.scale = dim_head ** -0.5
@@ -229,9 +230,19 @@ class MS_WSA(nn.Module):
         self.drop2 = nn.Identity()
         self.sub_layers = nn.ModuleList([self.ls1, self.drop1, self.norm2, self.mlp, self.ls2, self.drop2])
         self.eps = 1e-6
-        self.precision = default_precision()
+        self._precision = default_precision()
         self._pack_key = None
         self._packed: Optional[List[Tensor]] = None
+
+    @property
+    def precision(self) -> int:
+        """Requested precision, except that shapes the tcgen05 kernels do not take (dim_head != 32, as in the
+        reference's "small" configs with dim_head 24, or dim % 32 != 0) always run the fp32 CUDA-core kernels."""
+        return L.FP32 if (self.dim_head != 32 or self.dim % 32 != 0) else self._precision
+
+    @precision.setter
+    def precision(self, value: int):
+        self._precision = int(value)
 
     # -- weights in the order the C ABI wants them (sast_layer_weights) ------------------------
     def packed_weights(self) -> List[Tensor]:
@@ -320,7 +331,7 @@ class MS_WSA(nn.Module):
         grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         ws = self.packed_weights_autograd() if grad else self.packed_weights()
         return ops.layer_fwd(x, sel.pool, ws, sel.p0, sel.p1, flavor, self.precision,
-                             bool(enable_CB), self.mlp.inner_dim, float(self.norm1.eps))
+                             bool(enable_CB), self.mlp.inner_dim, float(self.norm1.eps), self.dim_head)
 
     def forward(self, x: Tensor, index_window: Tensor, index_token: Tensor, padding_index: Tensor,
                 asy_index: Tensor, M: int, B: int, enable_CB: bool) -> Tensor:
@@ -332,7 +343,7 @@ class MS_WSA(nn.Module):
         NW, T = x3.shape[:2]
         sel = ops.selection_from_lists(index_window, asy_index, int(B), NW // int(B), T, 1, T)
         y = ops.layer_fwd_flat(x3, sel, self.packed_weights(), self.precision, bool(enable_CB), self.mlp.inner_dim,
-                               float(self.norm1.eps), int(B))
+                               float(self.norm1.eps), int(B), self.dim_head)
         return y.view(*shape)
 
 

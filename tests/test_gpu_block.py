@@ -9,6 +9,7 @@ from oracle.golden_common import event_histogram
 from sast_b200 import _lib as L
 from sast_b200 import ops
 from gpu_common import DEV, build_backbone, build_block, pos_module, sel_mask
+from sast_b200.backbone import PositionEmbeddingSine
 
 pytestmark = pytest.mark.gpu
 
@@ -329,3 +330,35 @@ def test_layer_explicit_selection(case, precision):
     ref = _dense_layer_reference(x, mask_map.float(), params, prefix, C, part, flavor)
     err = (y.cpu() - ref).abs().max().item()
     assert err < TOL[precision], err
+
+
+def test_block_dim_head_24_forward_and_gradients():
+    """dim_head 24 (the reference's "small" configs): C = 48, two heads of 24 -- fp32 CUDA-core kernels, forward and the
+    hand-written backward, against the oracle and autograd through it."""
+    from sast_b200.config import attention_config
+    from oracle.golden_common import make_params, with_aliases
+    C, part, B, H, W, amp = 48, (4, 6), 2, 16, 24, 2e-3
+    blk = sast_b200.SAST_block(C, attention_config(part, AMP=amp, dim_head=24), first_block=True)
+    shapes = {k: tuple(v.shape) for k, v in blk.state_dict().items() if ".sub_layers." not in k}
+    params = make_params(shapes, seed=24)
+    blk.load_state_dict(with_aliases(params, blk.state_dict().keys()))
+    blk = blk.to(DEV).train()
+    assert blk.win_attn.num_heads == 2 and blk.win_attn.precision == L.FP32
+    gen = torch.Generator().manual_seed(24)
+    x = torch.randn(B, H, W, C, generator=gen) * torch.linspace(0.3, 1.7, W).view(1, 1, W, 1)
+    r = torch.rand(B, 20, generator=gen) * 0.02
+    wgt = torch.randn(x.shape, generator=gen)
+    p_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    x_ref = x.clone().requires_grad_(True)
+    y_ref, cnt_ref, _ = O.sast_block(x_ref, O.position_table(H, W, C), r, p_ref, part, amp=amp, dim_head=24)
+    (y_ref * wgt).sum().backward()
+    pos = PositionEmbeddingSine(C // 2, normalize=True, input_size=(1, H, W))
+    x_gpu = x.to(DEV).requires_grad_(True)
+    y, cnt, _ = blk(x_gpu, pos, r.to(DEV), None)
+    assert int(cnt) == cnt_ref and 0 < cnt_ref < 2 * H * W
+    assert (y.detach().cpu() - y_ref.detach()).abs().max() < 2e-4
+    (y * wgt.to(DEV)).sum().backward()
+    assert (x_gpu.grad.cpu() - x_ref.grad).abs().max() < 2e-3 * x_ref.grad.abs().max()
+    sd = dict(blk.named_parameters())
+    for k, ref in p_ref.items():
+        assert (sd[k].grad.cpu() - ref.grad).abs().max() < 2e-3 * ref.grad.abs().max().clamp_min(1e-6), k

@@ -86,3 +86,43 @@ def test_backbone_full_config_against_oracle(wl, kind, sparsity, precision, gamm
         bad = (d > tol).float().mean().item()
         assert torch.isfinite(f[st]).all()
         assert bad < frac, (st, bad, d.max().item())
+
+
+@pytest.mark.parametrize("precision", [L.FP32, L.BF16], ids=["fp32", "bf16"])
+def test_backbone_small_config_dim_head_24(precision):
+    """The reference's "small" model (config/experiment/gen1/small.yaml: embed_dim 48, dim_head 24 -> C = 48 / 96 / 192 /
+    384 with 2 / 4 / 8 / 16 heads) against the oracle: dim_head != 32 takes the fp32 CUDA-core layer kernels whatever
+    precision is requested (the tcgen05 kernels are built for dim_head 32); stem / LSTM follow the requested precision."""
+    res, B = (128, 192), 2
+    torch.manual_seed(0)
+    net = sast_b200.build_recurrent_backbone(backbone_config(res, embed_dim=48, partition_split_32=1, dim_head=24))
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if n.endswith(".gamma"):
+                p.fill_(0.5)
+    net = net.eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    cfg = dict(embed_dim=48, dim_multiplier=[1, 2, 4, 8], num_blocks=[1, 1, 1, 1], patch_size=4, in_res_hw=list(res),
+               partition_size=[res[0] // 32, res[1] // 32], dim_head=24)
+    x = make_inputs(B, res, 0.97, 1, seed=9)[0]
+    with torch.no_grad():
+        f_ref, s_ref, p_ref = O.backbone_forward(x.int(), None, sd, cfg)
+        f_ref2, _, p_ref2 = O.backbone_forward(x.int(), s_ref, sd, cfg)
+    net = net.to(DEV)
+    set_precision(net, precision)
+    assert all(m.precision == L.FP32 for m in net.modules() if isinstance(m, sast_b200.MS_WSA))
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = precision != L.FP32
+    try:
+        with torch.no_grad():
+            f, s, p = net(x.to(DEV), None)
+            f2, _, p2 = net(x.to(DEV), s)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    tol = 1e-3 if precision == L.FP32 else 3e-2
+    for got_p, ref_p, got_f, ref_f in ((p, p_ref, f, f_ref), (p2, p_ref2, f2, f_ref2)):
+        for a, b in zip([int(v) for v in got_p], ref_p):
+            assert abs(a - b) <= max(2, (2e-3 if precision == L.FP32 else 3e-2) * b), (got_p, ref_p)
+        for st in (1, 2, 3, 4):
+            d = (got_f[st].cpu() - ref_f[st]).abs()
+            assert (d > tol).float().mean().item() < (2e-3 if precision == L.FP32 else 2e-2), (st, d.max().item())
