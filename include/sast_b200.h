@@ -84,7 +84,8 @@ typedef struct sast_selection {
                                 of frame b is slot b*N + j: tiles[2 slot] = its first window (-1 = unused slot),
                                 tiles[2 slot + 1] = one past its last window                   */
   int32_t* tile_list; /* [NW*2] the same tiles as one dense work list (any order): entry k < counts[3] is
-                                {first compacted row, number of rows}; a tile holds whole windows        */
+                                {first compacted row, number of rows | split << 8}; a tile holds whole windows; split
+                                = K of the first window when the tile is exactly two windows of <= 64 tokens, else 0 */
   int32_t* row_win;   /* [P]    first S entries: (first compacted row of row r's window) << 8 | (K of that window):
                                 the keys a row attends to, without a dependent look-up (needs P < 2^23)        */
 } sast_selection;
@@ -208,10 +209,11 @@ typedef struct sast_layer_args {
 } sast_layer_args;
 size_t sast_layer_workspace_bytes(int64_t P, int32_t C, int32_t I, int32_t B, int32_t precision);
 int sast_layer_fwd(const sast_layer_args* a, void* stream);
-/* 1 if sast_layer_fwd runs this configuration as ONE fused kernel (SAST_BF16, C = 64 or 128 with the mlp_ratio-4
- * GLU width, no context broadcast): the whole layer per 128-row tile with qkv / attention / MLP intermediates kept
- * in shared and tensor memory.  Such calls need no workspace (workspace may be NULL).  0: the multi-kernel chain. */
-int32_t sast_layer_is_fused(int32_t C, int32_t I, int32_t precision, int32_t enable_cb);
+/* 1 if sast_layer_fwd runs this configuration (P = B*H*W tokens) as ONE fused kernel (SAST_BF16, dim_head 32, C = 64,
+ * or C = 128 with P >= 8192, with the mlp_ratio-4 GLU width, no context broadcast): the whole layer per 128-row tile
+ * with qkv / attention / MLP intermediates kept in shared and tensor memory.  Such calls need no workspace (workspace
+ * may be NULL).  0: the multi-kernel chain. */
+int32_t sast_layer_is_fused(int64_t P, int32_t C, int32_t I, int32_t precision, int32_t enable_cb);
 
 /*
  * Backward twins for the training configuration (the reference trains through stock autograd: train.py,

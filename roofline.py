@@ -125,7 +125,7 @@ def roofline_block(net, workload, args, device, ms_per_step=None):
                                   "tflops": fl / t / 1e12, "tensor_frac": fl / t / 1e12 / pk["bf16_tflops"],
                                   "gbs": by / t / 1e9, "hbm_frac_of_min_traffic": by / t / 1e9 / pk["hbm_gbs"]}
     dense = layers["keep_1.0"]
-    kname = "fl::layer_fused_kernel<64>" if lib.sast_layer_is_fused(C, I, layer.precision, 0) else "layer.cu kernel chain (6 launches)"
+    kname = "fl::layer_fused_kernel<64>" if lib.sast_layer_is_fused(P, C, I, layer.precision, 0) else "layer.cu kernel chain (6 launches)"
     nc = next((v for k, v in ncu.items() if k.startswith("layer_fused_kernel<64")), {})
     head = {"bound": "tensor", "achieved": dense["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": dense["tensor_frac"],
             "traffic": None,

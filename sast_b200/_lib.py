@@ -90,7 +90,7 @@ def _load():
         "sast_select2": (C.c_int, [C.POINTER(SelectArgs), i32, C.POINTER(Selection), vp]),
         "sast_layer_workspace_bytes": (sz, [i64, i32, i32, i32, i32]),
         "sast_layer_fwd": (C.c_int, [C.POINTER(LayerArgs), vp]),
-        "sast_layer_is_fused": (i32, [i32, i32, i32, i32]),
+        "sast_layer_is_fused": (i32, [i64, i32, i32, i32, i32]),
         "sast_layer_bwd_workspace_bytes": (sz, [i64, i32, i32]),
         "sast_layer_bwd": (C.c_int, [C.POINTER(LayerArgs), vp, vp, C.POINTER(LayerGrads), vp]),
         "sast_score_bwd_workspace_bytes": (sz, [i64, i32, i32]),

@@ -100,6 +100,15 @@ struct Params {
   long long* trace;      // debug stamps (sast_debug_trace which = 4), normally null; trace build only
 };
 
+// tile row -> offset of its compacted row inside the tile's row range, or -1.  split > 0 ("aligned" tile: two windows of
+// <= 64 tokens): the second window starts at tile row 64, so every row's keys lie inside one 64-column block of S.
+__device__ __forceinline__ int tile_src(int r, int rows, int split) {
+  if (split == 0) return r < rows ? r : -1;
+  if (r < 64) return r < split ? r : -1;
+  const int s = split + (r - 64);
+  return s < rows ? s : -1;
+}
+
 template <int TPC>
 __device__ __forceinline__ void ctx_sync(int ctx) {
   asm volatile("bar.sync %0, %1;" ::"r"(ctx + 1), "n"(TPC) : "memory");
@@ -321,27 +330,36 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const int t_stride = gridDim.x * NCTX;
     const int gr = ct >> 2, gl = ct & 3;                   // gather mapping: 4 lanes per row
     int t = blockIdx.x * NCTX + ctx;
-    int row0 = 0, rows = 0;
+    int row0 = 0, rows = 0, split = 0;
     int gpix[128 / K::RPP];
     int bk_pix = 0, bk_win = 0;                            // threads ct < 128: pixel of tile row ct and its window {first row << 8 | K}
     if (t < n_tiles) {
       row0 = p.tile_list[2 * t]; rows = p.tile_list[2 * t + 1];
+      split = rows >> 8; rows &= 255;
 #pragma unroll
-      for (int ps = 0; ps < 128 / K::RPP; ++ps) gpix[ps] = ps * K::RPP + gr < rows ? p.row_pix[row0 + ps * K::RPP + gr] : -1;
-      if (ct < rows) { bk_pix = p.row_pix[row0 + ct]; bk_win = p.row_win[row0 + ct]; }
+      for (int ps = 0; ps < 128 / K::RPP; ++ps) {
+        const int src = tile_src(ps * K::RPP + gr, rows, split);
+        gpix[ps] = src >= 0 ? p.row_pix[row0 + src] : -1;
+      }
+      if (ct < 128) {
+        const int src = tile_src(ct, rows, split);
+        if (src >= 0) { bk_pix = p.row_pix[row0 + src]; bk_win = p.row_win[row0 + src]; }
+      }
     }
     [[maybe_unused]] int ti = -1;
     for (; t < n_tiles; t += t_stride) {
       ++ti;
       FL_STAMP(0);
       const int tn = t + t_stride;
-      int nrow0 = 0, nrows = 0;
-      if (tn < n_tiles) { nrow0 = ldg_pinned(p.tile_list + 2 * tn); nrows = ldg_pinned(p.tile_list + 2 * tn + 1); }   // consumed after the QKV epilogue
+      int nrow0 = 0, nrows = 0;                              // nrows: rows | split << 8, decoded after the QKV epilogue
+      if (tn < n_tiles) { nrow0 = ldg_pinned(p.tile_list + 2 * tn); nrows = ldg_pinned(p.tile_list + 2 * tn + 1); }
 
       // ---- tile bookkeeping (consumed after later barriers) + gather / LN1 / LN2 -------------------------------
       if (ct < 128) {                                        // keys of row ct: the rows of its own window (a tile holds whole windows)
-        const int lo = ct < rows ? (bk_win >> 8) - row0 : 0;
-        ctl->pix[ctx][ct] = bk_pix; ctl->lo[ctx][ct] = (uint8_t)lo; ctl->hi[ctx][ct] = (uint8_t)(ct < rows ? lo + (bk_win & 255) : 0);
+        const bool on = tile_src(ct, rows, split) >= 0;
+        const int off = (bk_win >> 8) - row0;                // first compacted row of the row's window, tile relative
+        const int lo = !on ? 0 : (split && off) ? 64 : off;
+        ctl->pix[ctx][ct] = bk_pix; ctl->lo[ctx][ct] = (uint8_t)lo; ctl->hi[ctx][ct] = (uint8_t)(on ? lo + (bk_win & 255) : 0);
       }
       constexpr int NV = C / 16;                             // float4 per lane, 4 lanes per row
       float4 xin[128 / K::RPP][NV];                          // every pass's rows requested up front (y[] is not live yet)
@@ -457,15 +475,23 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       FL_STAMP(3);
       // next tile: pixel of this thread's gather rows (the tile_list entry requested at the top has landed by now) and,
       // for threads ct < 128, the row table: each dependent load is issued one phase before its value is needed
+      const int nsplit = nrows >> 8;
+      nrows &= 255;
       int npix[128 / K::RPP];
 #pragma unroll
-      for (int ps = 0; ps < 128 / K::RPP; ++ps) npix[ps] = ps * K::RPP + gr < nrows ? ldg_pinned(p.row_pix + nrow0 + ps * K::RPP + gr) : -1;
+      for (int ps = 0; ps < 128 / K::RPP; ++ps) {
+        const int src = tile_src(ps * K::RPP + gr, nrows, nsplit);
+        npix[ps] = src >= 0 ? ldg_pinned(p.row_pix + nrow0 + src) : -1;
+      }
       int nb_pix = 0, nb_win = 0;
-      if (ct < nrows) { nb_pix = ldg_pinned(p.row_pix + nrow0 + ct); nb_win = ldg_pinned(p.row_win + nrow0 + ct); }     // nrows <= 128
+      if (ct < 128) {
+        const int src = tile_src(ct, nrows, nsplit);
+        if (src >= 0) { nb_pix = ldg_pinned(p.row_pix + nrow0 + src); nb_win = ldg_pinned(p.row_win + nrow0 + src); }
+      }
 
       // ---- attention, two heads at a time -------------------------------------------------------------------------
       const int lo = ctl->lo[ctx][row], hi = ctl->hi[ctx][row];
-      const bool rvalid = row < rows;
+      const bool rvalid = hi > lo;                           // rows past the tile / in the alignment gap hold no token
       const int hh = sub / TPR, half = sub % TPR;            // softmax / O mapping: head of the pair, part of the columns
       constexpr int SCOLS = 128 / TPR;                       // S columns per softmax thread
       for (int hp = 0; hp < H / 2; ++hp) {
@@ -486,18 +512,26 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         FL_STAMP(4);
         // pass 1: row maximum over the keys of the row's own window, this thread's columns
         float mx = -INFINITY;
-        bool need[SCOLS / 32];
+        bool need[SCOLS / 32], full[SCOLS / 32];
 #pragma unroll
         for (int cc = 0; cc < SCOLS / 32; ++cc) {
           const int c0 = half * SCOLS + cc * 32;
           need[cc] = __any_sync(kFull, lo < c0 + 32 && hi > c0);
+          // whole chunk inside the window of every row of the warp that has one: no per-element masks (rows without a
+          // token compute garbage that is never stored)
+          full[cc] = __all_sync(kFull, !rvalid || (lo <= c0 && c0 + 32 <= hi));
           if (need[cc]) {
             uint32_t raw[32];
             ptx::tmem_ld_32x32(tm + lane_sel + (uint32_t)(K::TM_S * hh + c0), raw);
             ptx::tmem_ld_wait();
+            if (full[cc]) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j >= lo && c0 + j < hi) mx = fmaxf(mx, __uint_as_float(raw[j]));
+              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j >= lo && c0 + j < hi) mx = fmaxf(mx, __uint_as_float(raw[j]));
+            }
           }
         }
         if constexpr (TPR == 2) {
@@ -518,15 +552,25 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             uint32_t raw[32];
             ptx::tmem_ld_32x32(tm + lane_sel + (uint32_t)(K::TM_S * hh + c0), raw);
             ptx::tmem_ld_wait();
+            if (full[cc]) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(raw[j]), sc, -mxs));
-              float p1 = ex2_approx(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs));
-              p0 = (c0 + j >= lo && c0 + j < hi) ? p0 : 0.f;
-              p1 = (c0 + j + 1 >= lo && c0 + j + 1 < hi) ? p1 : 0.f;
-              const uint32_t w = pack_bf16(p0, p1);
-              pk[j >> 1] = w;
-              rsum += __uint_as_float(w << 16) + __uint_as_float(w & 0xFFFF0000u);
+              for (int j = 0; j < 32; j += 2) {
+                const uint32_t w = pack_bf16(ex2_approx(fmaf(__uint_as_float(raw[j]), sc, -mxs)),
+                                             ex2_approx(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs)));
+                pk[j >> 1] = w;
+                rsum += __uint_as_float(w << 16) + __uint_as_float(w & 0xFFFF0000u);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(raw[j]), sc, -mxs));
+                float p1 = ex2_approx(fmaf(__uint_as_float(raw[j + 1]), sc, -mxs));
+                p0 = (c0 + j >= lo && c0 + j < hi) ? p0 : 0.f;
+                p1 = (c0 + j + 1 >= lo && c0 + j + 1 < hi) ? p1 : 0.f;
+                const uint32_t w = pack_bf16(p0, p1);
+                pk[j >> 1] = w;
+                rsum += __uint_as_float(w << 16) + __uint_as_float(w & 0xFFFF0000u);
+              }
             }
           } else {
 #pragma unroll
@@ -722,8 +766,8 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 #pragma unroll
         for (int ps = 0; ps < 128 / K::RPP; ++ps) {
           const int r = ps * K::RPP + gr;
-          if (r < rows) {
-            float* orow = p.out + (long long)ctl->pix[ctx][r] * C;
+          if (gpix[ps] >= 0) {
+            float* orow = p.out + (long long)gpix[ps] * C;
 #pragma unroll
             for (int i = 0; i < C / 16; ++i) {
               const uint32_t ch4 = (uint32_t)(gl + 4 * i);
@@ -736,7 +780,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       ctx_sync<TPC>(ctx);                                    // TMEM, the A tile and ctl->pix/lo/hi are free for the next tile
       FL_STAMP(14);
       bk_pix = nb_pix; bk_win = nb_win;
-      row0 = nrow0; rows = nrows;
+      row0 = nrow0; rows = nrows; split = nsplit;
 #pragma unroll
       for (int ps = 0; ps < 128 / K::RPP; ++ps) gpix[ps] = npix[ps];
     }
@@ -819,8 +863,11 @@ static int fused_contexts() {
 // true if this layer can take the fused kernel (bf16 path, C 64 / 128 with the mlp_ratio-4 GLU width, no context broadcast)
 bool fused_layer_supported(const sast_layer_args& a) {
   if (a.precision != SAST_BF16 || a.enable_cb || !fused_layer_enabled()) return false;
+  if (a.w.dim_head != 0 && a.w.dim_head != 32) return false;
   if (a.g.C == 64) return a.w.I == fl::Cfg<64, 1>::I;
-  if (a.g.C == 128) return a.w.I == fl::Cfg<128, 1>::I;
+  // C = 128 streams 368 KB of weights per tile: below ~64 tiles (Gen1 B=1 stage 2: 10) the N-split GEMM chain, which
+  // spreads one weight pass over all SMs, is faster (measured: 67 us against ~50 us per layer)
+  if (a.g.C == 128) return a.w.I == fl::Cfg<128, 1>::I && (a.g.B <= 0 || (long long)a.g.B * a.g.H * a.g.W >= 64 * 128);
   return false;
 }
 

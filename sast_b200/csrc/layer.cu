@@ -472,8 +472,9 @@ extern "C" size_t sast_layer_workspace_bytes(int64_t P, int32_t C, int32_t I, in
   return sast::layer_workspace_layout(P, C, I, B, precision, nullptr, nullptr);
 }
 
-extern "C" int32_t sast_layer_is_fused(int32_t C, int32_t I, int32_t precision, int32_t enable_cb) {
+extern "C" int32_t sast_layer_is_fused(int64_t P, int32_t C, int32_t I, int32_t precision, int32_t enable_cb) {
   sast_layer_args a{};
+  a.g.B = 1; a.g.H = 1; a.g.W = (int32_t)(P > 0x7fffffff ? 0x7fffffff : P);
   a.g.C = C; a.w.I = I; a.precision = precision; a.enable_cb = enable_cb;
   return sast::fused_layer_supported(a) ? 1 : 0;
 }

@@ -274,8 +274,16 @@ __global__ void __launch_bounds__(kSelThreads) select_scan_kernel(SelectParams p
   for (int j = threadIdx.x; j < pack_n; j += blockDim.x) {
     const int slot = b * g.N + j;
     const int n = sel.tiles[2 * slot] - b * g.N, m = sel.tiles[2 * slot + 1] - b * g.N;
+    // "aligned" tiles: exactly two selected windows of <= 64 tokens each (the dense 1 Mpx case: 2 x 60).  The fused layer
+    // kernel then places the second window at tile row 64, so that a row's keys never straddle a 64-column block of S.
+    int nsel = 0, k0 = 0, k1 = 0;
+    for (int w = n; w < m; ++w) {
+      const int K = pre[w + 1] - pre[w];
+      if (K > 0) { if (nsel == 0) k0 = K; else k1 = K; ++nsel; }
+    }
+    const int split = (nsel == 2 && k0 <= 64 && k1 <= 64) ? k0 : 0;
     sel.tile_list[2 * (pack_base + j)] = frame_base + pre[n];
-    sel.tile_list[2 * (pack_base + j) + 1] = pre[m] - pre[n];
+    sel.tile_list[2 * (pack_base + j) + 1] = (pre[m] - pre[n]) | (split << 8);
   }
 }
 

@@ -468,7 +468,7 @@ WEIGHT_ORDER = ("ln1_w", "ln1_b", "ln2_w", "ln2_b", "qkv_w", "qkv_b", "proj_w", 
 
 def _layer_workspace(lib, P, Cc, mlp_inner, B, precision, enable_cb, device):
     """Scratch of the multi-kernel chain; the fused one-kernel layer (sast_layer_is_fused) needs none."""
-    if lib.sast_layer_is_fused(int(Cc), int(mlp_inner), int(precision), int(bool(enable_cb))):
+    if lib.sast_layer_is_fused(int(P), int(Cc), int(mlp_inner), int(precision), int(bool(enable_cb))):
         return None, 0
     nbytes = lib.sast_layer_workspace_bytes(P, Cc, mlp_inner, B, precision)
     return torch.empty(nbytes, device=device, dtype=torch.uint8), nbytes
