@@ -67,12 +67,16 @@ struct Cfg {
   static constexpr int TM_O0 = TPR == 1 ? 64 : 384, TM_OS = TPR == 1 ? 128 : 32;
   static constexpr int TM_GLU = kRing ? 128 : 64;
   static constexpr int GLU_CAP = kRing ? 384 : NCTX == 2 ? 160 : 320;                            // accumulator columns per GLU round
-  static constexpr bool kStagedOut = NCTX == 2;    // final rows through shared memory (dense row segments) or straight from registers
+  // per-channel parameter vectors staged in shared memory once per CTA (floats): the 60 KB of L1 left beside the tile
+  // buffers is swept by every tile's gather, so __ldg of these tiny vectors went back to L2 in every epilogue
+  static constexpr int PV_LN1W = 0, PV_LN1B = C, PV_LN2W = 2 * C, PV_LN2B = 3 * C, PV_QKVB = 4 * C, PV_PROJB = 7 * C,
+                       PV_G1 = 8 * C, PV_B1 = 9 * C, PV_B2 = 9 * C + 2 * I, PV_G2 = 10 * C + 2 * I, PV_FLOATS = 11 * C + 2 * I;
+  static constexpr int OUT_PITCH = C * 4 + 16;     // bytes per staged output row (padding: conflict-free 16-byte stores)
   static constexpr int GLU_ROUNDS = (2 * I + GLU_CAP - 1) / GLU_CAP;
   static constexpr int RING_CHUNKS = 3 * C / 64 + C / 64 + 2 * I / 64 + KB_HID;                  // per tile (ring mode)
   static_assert(C == 64 || C == 128, "fused layer kernel: C = 64 or 128");
   static_assert(NCTX == 1 || (NCTX == 2 && !kRing), "two contexts need resident weights");
-  static_assert(R_BYTES >= 128 * C * 4 && R_BYTES >= KB_HID * 16384, "R region too small");
+  static_assert(R_BYTES >= 128 * (C * 4 + 16) && R_BYTES >= KB_HID * 16384, "R region too small");
   static_assert(CPT == 32 || CPT == 16, "C-wide epilogues read 16 or 32 accumulator columns per thread");
   static_assert(TM_GLU + GLU_CAP <= TM_CTX && 3 * C <= TM_CTX, "TMEM plan");
 };
@@ -186,6 +190,8 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   const uint32_t sW = ptx::smem_u32(base);
   if ((sW & 1023u) != 0) __trap();
   CtlT* ctl = reinterpret_cast<CtlT*>(base + K::W_BYTES + NCTX * K::CTX_BYTES);
+  float* const spv = reinterpret_cast<float*>(base + K::W_BYTES + NCTX * K::CTX_BYTES + ((sizeof(CtlT) + 15) / 16) * 16);
+  const uint32_t sPV = sW + K::W_BYTES + NCTX * K::CTX_BYTES + ((sizeof(CtlT) + 15) / 16) * 16;
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(kFull, tid >> 5, 0), lane = tid & 31;
@@ -210,6 +216,20 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     }
   }
   if (warp == 0) ptx::tmem_alloc(&ctl->tmem_base, 512);
+  for (int i = threadIdx.x; i < K::PV_FLOATS; i += blockDim.x) {        // parameters are constants of the forward: before the PDL wait
+    float v;
+    if (i < K::PV_LN1B) v = p.ln1_w[i];
+    else if (i < K::PV_LN2W) v = p.ln1_b[i - K::PV_LN1B];
+    else if (i < K::PV_LN2B) v = p.ln2_w[i - K::PV_LN2W];
+    else if (i < K::PV_QKVB) v = p.ln2_b[i - K::PV_LN2B];
+    else if (i < K::PV_PROJB) v = p.qkv_b ? p.qkv_b[i - K::PV_QKVB] : 0.f;
+    else if (i < K::PV_G1) v = p.proj_b ? p.proj_b[i - K::PV_PROJB] : 0.f;
+    else if (i < K::PV_B1) v = p.gamma1 ? p.gamma1[i - K::PV_G1] : 1.f;
+    else if (i < K::PV_B2) v = p.mlp1_b ? p.mlp1_b[i - K::PV_B1] : 0.f;
+    else if (i < K::PV_G2) v = p.mlp2_b ? p.mlp2_b[i - K::PV_B2] : 0.f;
+    else v = p.gamma2 ? p.gamma2[i - K::PV_G2] : 1.f;
+    spv[i] = v;
+  }
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
@@ -313,8 +333,8 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         if (todo) {
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.ln1_w + (l + 4 * i) * 4));
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln1_b + (l + 4 * i) * 4));
+            const float4 w4 = lds128(sPV + (uint32_t)(K::PV_LN1W + (l + 4 * i) * 4) * 4);
+            const float4 b4 = lds128(sPV + (uint32_t)(K::PV_LN1B + (l + 4 * i) * 4) * 4);
             *reinterpret_cast<float4*>(p.out + pix * C + (l + 4 * i) * 4) =
                 make_float4((v[i].x - mean) * rstd * w4.x + b4.x, (v[i].y - mean) * rstd * w4.y + b4.y,
                             (v[i].z - mean) * rstd * w4.z + b4.z, (v[i].w - mean) * rstd * w4.w + b4.w);
@@ -380,8 +400,8 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         const float inv_c = 1.0f / (float)C;
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {               // LN1 then LN2 (SAST.py:206, :213)
-          const float* gw = pass == 0 ? p.ln1_w : p.ln2_w;
-          const float* gb = pass == 0 ? p.ln1_b : p.ln2_b;
+          const uint32_t gw = sPV + (uint32_t)(pass == 0 ? K::PV_LN1W : K::PV_LN2W) * 4;
+          const uint32_t gb = sPV + (uint32_t)(pass == 0 ? K::PV_LN1B : K::PV_LN2B) * 4;
           float s = 0.f;
 #pragma unroll
           for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -395,11 +415,15 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           const float rstd = rsqrtf(group4_sum(ss) * inv_c + p.eps);
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(gw + (gl + 4 * i) * 4));
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(gb + (gl + 4 * i) * 4));
+            const float4 w4 = lds128(gw + (uint32_t)(gl + 4 * i) * 16);
+            const float4 b4 = lds128(gb + (uint32_t)(gl + 4 * i) * 16);
             v[i].x = (v[i].x - mean) * rstd * w4.x + b4.x; v[i].y = (v[i].y - mean) * rstd * w4.y + b4.y;
             v[i].z = (v[i].z - mean) * rstd * w4.z + b4.z; v[i].w = (v[i].w - mean) * rstd * w4.w + b4.w;
           }
+        }
+        if (ps == 0) {                                         // the previous tile's output rows have left the staging area
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          ctx_sync<TPC>(ctx);
         }
         const uint32_t rr7 = (uint32_t)(r & 7);
 #pragma unroll
@@ -457,11 +481,8 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         const uint32_t sw = (uint32_t)((row >> 1) & 3);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-          if (p.qkv_b) {
-            b0 = __ldg(reinterpret_cast<const float4*>(p.qkv_b + u * 32 + c * 8));
-            b1 = __ldg(reinterpret_cast<const float4*>(p.qkv_b + u * 32 + c * 8 + 4));
-          }
+          const float4 b0 = lds128(sPV + (uint32_t)(K::PV_QKVB + u * 32 + c * 8) * 4);
+          const float4 b1 = lds128(sPV + (uint32_t)(K::PV_QKVB + u * 32 + c * 8 + 4) * 4);
           sts128(dst + (((uint32_t)c ^ sw) << 4),
                  pack_bf16(__uint_as_float(raw[8 * c]) + b0.x, __uint_as_float(raw[8 * c + 1]) + b0.y),
                  pack_bf16(__uint_as_float(raw[8 * c + 2]) + b0.z, __uint_as_float(raw[8 * c + 3]) + b0.w),
@@ -656,9 +677,8 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < CPT; j += 4) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (p.proj_b) b4 = __ldg(reinterpret_cast<const float4*>(p.proj_b + col0 + j));
-          if (p.gamma1) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma1 + col0 + j));
+          const float4 b4 = lds128(sPV + (uint32_t)(K::PV_PROJB + col0 + j) * 4);
+          const float4 g4 = lds128(sPV + (uint32_t)(K::PV_G1 + col0 + j) * 4);
           y[j] = fmaf(g4.x, __uint_as_float(raw[j]) + b4.x, y[j]);
           y[j + 1] = fmaf(g4.y, __uint_as_float(raw[j + 1]) + b4.y, y[j + 1]);
           y[j + 2] = fmaf(g4.z, __uint_as_float(raw[j + 2]) + b4.z, y[j + 2]);
@@ -704,8 +724,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           uint32_t pk[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.mlp1_b) b4 = __ldg(reinterpret_cast<const float4*>(p.mlp1_b + ac + 4 * j));
+            const float4 b4 = lds128(sPV + (uint32_t)(K::PV_B1 + ac + 4 * j) * 4);
             pk[j] = pack_bf16(glu_tanh_fit(0.5f * (__uint_as_float(raw[4 * j]) + b4.x), __uint_as_float(raw[4 * j + 1]) + b4.y),
                               glu_tanh_fit(0.5f * (__uint_as_float(raw[4 * j + 2]) + b4.z), __uint_as_float(raw[4 * j + 3]) + b4.w));
           }
@@ -741,41 +760,34 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         if constexpr (CPT == 32) ptx::tmem_ld_32x32(tm + lane_sel + (uint32_t)col0, raw);
         else ptx::tmem_ld_32x16(tm + lane_sel + (uint32_t)col0, raw);
         ptx::tmem_ld_wait();
-        // kStagedOut: rows -> shared memory (hid is dead: its MMA has completed), then dense row segments to the map (a
-        // thread owns CPT columns of ONE row here: as direct stores 32 different 128-byte lines per instruction)
-        float* op = p.out + (long long)ctl->pix[ctx][row] * C + col0;
+        // rows -> shared memory (hid is dead: its MMA has completed; 16-byte padded pitch: conflict-free), then ONE bulk
+        // async copy per row to the map (scatter-back): a thread owns CPT columns of one row here, which as direct stores
+        // would be 32 half-filled sectors per instruction
 #pragma unroll
         for (int j = 0; j < CPT; j += 4) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (p.mlp2_b) b4 = __ldg(reinterpret_cast<const float4*>(p.mlp2_b + col0 + j));
-          if (p.gamma2) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma2 + col0 + j));
-          const float4 o = make_float4(fmaf(g4.x, __uint_as_float(raw[j]) + b4.x, y[j]), fmaf(g4.y, __uint_as_float(raw[j + 1]) + b4.y, y[j + 1]),
-                                       fmaf(g4.z, __uint_as_float(raw[j + 2]) + b4.z, y[j + 2]), fmaf(g4.w, __uint_as_float(raw[j + 3]) + b4.w, y[j + 3]));
-          if constexpr (K::kStagedOut) {
-            const uint32_t ch4 = (uint32_t)((col0 + j) >> 2);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sR + (uint32_t)(row * C * 4) + ((ch4 ^ r7) << 4)),
-                         "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-          } else if (rvalid) {
-            *reinterpret_cast<float4*>(op + j) = o;
-          }
+          const float4 b4 = lds128(sPV + (uint32_t)(K::PV_B2 + col0 + j) * 4);
+          const float4 g4 = lds128(sPV + (uint32_t)(K::PV_G2 + col0 + j) * 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sR + (uint32_t)(row * K::OUT_PITCH + (col0 + j) * 4)),
+                       "f"(fmaf(g4.x, __uint_as_float(raw[j]) + b4.x, y[j])), "f"(fmaf(g4.y, __uint_as_float(raw[j + 1]) + b4.y, y[j + 1])),
+                       "f"(fmaf(g4.z, __uint_as_float(raw[j + 2]) + b4.z, y[j + 2])), "f"(fmaf(g4.w, __uint_as_float(raw[j + 3]) + b4.w, y[j + 3]))
+                       : "memory");
         }
       }
-      if constexpr (K::kStagedOut) {
-        ptx::tc_fence_before();
-        ctx_sync<TPC>(ctx);
-#pragma unroll
-        for (int ps = 0; ps < 128 / K::RPP; ++ps) {
-          const int r = ps * K::RPP + gr;
-          if (gpix[ps] >= 0) {
-            float* orow = p.out + (long long)gpix[ps] * C;
-#pragma unroll
-            for (int i = 0; i < C / 16; ++i) {
-              const uint32_t ch4 = (uint32_t)(gl + 4 * i);
-              *reinterpret_cast<float4*>(orow + ch4 * 4) = lds128(sR + (uint32_t)(r * C * 4) + ((ch4 ^ (uint32_t)(r & 7)) << 4));
-            }
-          }
+      FL_STAMP(21);
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ctx_sync<TPC>(ctx);
+      FL_STAMP(22);
+      {   // one bulk copy per row, spread over all warps (a warp issues its lanes' copies one after the other)
+        constexpr int RPW = 128 / K::WPC;                    // rows per warp
+        const int orow = cw * RPW + lane;
+        if (lane < RPW && ctl->hi[ctx][orow] > ctl->lo[ctx][orow]) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out + (long long)ctl->pix[ctx][orow] * C),
+                       "r"(sR + (uint32_t)(orow * K::OUT_PITCH)), "r"(C * 4) : "memory");
         }
       }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      FL_STAMP(23);
       ptx::tc_fence_before();
       ctx_sync<TPC>(ctx);                                    // TMEM, the A tile and ctl->pix/lo/hi are free for the next tile
       FL_STAMP(14);
@@ -790,6 +802,7 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 #endif
 
     if (ctx == 0) unselected_pass();
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // the last tile's rows have reached the map
     SAST_STAMP(trc, tid == 0, 18);
   }
 
@@ -821,7 +834,7 @@ static int launch_fused_t(const sast_layer_args& a, const Geom& g, cudaStream_t 
   p.tok_row = a.sel.tok_row;
   p.g = g; p.flavor = a.flavor;
   p.trace = g_trace_which == 4 ? g_trace : nullptr;
-  const size_t smem = (size_t)K::W_BYTES + K::NCTX * K::CTX_BYTES + sizeof(Ctl<K::NCTX, K::TPR>);
+  const size_t smem = (size_t)K::W_BYTES + K::NCTX * K::CTX_BYTES + (sizeof(Ctl<K::NCTX, K::TPR>) + 15) / 16 * 16 + K::PV_FLOATS * 4;
   static thread_local unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(layer_fused_kernel<C, NCTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -848,17 +861,10 @@ bool fused_layer_enabled() {
   return v != 0;
 }
 
-// C = 64: tile contexts per CTA.  Measured equal on the 1 Mpx B=8 stage-1 shape (two 8-warp contexts: 39 k clk per tile and
-// context, 3.46 tiles each; one 16-warp context: 23 k clk per tile, 6.92 tiles): the default is the simpler single context
-// (no register spills); SAST_B200_FUSED_CTX=2 selects the two-context variant (A/B knob).
-static int fused_contexts() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SAST_B200_FUSED_CTX");
-    v = (e && e[0] == '2') ? 2 : 1;
-  }
-  return v;
-}
+// Tile contexts per CTA: the kernel template also instantiates with two independent 8-warp contexts sharing C = 64's
+// resident weights (NCTX = 2).  Measured equal to one 16-warp context on the 1 Mpx B=8 stage-1 shape (19.6 k clk per tile
+// against 23 k, but 3.46 tiles per context quantise to 4 rounds; profiles/r02_fused_trace_v7_2ctx.txt) and no longer
+// fitting shared memory next to the staged parameter vectors, so only NCTX = 1 is built.
 
 // true if this layer can take the fused kernel (bf16 path, C 64 / 128 with the mlp_ratio-4 GLU width, no context broadcast)
 bool fused_layer_supported(const sast_layer_args& a) {
@@ -873,7 +879,7 @@ bool fused_layer_supported(const sast_layer_args& a) {
 
 int launch_layer_fused(const sast_layer_args& a, const Geom& g, cudaStream_t st) {
   if (!a.sel.tile_list || !a.sel.row_win) return SAST_E_NULL;
-  if (g.C == 64) return fused_contexts() == 2 ? fl::launch_fused_t<64, 2>(a, g, st) : fl::launch_fused_t<64, 1>(a, g, st);
+  if (g.C == 64) return fl::launch_fused_t<64, 1>(a, g, st);
   if (g.C == 128) return fl::launch_fused_t<128, 1>(a, g, st);
   return SAST_E_UNSUPPORTED;
 }

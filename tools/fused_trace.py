@@ -57,6 +57,10 @@ if len(t2) == 0:
 for i, n in enumerate(names):
     col = d[:, i]
     print(f"  {n:40s} median {col.median():8.0f}  p90 {col.quantile(0.9):8.0f} clk")
+for a, b, n in ((13, 21, "out: tmem ld + math + st.shared"), (21, 22, "out: fence + sync"), (22, 23, "out: bulk store issue"), (23, 14, "out: final sync")):
+    if len(t2) and (t2[:, 21] != 0).all():
+        col = (t2[:, b] - t2[:, a]).float()
+        print(f"    {n:38s} median {col.median():8.0f}  p90 {col.quantile(0.9):8.0f} clk")
 tot = (t2[:, 14] - t2[:, 0]).float() if len(t2) else torch.zeros(1)
 print(f"  second tile total: median {tot.median():.0f} clk, p90 {tot.quantile(0.9):.0f}")
 for a, b, n in ((15, 16, "entry -> set-up done (incl. PDL wait)"), (16, 17, "all tiles"), (17, 18, "unselected pass"), (15, 18, "kernel total")):
