@@ -469,7 +469,9 @@ int launch_rows_gather(const float* map, float* rows, const sast_selection* sel,
 
 extern "C" size_t sast_layer_workspace_bytes(int64_t P, int32_t C, int32_t I, int32_t B, int32_t precision) {
   if (precision == SAST_BF16_CHAIN) precision = SAST_BF16;
-  return sast::layer_workspace_layout(P, C, I, B, precision, nullptr, nullptr);
+  const size_t chain = sast::layer_workspace_layout(P, C, I, B, precision, nullptr, nullptr);
+  const size_t grp = precision == SAST_BF16 ? sast::group_layer_workspace_bytes(P, C, I) : 0;
+  return chain > grp ? chain : grp;
 }
 
 extern "C" int32_t sast_layer_is_fused(int64_t P, int32_t C, int32_t I, int32_t precision, int32_t enable_cb) {
@@ -511,6 +513,7 @@ extern "C" int sast_layer_fwd(const sast_layer_args* ap, void* stream) {
   const size_t need = layer_workspace_layout(g.P, C, I, g.B, a.precision, a.workspace, &ws);
   if (need > a.workspace_bytes) return SAST_E_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(a.workspace) & 255) != 0) return SAST_E_SHAPE;
+  if (!chain && group_layer_supported(a)) return launch_layer_group(a, g, (cudaStream_t)stream);         // one kernel, CTA groups
   cudaStream_t st = (cudaStream_t)stream;
   const int heads = C / dh;
 

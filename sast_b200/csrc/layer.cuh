@@ -52,4 +52,9 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* att, int C, con
 bool fused_layer_supported(const sast_layer_args& a);
 int launch_layer_fused(const sast_layer_args& a, const Geom& g, cudaStream_t st);
 
+// one kernel per layer with a group of C/64 CTAs per tile (group_layer.cu): bf16 path, C = 256 / 512
+bool group_layer_supported(const sast_layer_args& a);
+int launch_layer_group(const sast_layer_args& a, const Geom& g, cudaStream_t st);
+size_t group_layer_workspace_bytes(long long P, int C, int I);
+
 }  // namespace sast
