@@ -304,7 +304,7 @@ int sast_gemm_bf16_glu(const uint16_t* A, const uint16_t* W, const float* bias, 
  * attention and GEMM kernels write thread-level clock64 stamps of their phase boundaries into buf
  * (attention: [CTA][16], GEMM and scoring: [CTA][128] int64; last slot = SM id).  Pass NULL to switch it off (the default).
  * Only the instrumented build (`make -C sast_b200/csrc trace`) stamps; the regular library ignores the call. */
-void sast_debug_trace(long long* buf, int32_t which /* 1 attention, 2 GEMM, 3 scoring */);
+void sast_debug_trace(long long* buf, int32_t which /* 1 attention, 2 GEMM, 3 scoring, 4 fused layer, 5 group layer */);
 
 /* Library / build info. */
 int sast_abi_version(void);

@@ -71,7 +71,12 @@ struct Params {
   __nv_bfloat16 *n2h, *att, *yh, *hid;
   float* n2f;
   int* flags;                  // [n_groups][4], zero on entry
+  long long* trace;            // debug stamps (sast_debug_trace which = 5), normally null; trace build only
 };
+
+// trace build only: [CTA][32] clock64 stamps of thread 0 at the phase boundaries of the CTA's FIRST tile; 20 kernel entry,
+// 21 set-up done, 22 tiles done, 23 unselected pass done
+#define GL_STAMP(i) SAST_STAMP(trc, tid == 0 && tile_it == 0, (i))
 
 template <int LPT>
 __device__ __forceinline__ float lanes_sum(float v) {
@@ -124,6 +129,8 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(kFull, tid >> 5, 0), lane = tid & 31;
+  [[maybe_unused]] long long* const trc = p.trace ? p.trace + (size_t)blockIdx.x * 32 : nullptr;
+  SAST_STAMP(trc, tid == 0, 20);
   const int group = blockIdx.x / G, slice = blockIdx.x % G, n_groups = gridDim.x / G;
 
   if (tid == 0) {
@@ -156,6 +163,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
 
   pdl_entry();
   const int n_tiles = p.counts[3];
+  SAST_STAMP(trc, tid == 0, 21);
   const int srow = group * 128;                              // this group's rows of the scratch buffers
 
   if (warp == 16) {
@@ -232,6 +240,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
     };
 
     for (int t = group; t < n_tiles; t += n_groups, ++tile_it) {
+      GL_STAMP(0);
       const int row0 = p.tile_list[2 * t];
       int rows = p.tile_list[2 * t + 1];
       const int split = rows >> 8;
@@ -274,7 +283,9 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
           *reinterpret_cast<float4*>(frow + c) = v[i];
         }
       }
+      GL_STAMP(1);
       group_sync(0);
+      GL_STAMP(2);
 
       // ---- QKV slice (heads 2s, 2s+1) ----
       if (mma_warp) {
@@ -291,6 +302,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
         }
       }
       wait_mma();
+      GL_STAMP(3);
       for (int u = sub; u < 6; u += 4) {                     // 32 accumulator columns = q, k or v of one head
         uint32_t raw[32];
         ptx::tmem_ld_32x32(tm + lane_sel + (uint32_t)(u * 32), raw);
@@ -314,6 +326,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
       ptx::tc_fence_before();
       compute_sync();
 
+      GL_STAMP(4);
       // ---- attention of the two heads (same code as the one-CTA kernel, two softmax threads per row) ----
       const int lo = ctl->lo[row], hi = ctl->hi[row];
       const bool rvalid = hi > lo;
@@ -418,7 +431,9 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
         }
         ptx::tc_fence_before();
       }
+      GL_STAMP(5);
       group_sync(1);
+      GL_STAMP(6);
 
       // ---- proj slice + LayerScale + shortcut ----
       if (mma_warp) {
@@ -427,6 +442,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
         if (leader) ptx::umma_commit(&ctl->mma_bar);
       }
       wait_mma();
+      GL_STAMP(7);
       {
         const int col0 = sub * 16;
         uint32_t raw[16];
@@ -448,7 +464,9 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
                                                                pack_bf16(y[8 * c + 4], y[8 * c + 5]), pack_bf16(y[8 * c + 6], y[8 * c + 7]));
       }
       ptx::tc_fence_before();
+      GL_STAMP(8);
       group_sync(2);
+      GL_STAMP(9);
 
       // ---- GLU slice: 336 accumulator columns in two passes over y ----
       if (mma_warp) {
@@ -458,6 +476,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
         if (leader) ptx::umma_commit(&ctl->mma_bar);
       }
       wait_mma();
+      GL_STAMP(10);
       for (int u = sub; u < 2 * IS / 16; u += 4) {            // 16 accumulator columns -> 8 hid columns = 16 bytes
         uint32_t raw[16];
         ptx::tmem_ld_32x16(tm + lane_sel + (uint32_t)(128 + 16 * u), raw);
@@ -472,7 +491,9 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
         *reinterpret_cast<uint4*>(p.hid + (size_t)(srow + row) * I + IS * slice + 8 * u) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       ptx::tc_fence_before();
+      GL_STAMP(11);
       group_sync(3);
+      GL_STAMP(12);
 
       // ---- MLP-out slice + LayerScale + residual + scatter-back ----
       if (mma_warp) {
@@ -481,6 +502,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
         if (leader) ptx::umma_commit(&ctl->mma_bar);
       }
       wait_mma();
+      GL_STAMP(13);
       {
         const int col0 = sub * 16;
         uint32_t raw[16];
@@ -510,7 +532,9 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the staging area is the next tile's Q,K,V tiles
       ptx::tc_fence_before();
       compute_sync();
+      GL_STAMP(14);
     }
+    SAST_STAMP(trc, tid == 0, 22);
 
     // ---- unselected tokens keep norm1(x): this CTA's share of the map, LPT lanes per token ----
     {
@@ -533,6 +557,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
       }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    SAST_STAMP(trc, tid == 0, 23);
   }
 
   ptx::tc_fence_before();
@@ -585,6 +610,7 @@ static int launch_group_t(const sast_layer_args& a, const Geom& g, cudaStream_t 
   p.counts = a.sel.counts; p.tile_list = a.sel.tile_list; p.row_pix = a.sel.row_pix; p.row_win = a.sel.row_win;
   p.tok_row = a.sel.tok_row;
   p.g = g; p.flavor = a.flavor;
+  p.trace = g_trace_which == 5 ? g_trace : nullptr;
   const size_t smem = (size_t)kStages * kStageBytes + K::R_BYTES + (sizeof(Ctl) + 15) / 16 * 16 + K::PV_FLOATS * 4;
   static thread_local unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {

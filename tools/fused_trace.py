@@ -37,12 +37,28 @@ with torch.no_grad():
         layer.run(x, sel, L.WINDOW, False)
     torch.cuda.synchronize()
     buf = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
-    L.lib().sast_debug_trace(buf.data_ptr(), 4)
+    L.lib().sast_debug_trace(buf.data_ptr(), 4 if stage <= 2 else 5)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush.zero_()
     layer.run(x, sel, L.WINDOW, False)
     torch.cuda.synchronize()
     L.lib().sast_debug_trace(None, 0)
+if stage >= 3:          # group kernel (C = 256 / 512): stamps of each CTA's first tile
+    t = buf.view(-1, 32).cpu()
+    t = t[t[:, 22] != 0]
+    cnt = sel.counts.tolist()
+    print(f"stage {stage}: C={C} keep={keep} S={cnt[1]} tiles={cnt[3]} traced CTAs={len(t)}")
+    names = ["LN of own rows -> scratch", "group barrier 0", "QKV stream + mma", "QKV epilogue + sync", "attention (S, softmax, PV, O -> scratch)",
+             "group barrier 1", "proj stream + mma", "proj epilogue", "group barrier 2", "GLU stream (2 passes) + mma", "GLU epilogue -> scratch",
+             "group barrier 3", "out stream + mma", "out epilogue + stores + sync"]
+    d = (t[:, 1:15] - t[:, 0:14]).float()
+    for i, n in enumerate(names):
+        print(f"  {n:44s} median {d[:, i].median():8.0f}  p90 {d[:, i].quantile(0.9):8.0f} clk")
+    print(f"  first tile total: median {(t[:, 14] - t[:, 0]).float().median():.0f} clk")
+    for a, b, n in ((20, 21, "entry -> set-up done"), (21, 22, "all tiles"), (22, 23, "unselected pass"), (20, 23, "kernel total")):
+        col = (t[:, b] - t[:, a]).float()
+        print(f"  [{n:38s}] median {col.median():9.0f}  max {col.max():9.0f} clk")
+    sys.exit(0)
 t = buf.view(-1, 32).cpu()
 t = t[t[:, 17] != 0]
 t2 = t[t[:, 14] != 0]
