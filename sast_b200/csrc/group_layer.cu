@@ -46,7 +46,7 @@ struct Cfg {
   static constexpr int CHUNKS = 4 * KB + KBI;       // ring chunks per tile: QKV, proj, GLU a, GLU b (KB each), out (KBI)
   static_assert(C == 256 || C == 512, "group layer kernel: C = 256 or 512");
   static_assert(2 * IS == kGluA + kGluB && IS % 8 == 0, "GLU slice");
-  static_assert(128 * OUT_PITCH <= R_BYTES, "output staging");
+  static_assert(128 * OUT_PITCH <= R_BYTES && 128 * IS * 2 <= R_BYTES, "output / hid staging");
 };
 
 struct Ctl {
@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(544, 1)
 layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_constant__ CUtensorMap map_att,
                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_hid,
                    const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_proj,
-                   const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const Params p) {
+                   const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2,
+                   const __grid_constant__ CUtensorMap map_hid_st, const Params p) {
   using K = Cfg<C>;
   constexpr int G = K::G, I = K::I, IS = K::IS, KB = K::KB, KBI = K::KBI, LPT = K::LPT;
   extern __shared__ __align__(1024) uint8_t base[];
@@ -135,7 +136,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
 
   if (tid == 0) {
     ptx::tma_prefetch_desc(&map_n2); ptx::tma_prefetch_desc(&map_att); ptx::tma_prefetch_desc(&map_y); ptx::tma_prefetch_desc(&map_hid);
-    ptx::tma_prefetch_desc(&map_qkv); ptx::tma_prefetch_desc(&map_proj); ptx::tma_prefetch_desc(&map_w1); ptx::tma_prefetch_desc(&map_w2);
+    ptx::tma_prefetch_desc(&map_qkv); ptx::tma_prefetch_desc(&map_proj); ptx::tma_prefetch_desc(&map_w1); ptx::tma_prefetch_desc(&map_w2); ptx::tma_prefetch_desc(&map_hid_st);
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
     ptx::mbar_init(&ctl->mma_bar, 1);
     for (int k = 0; k < 4; ++k) ptx::mbar_init(&ctl->go[k], 1);
@@ -172,21 +173,34 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
     uint32_t it = 0, tile_it = 0;
     for (int t = group; t < n_tiles; t += n_groups, ++tile_it) {
       for (int ph = 0; ph < 5; ++ph) {                       // QKV, proj, GLU a, GLU b, out
-        if (ph != 3) ptx::mbar_wait(&ctl->go[ph == 4 ? 3 : ph], tile_it & 1);     // GLU b reads the same operand as GLU a
         const CUtensorMap* ma = ph == 0 ? &map_n2 : ph == 1 ? &map_att : ph == 4 ? &map_hid : &map_y;
         const CUtensorMap* mw = ph == 0 ? &map_qkv : ph == 1 ? &map_proj : ph == 4 ? &map_w2 : &map_w1;
         const int wrow = ph == 0 ? 192 * slice : ph == 1 ? 64 * slice : ph == 2 ? 2 * IS * slice : ph == 3 ? 2 * IS * slice + kGluA : 64 * slice;
         const uint32_t wbytes = ph == 0 ? 192 * 128 : (ph == 2 || ph == 3) ? kGluA * 128 : 64 * 128;
         const int nkb = ph == 4 ? KBI : KB;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % kStages, round = it / kStages;
+        // the weight chunks do not depend on the partners: the first ring-full of them is in flight BEFORE the phase's group
+        // barrier opens; the operand chunks (written by the partners) follow it
+        const int pre = ph == 3 ? 0 : (nkb < kStages ? nkb : kStages);        // GLU b reads the same operand as GLU a: no barrier
+        for (int kb = 0; kb < pre; ++kb) {
+          const uint32_t s = (it + kb) % kStages, round = (it + kb) / kStages;
           ptx::mbar_wait(&ctl->empty[s], (round & 1) ^ 1);
           if (leader) {
-            uint8_t* dst = base + s * kStageBytes;
             ptx::mbar_arrive_expect_tx(&ctl->full[s], 16384 + wbytes);
-            ptx::tma_load_2d(dst, ma, &ctl->full[s], 64 * kb, srow);
-            ptx::tma_load_2d(dst + kWOff, mw, &ctl->full[s], 64 * kb, wrow);
+            ptx::tma_load_2d(base + s * kStageBytes + kWOff, mw, &ctl->full[s], 64 * kb, wrow);
           }
+        }
+        if (ph != 3) ptx::mbar_wait(&ctl->go[ph == 4 ? 3 : ph], tile_it & 1);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % kStages, round = it / kStages;
+          uint8_t* dst = base + s * kStageBytes;
+          if (kb >= pre) {
+            ptx::mbar_wait(&ctl->empty[s], (round & 1) ^ 1);
+            if (leader) {
+              ptx::mbar_arrive_expect_tx(&ctl->full[s], 16384 + wbytes);
+              ptx::tma_load_2d(dst + kWOff, mw, &ctl->full[s], 64 * kb, wrow);
+            }
+          }
+          if (leader) ptx::tma_load_2d(dst, ma, &ctl->full[s], 64 * kb, srow);
         }
       }
     }
@@ -219,10 +233,18 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
         ++ring_it;
       }
     };
-    // group barrier k: every CTA of the group has written its slice of the phase's output to the scratch area
-    auto group_sync = [&](int k) {
+    // group barrier k: every CTA of the group has written its slice of the phase's output to the scratch area.  Slices
+    // staged in shared memory (att, y: one SWIZZLE_128B k-block tile; hid: dense rows) leave through ONE TMA tensor store
+    // issued by thread 0 here (store_map != nullptr), instead of 16-byte global stores with one row per lane.
+    auto group_sync = [&](int k, const CUtensorMap* store_map, int c0) {
+      if (store_map) ptx::fence_proxy_async();
       compute_sync();
       if (ct == 0) {
+        if (store_map) {
+          ptx::tma_store_2d(store_map, sR, c0, srow);
+          ptx::bulk_commit();
+          ptx::bulk_wait_all();
+        }
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores before the TMA (async proxy) loads of the partners
         atomicAdd(flags + k, 1);
@@ -284,7 +306,7 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
         }
       }
       GL_STAMP(1);
-      group_sync(0);
+      group_sync(0, nullptr, 0);
       GL_STAMP(2);
 
       // ---- QKV slice (heads 2s, 2s+1) ----
@@ -419,20 +441,22 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
           ptx::tmem_ld_32x16(tm + lane_sel + (uint32_t)(384 + 32 * hh + 16 * half), raw);
           ptx::tmem_ld_wait();
           const float il = rvalid ? __fdividef(1.0f, ctl->psum[hh][0][row] + ctl->psum[hh][1][row]) : 0.f;
-          // att[row][64 s + 32 hh + 16 half ..] -> scratch (the A operand of every slice's proj GEMM)
-          __nv_bfloat16* dst = p.att + (size_t)(srow + row) * C + 64 * slice + 32 * hh + 16 * half;
+          // att slice [128 x 64] bf16 as one SWIZZLE_128B k-block tile in shared memory (Q,K,V are dead: P V has completed);
+          // the group barrier's TMA store moves it to the scratch area (the A operand of every slice's proj GEMM)
+          const uint32_t dst = sR + (uint32_t)(row * 128);
+          const uint32_t ch = (uint32_t)(4 * hh + 2 * half), r7 = (uint32_t)(row & 7);
 #pragma unroll
           for (int c = 0; c < 2; ++c)
-            *reinterpret_cast<uint4*>(dst + 8 * c) =
-                make_uint4(pack_bf16(__uint_as_float(raw[8 * c]) * il, __uint_as_float(raw[8 * c + 1]) * il),
-                           pack_bf16(__uint_as_float(raw[8 * c + 2]) * il, __uint_as_float(raw[8 * c + 3]) * il),
-                           pack_bf16(__uint_as_float(raw[8 * c + 4]) * il, __uint_as_float(raw[8 * c + 5]) * il),
-                           pack_bf16(__uint_as_float(raw[8 * c + 6]) * il, __uint_as_float(raw[8 * c + 7]) * il));
+            sts128(dst + (((ch + c) ^ r7) << 4),
+                   pack_bf16(__uint_as_float(raw[8 * c]) * il, __uint_as_float(raw[8 * c + 1]) * il),
+                   pack_bf16(__uint_as_float(raw[8 * c + 2]) * il, __uint_as_float(raw[8 * c + 3]) * il),
+                   pack_bf16(__uint_as_float(raw[8 * c + 4]) * il, __uint_as_float(raw[8 * c + 5]) * il),
+                   pack_bf16(__uint_as_float(raw[8 * c + 6]) * il, __uint_as_float(raw[8 * c + 7]) * il));
         }
         ptx::tc_fence_before();
       }
       GL_STAMP(5);
-      group_sync(1);
+      group_sync(1, &map_att, 64 * slice);
       GL_STAMP(6);
 
       // ---- proj slice + LayerScale + shortcut ----
@@ -457,15 +481,16 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
           y[j + 2] = fmaf(g4.z, __uint_as_float(raw[j + 2]) + b4.z, y[j + 2]);
           y[j + 3] = fmaf(g4.w, __uint_as_float(raw[j + 3]) + b4.w, y[j + 3]);
         }
-        __nv_bfloat16* dst = p.yh + (size_t)(srow + row) * C + 64 * slice + col0;
+        const uint32_t dst = sR + (uint32_t)(row * 128);
+        const uint32_t ch = (uint32_t)(col0 >> 3), r7 = (uint32_t)(row & 7);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
-          *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(pack_bf16(y[8 * c], y[8 * c + 1]), pack_bf16(y[8 * c + 2], y[8 * c + 3]),
-                                                               pack_bf16(y[8 * c + 4], y[8 * c + 5]), pack_bf16(y[8 * c + 6], y[8 * c + 7]));
+          sts128(dst + (((ch + c) ^ r7) << 4), pack_bf16(y[8 * c], y[8 * c + 1]), pack_bf16(y[8 * c + 2], y[8 * c + 3]),
+                 pack_bf16(y[8 * c + 4], y[8 * c + 5]), pack_bf16(y[8 * c + 6], y[8 * c + 7]));
       }
       ptx::tc_fence_before();
       GL_STAMP(8);
-      group_sync(2);
+      group_sync(2, &map_y, 64 * slice);
       GL_STAMP(9);
 
       // ---- GLU slice: 336 accumulator columns in two passes over y ----
@@ -488,11 +513,11 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
           pk[j] = pack_bf16(glu_tanh_fit(0.5f * (__uint_as_float(raw[4 * j]) + b4.x), __uint_as_float(raw[4 * j + 1]) + b4.y),
                             glu_tanh_fit(0.5f * (__uint_as_float(raw[4 * j + 2]) + b4.z), __uint_as_float(raw[4 * j + 3]) + b4.w));
         }
-        *reinterpret_cast<uint4*>(p.hid + (size_t)(srow + row) * I + IS * slice + 8 * u) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        sts128(sR + (uint32_t)(row * (IS * 2) + 16 * u), pk[0], pk[1], pk[2], pk[3]);     // dense [128][IS] bf16: the TMA store's box
       }
       ptx::tc_fence_before();
       GL_STAMP(11);
-      group_sync(3);
+      group_sync(3, &map_hid_st, IS * slice);
       GL_STAMP(12);
 
       // ---- MLP-out slice + LayerScale + residual + scatter-back ----
@@ -603,6 +628,8 @@ static int launch_group_t(const sast_layer_args& a, const Geom& g, cudaStream_t 
   if ((rc = make_tmap_bf16_box(&mp, w.proj_w_bf16, C, C, C, 64, 64, 128))) return rc;
   if ((rc = make_tmap_bf16_box(&m1, w.mlp1_w_bf16, 2 * K::I, C, C, 64, kGluA, 128))) return rc;
   if ((rc = make_tmap_bf16_box(&m2, w.mlp2_w_bf16, C, K::I, K::I, 64, 64, 128))) return rc;
+  CUtensorMap mhs;                                               // hid slice store: dense [128 x IS] box, no swizzle
+  if ((rc = make_tmap_bf16_box(&mhs, p.hid, (long long)rows, K::I, K::I, K::IS, 128, 0))) return rc;
   p.x = a.x; p.out = a.out;
   p.ln1_w = w.ln1_w; p.ln1_b = w.ln1_b; p.ln2_w = w.ln2_w; p.ln2_b = w.ln2_b;
   p.qkv_b = w.qkv_b; p.proj_b = w.proj_b; p.gamma1 = w.gamma1; p.gamma2 = w.gamma2; p.mlp1_b = w.mlp1_b; p.mlp2_b = w.mlp2_b;
@@ -617,7 +644,7 @@ static int launch_group_t(const sast_layer_args& a, const Geom& g, cudaStream_t 
     cudaError_t e2 = cudaFuncSetAttribute(layer_group_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e2 != cudaSuccess) return (int)e2;
   }
-  sast::launch_k(layer_group_kernel<C>, (unsigned)(n_groups * K::G), 544, smem, st, mn, ma, my, mh, mq, mp, m1, m2, p);
+  sast::launch_k(layer_group_kernel<C>, (unsigned)(n_groups * K::G), 544, smem, st, mn, ma, my, mh, mq, mp, m1, m2, mhs, p);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }
