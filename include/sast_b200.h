@@ -277,6 +277,29 @@ int sast_stem_fwd(const uint8_t* x, int32_t B, int32_t Cin, int32_t H, int32_t W
                   float eps, float* out, void* stream);
 
 /*
+ * TMA-fed stem for the 16-bit mode (same reference lines as sast_stem_fwd), two calls:
+ *
+ * sast_events_nhwc: the event histogram src -- bit-packed along x (bits = 1 / 4, the format of
+ * sast_unpack_nonzero_ratio) or plain uint8 (bits = 8), NCHW [B,Cin,H,W*bits/8] -- becomes xh = fp16 NHWC
+ * [B, H+8, W+8, Cin] with the stem's replicate padding of 3 materialised (row yy = source row clamp(yy-3), column xx =
+ * source column clamp(xx-3); the trailing 5 rows / columns are zeros).  With r != NULL it also computes the scene
+ * sparsity ratios r [4,B,Cin] exactly as sast_nonzero_ratio does (scratch: B*Cin*4 zeroed int32, left zeroed).
+ * W % 32 == 0, Cin == 20 (the stem it feeds).
+ *
+ * sast_stem_nhwc_fwd: xh -> out [B,H/4,W/4,Cout] fp32 NHWC = LayerNorm(conv 7x7, stride 4, no bias).  The im2col operand
+ * is read by TMA straight from xh (a 5-D overlapping-stride tensor map), the fp16 weights stay resident in shared
+ * memory: w16 is fp16 [7*Cout, 144], row ky*Cout + n = conv.weight[n, :, ky, :] ordered (kx, c) followed by 4 zeros.
+ * One fp16 rounding per weight (finer than the TF32 rounding of the cuDNN convolution it replaces); event counts are
+ * exact.  Geometry: sast_stem_nhwc_supported (Cin 20, Cout 64, H % 4 == 0, W % 32 == 0) -- else SAST_E_UNSUPPORTED and
+ * the caller takes sast_stem_fwd.
+ */
+int sast_events_nhwc(const uint8_t* src, int32_t bits, int32_t B, int32_t Cin, int32_t H, int32_t W, uint16_t* xh, float* r,
+                     int32_t* scratch, void* stream);
+int sast_stem_nhwc_supported(int32_t Cin, int32_t H, int32_t W, int32_t Cout);
+int sast_stem_nhwc_fwd(const uint16_t* xh, int32_t B, int32_t Cin, int32_t H, int32_t W, const uint16_t* w16, int32_t Cout,
+                       const float* ln_w, const float* ln_b, float eps, float* out, void* stream);
+
+/*
  * Conv-LSTM cell as one kernel (ref: models/layers/rnn.py:36-69 with dws_conv False): the 1x1 conv of
  * [x | h_prev] as a TF32 tcgen05 GEMM straight from the fp32 NHWC maps, gates in the epilogue.
  * x, h_prev, c_prev, h_out, c_out: [P,C] fp32 (NHWC rows); h_prev/c_prev both NULL = zero state.

@@ -95,6 +95,25 @@ class ConvDownsampling_Cf2Cl(nn.Module):
                 and pad == 3 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0 and c.out_channels % 32 == 0
                 and c.out_channels <= 256 and getattr(self, "fused_stem", True))
 
+    def nhwc_stem_ok(self, Cin: int, H: int, W: int) -> bool:
+        """The TMA-fed stem (fp16 weights resident in shared memory, operand read by TMA from the fp16 NHWC copy of the
+        histogram, stem_nhwc.cu): taken where the cuDNN convolution it replaces would round its operands to TF32
+        (torch.backends.cudnn.allow_tf32, the PyTorch default); the split-weight fp32-grade stem (stem_tc.cu) otherwise."""
+        c = self.conv
+        pad = c.padding[0] if isinstance(c.padding, tuple) else int(c.padding)
+        return (tuple(c.kernel_size) == (7, 7) and tuple(c.stride) == (4, 4) and pad == 3 and c.in_channels == Cin
+                and torch.backends.cudnn.allow_tf32 and getattr(self, "fused_stem", True) and getattr(self, "nhwc_stem", True)
+                and not (torch.is_grad_enabled() and c.weight.requires_grad)
+                and ops.stem_nhwc_supported(Cin, H, W, c.out_channels))
+
+    def _stem_pack_nhwc(self):
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_nkey", None) != key:
+            self._npack = ops.pack_stem_weight_nhwc(w)
+            self._nkey = key
+        return self._npack
+
     def _stem_pack(self):
         w = self.conv.weight
         key = (w.data_ptr(), w._version)
@@ -115,6 +134,8 @@ class ConvDownsampling_Cf2Cl(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         """x: NCHW (the stem takes the raw uint8 / int32 / float histogram; later stages take the
         previous stage's h, NCHW-logical over channels-last memory).  Returns NHWC fp32."""
+        if isinstance(x, ops.EventsNHWC):
+            return ops.stem_nhwc_fwd(x.xh, x.H, x.W, self._stem_pack_nhwc(), self.norm.weight, self.norm.bias, self.norm.eps)
         if torch.is_grad_enabled() and (x.requires_grad or self.conv.weight.requires_grad):
             # training: the dense callers run as stock differentiable torch ops (cuDNN conv + LayerNorm)
             y = self.conv(x.float()).permute(0, 2, 3, 1)
@@ -344,7 +365,14 @@ class RNNDetector(BaseDetector):
         assert len(prev_states) == self.num_stages
         states: List[Tuple[Tensor, Tensor]] = []
         output: Dict[int, Tensor] = {}
-        if isinstance(x, ops.PackedEvents):      # bit-packed histogram: unpacked in the pass that computes r
+        stem = self.stages[0].downsample_cf2cl
+        packed = isinstance(x, ops.PackedEvents)
+        if ((packed or (x.dtype == torch.uint8 and x.dim() == 4)) and x.is_cuda and hasattr(stem, "nhwc_stem_ok")
+                and stem.nhwc_stem_ok(x.shape[1], x.shape[2], x.shape[3])):
+            # histogram -> fp16 NHWC (padding materialised) in one pass next to the scene sparsity ratios: the stem's TMA operand
+            xh, r = ops.events_nhwc(x.data if packed else x, x.bits if packed else 8, x.shape[3], True)
+            x = ops.EventsNHWC(xh, x.shape[2], x.shape[3])
+        elif packed:                             # bit-packed histogram: unpacked in the pass that computes r
             x, r = ops.unpack_nonzero_ratio(x.data, x.bits, x.width)
         else:
             r = non_zero_ratio(x)

@@ -746,6 +746,69 @@ def pack_stem_weight(w: Tensor) -> Tuple[Tensor, Tensor, int]:
     return hi.contiguous(), lo.contiguous(), gpad
 
 
+def pack_stem_weight_nhwc(w: Tensor) -> Tensor:
+    """conv.weight [Cout,Cin,7,7] fp32 -> fp16 [7*Cout, 144] for sast_stem_nhwc_fwd: row ky*Cout + n holds w[n, :, ky, :]
+    ordered (kx, c), zero-padded from 7*Cin = 140 to 144."""
+    Cout, Cin, kh, kw = w.shape
+    assert (kh, kw) == (7, 7) and 7 * Cin <= 144
+    wp = torch.zeros(7, Cout, 144, device=w.device, dtype=torch.float32)
+    wp[:, :, :7 * Cin] = w.detach().float().permute(2, 0, 3, 1).reshape(7, Cout, 7 * Cin)      # [ky, n, kx, c]
+    return wp.reshape(7 * Cout, 144).to(torch.float16).contiguous()
+
+
+def stem_nhwc_supported(Cin: int, H: int, W: int, Cout: int) -> bool:
+    return bool(L.lib().sast_stem_nhwc_supported(int(Cin), int(H), int(W), int(Cout)))
+
+
+class EventsNHWC:
+    """The stem's input after :func:`events_nhwc`: fp16 [B, H+8, W+8, Cin] with the replicate padding materialised."""
+
+    def __init__(self, xh: Tensor, H: int, W: int):
+        self.xh, self.H, self.W = xh, H, W
+
+
+@torch.library.custom_op("sast::events_nhwc", mutates_args=())
+def events_nhwc(data: Tensor, bits: int, width: int, want_r: bool) -> Tuple[Tensor, Tensor]:
+    """histogram (packed uint8 [B,Cin,H,W*bits/8], bits 1 / 4; or uint8 [B,Cin,H,W], bits 8) -> (xh fp16
+    [B,H+8,W+8,Cin], r [B,4,Cin] (empty unless want_r)); see sast_events_nhwc."""
+    L.require_cuda(data, "data")
+    assert data.dtype == torch.uint8
+    data = data.contiguous()
+    B, Cin, H, _ = data.shape
+    xh = torch.empty(B, H + 8, width + 8, Cin, device=data.device, dtype=torch.float16)
+    r = torch.empty(4, B, Cin, device=data.device, dtype=torch.float32)
+    scratch = torch.zeros(B * Cin * 4, device=data.device, dtype=torch.int32) if want_r else None
+    L.run(data.device, "sast_events_nhwc", data.data_ptr(), int(bits), B, Cin, H, int(width), xh.data_ptr(),
+          r.data_ptr() if want_r else 0, L.ptr(scratch))
+    return xh, r.permute(1, 0, 2)
+
+
+@events_nhwc.register_fake
+def _(data, bits, width, want_r):
+    B, Cin, H, _ = data.shape
+    return (data.new_empty(B, H + 8, width + 8, Cin, dtype=torch.float16),
+            data.new_empty(4, B, Cin, dtype=torch.float32).permute(1, 0, 2))
+
+
+@torch.library.custom_op("sast::stem_nhwc_fwd", mutates_args=())
+def stem_nhwc_fwd(xh: Tensor, H: int, W: int, w16: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tensor], eps: float) -> Tensor:
+    """fp16 [B,H+8,W+8,Cin] -> LayerNorm(conv7x7/4) fp32 NHWC [B,H/4,W/4,Cout]; see sast_stem_nhwc_fwd."""
+    L.require_cuda(xh, "xh")
+    assert xh.dtype == torch.float16 and xh.is_contiguous() and w16.dtype == torch.float16 and w16.is_contiguous()
+    B, Hp, Wp, Cin = xh.shape
+    assert (Hp, Wp) == (H + 8, W + 8)
+    Cout = w16.shape[0] // 7
+    out = torch.empty(B, H // 4, W // 4, Cout, device=xh.device, dtype=torch.float32)
+    L.run(xh.device, "sast_stem_nhwc_fwd", xh.data_ptr(), B, Cin, int(H), int(W), w16.data_ptr(), Cout, L.ptr(ln_w), L.ptr(ln_b),
+          float(eps), out.data_ptr())
+    return out
+
+
+@stem_nhwc_fwd.register_fake
+def _(xh, H, W, w16, ln_w, ln_b, eps):
+    return xh.new_empty(xh.shape[0], H // 4, W // 4, w16.shape[0] // 7, dtype=torch.float32)
+
+
 @torch.library.custom_op("sast::stem_fwd", mutates_args=())
 def stem_fwd(x: Tensor, w_hi: Tensor, w_lo: Tensor, n_groups_pad: int, ln_w: Optional[Tensor], ln_b: Optional[Tensor],
              eps: float) -> Tensor:

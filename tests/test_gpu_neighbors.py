@@ -123,3 +123,51 @@ def test_fused_stem(B, H, W, cout, density):
     assert got.shape == ref.shape
     assert (got.cpu() - ref).abs().max() < 1e-4, (got.cpu() - ref).abs().max()
     assert (got_cudnn.cpu() - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("bits,B,H,W,density", [(1, 2, 384, 640, 0.03), (4, 1, 256, 320, 0.3), (8, 3, 100, 96, 0.5),
+                                                (1, 1, 64, 64, 0.01), (8, 2, 36, 160, 0.9)])
+def test_nhwc_stem(bits, B, H, W, density):
+    """The TMA-fed stem: sast_events_nhwc (histogram -> fp16 NHWC with the replicate padding materialised, + r) is
+    EXACT against plain torch ops; sast_stem_nhwc_fwd (im2col by TMA, fp16 weights resident) against the oracle's fp32
+    conv + LayerNorm within the fp16 weight rounding (2^-12 relative per weight; the TF32 cuDNN route it replaces
+    rounds at 2^-11).  Geometries include ragged tile edges (Ho % 8 != 0, Wo % 16 != 0) and every input format."""
+    cout = 64
+    p = make_params({"conv.weight": (cout, 20, 7, 7), "norm.weight": (cout,), "norm.bias": (cout,)}, seed=bits + H)
+    if bits == 1:
+        x = (torch.rand(B, 20, H, W, generator=torch.Generator().manual_seed(H)) < density).to(torch.uint8)
+    else:
+        x = event_histogram(B, 20, H, W, density, seed=H).clamp_(max=15 if bits == 4 else 255)
+        x[:, :, 0, :] = 7          # make the replicated borders matter
+        x[:, :, :, 0] = 9
+        x[:, :, -1, :] = 3
+        x[:, :, :, -1] = 5
+    x[0, 3] = 0
+    xd = x.to(DEV)
+    src = xd if bits == 8 else sast_b200.pack_events(xd, bits).data
+    xh, r = ops.events_nhwc(src, bits, W, True)
+    ref_h = F.pad(x.float(), (3, 3, 3, 3), mode="replicate").permute(0, 2, 3, 1)
+    assert xh.shape == (B, H + 8, W + 8, 20) and xh.dtype == torch.float16
+    # rows / columns up to H+2 / W+2 are what the stride-4 windows reach (4 (Ho-1) + 6 = H + 2); the rest is zero filler
+    assert torch.equal(xh[:, :H + 3, :W + 3].float().cpu(), ref_h[:, :H + 3, :W + 3])
+    assert float(xh[:, H + 3:].float().abs().max()) == 0 and float(xh[:, :, W + 3:].float().abs().max()) == 0
+    assert torch.equal(r, ops.nonzero_ratio(xd))
+    assert ops.stem_nhwc_supported(20, H, W, cout)
+    got = ops.stem_nhwc_fwd(xh, H, W, ops.pack_stem_weight_nhwc(p["conv.weight"].to(DEV)), p["norm.weight"].to(DEV),
+                            p["norm.bias"].to(DEV), 1e-5)
+    ref = O.conv_downsample(x.float(), p, 4)
+    assert got.shape == ref.shape
+    d = (got.cpu() - ref).abs()
+    assert d.max() < 4e-3 and d.mean() < 4e-4, (d.max(), d.mean())
+    # the same through the module: a backbone stem in the 16-bit mode takes this path, the fp32 mode the split-weight kernel
+    mod = sast_b200.ConvDownsampling_Cf2Cl(20, cout, 4, Config(type="patch", overlap=True, norm_affine=True)).eval()
+    mod.load_state_dict(p)
+    mod = mod.to(DEV)
+    with torch.no_grad():
+        assert mod.nhwc_stem_ok(20, H, W)
+        assert torch.equal(mod(ops.EventsNHWC(xh, H, W)), got)
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            assert not mod.nhwc_stem_ok(20, H, W)
+        finally:
+            torch.backends.cudnn.allow_tf32 = True

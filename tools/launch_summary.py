@@ -11,7 +11,7 @@ detail = len(sys.argv) > 3
 with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
-idx = [i for i, r in enumerate(rows) if any(k in r["Kernel Name"] for k in ("nonzero_count", "nonzero_ratio", "unpack_count"))]
+idx = [i for i, r in enumerate(rows) if any(k in r["Kernel Name"] for k in ("nonzero_count", "nonzero_ratio", "unpack_count", "packed1_count"))]
 idx.append(len(rows))
 which = min(which, len(idx) - 2)
 s, e = idx[which], idx[which + 1]
@@ -22,13 +22,13 @@ for r in rows[s:e]:
         v /= 1000
     tot += v
     name = re.sub(r"\(.*", "", r["Kernel Name"])[:64]
-    if detail and ("sast::" in name or "fl::" in name):
+    if detail and any(p in name for p in ("sast::", "fl::", "gl::", "sn::", "sb::")):
         print(f"{v:8.1f} {r['Grid Size']:>16} {name}")
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += v
 print(f"--- one forward: {e - s} launches, {tot:.1f} us (serialised, cold cache)")
-ours = sum(t for k, (n, t) in agg.items() if "sast::" in k or "fl::" in k)
+ours = sum(t for k, (n, t) in agg.items() if any(p in k for p in ("sast::", "fl::", "gl::", "sn::", "sb::")))
 print(f"--- sast:: kernels {ours:.1f} us ({100 * ours / tot:.0f} %), library/torch kernels {tot - ours:.1f} us")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
     print(f"{t:9.1f} us {100 * t / tot:5.1f}% {n:4d}  {k}")
