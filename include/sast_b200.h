@@ -284,7 +284,7 @@ int sast_stem_fwd(const uint8_t* x, int32_t B, int32_t Cin, int32_t H, int32_t W
  * [B, H+8, W+8, Cin] with the stem's replicate padding of 3 materialised (row yy = source row clamp(yy-3), column xx =
  * source column clamp(xx-3); the trailing 5 rows / columns are zeros).  With r != NULL it also computes the scene
  * sparsity ratios r [4,B,Cin] exactly as sast_nonzero_ratio does (scratch: B*Cin*4 zeroed int32, left zeroed).
- * W % 32 == 0, Cin == 20 (the stem it feeds).
+ * xh == NULL computes only r (the caller feeds sast_stem_bits_fwd).  W % 32 == 0, Cin == 20 (the stem it feeds).
  *
  * sast_stem_nhwc_fwd: xh -> out [B,H/4,W/4,Cout] fp32 NHWC = LayerNorm(conv 7x7, stride 4, no bias).  The im2col operand
  * is read by TMA straight from xh (a 5-D overlapping-stride tensor map), the fp16 weights stay resident in shared
@@ -298,6 +298,19 @@ int sast_events_nhwc(const uint8_t* src, int32_t bits, int32_t B, int32_t Cin, i
 int sast_stem_nhwc_supported(int32_t Cin, int32_t H, int32_t W, int32_t Cout);
 int sast_stem_nhwc_fwd(const uint16_t* xh, int32_t B, int32_t Cin, int32_t H, int32_t W, const uint16_t* w16, int32_t Cout,
                        const float* ln_w, const float* ln_b, float eps, float* out, void* stream);
+
+/*
+ * Stem straight from the 1-bit packed histogram (same reference lines as sast_stem_fwd; the benchmark's binary input,
+ * benchmark.py:58-60): packed uint8 [B,Cin,H,W/8] -> out [B,H/4,W/4,Cout] fp32 NHWC = LayerNorm(conv 7x7, stride 4,
+ * replicate padding 3, no bias).  Nothing is unpacked to memory: the producer warps stage the bits a tile touches in
+ * shared memory and expand 8-bit windows into fp16 operand chunks through a 256-entry table; fp16 weights resident in
+ * shared memory: w16 is fp16 [7*Cout, 160], row ky*Cout + n holds conv.weight[n, c, ky, kx] at column c*8 + kx (column
+ * c*8 + 7 zero).  One fp16 rounding per weight, event bits exact.  Geometry: sast_stem_bits_supported (bits 1, Cin 20,
+ * Cout 64, H % 4 == 0, W % 32 == 0, W >= 64) -- else SAST_E_UNSUPPORTED and the caller takes the NHWC or uint8 stem.
+ */
+int sast_stem_bits_supported(int32_t bits, int32_t Cin, int32_t H, int32_t W, int32_t Cout);
+int sast_stem_bits_fwd(const uint8_t* packed, int32_t bits, int32_t B, int32_t Cin, int32_t H, int32_t W, const uint16_t* w16,
+                       int32_t Cout, const float* ln_w, const float* ln_b, float eps, float* out, void* stream);
 
 /*
  * Conv-LSTM cell as one kernel (ref: models/layers/rnn.py:36-69 with dws_conv False): the 1x1 conv of

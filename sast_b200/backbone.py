@@ -95,16 +95,32 @@ class ConvDownsampling_Cf2Cl(nn.Module):
                 and pad == 3 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0 and c.out_channels % 32 == 0
                 and c.out_channels <= 256 and getattr(self, "fused_stem", True))
 
+    def bits_stem_ok(self, bits: int, Cin: int, H: int, W: int) -> bool:
+        """The stem that reads the 1-bit packed histogram itself (stem_bits.cu); same precision rule as :meth:`nhwc_stem_ok`."""
+        return (getattr(self, "bits_stem", True) and self.nhwc_rule_ok(Cin)
+                and ops.stem_bits_supported(bits, Cin, H, W, self.conv.out_channels))
+
+    def nhwc_rule_ok(self, Cin: int) -> bool:
+        c = self.conv
+        pad = c.padding[0] if isinstance(c.padding, tuple) else int(c.padding)
+        return (tuple(c.kernel_size) == (7, 7) and tuple(c.stride) == (4, 4) and pad == 3 and c.in_channels == Cin
+                and torch.backends.cudnn.allow_tf32 and getattr(self, "fused_stem", True)
+                and not (torch.is_grad_enabled() and c.weight.requires_grad))
+
+    def _stem_pack_bits(self):
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_bkey", None) != key:
+            self._bpack = ops.pack_stem_weight_bits(w)
+            self._bkey = key
+        return self._bpack
+
     def nhwc_stem_ok(self, Cin: int, H: int, W: int) -> bool:
         """The TMA-fed stem (fp16 weights resident in shared memory, operand read by TMA from the fp16 NHWC copy of the
         histogram, stem_nhwc.cu): taken where the cuDNN convolution it replaces would round its operands to TF32
         (torch.backends.cudnn.allow_tf32, the PyTorch default); the split-weight fp32-grade stem (stem_tc.cu) otherwise."""
-        c = self.conv
-        pad = c.padding[0] if isinstance(c.padding, tuple) else int(c.padding)
-        return (tuple(c.kernel_size) == (7, 7) and tuple(c.stride) == (4, 4) and pad == 3 and c.in_channels == Cin
-                and torch.backends.cudnn.allow_tf32 and getattr(self, "fused_stem", True) and getattr(self, "nhwc_stem", True)
-                and not (torch.is_grad_enabled() and c.weight.requires_grad)
-                and ops.stem_nhwc_supported(Cin, H, W, c.out_channels))
+        return (getattr(self, "nhwc_stem", True) and self.nhwc_rule_ok(Cin)
+                and ops.stem_nhwc_supported(Cin, H, W, self.conv.out_channels))
 
     def _stem_pack_nhwc(self):
         w = self.conv.weight
@@ -134,6 +150,8 @@ class ConvDownsampling_Cf2Cl(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         """x: NCHW (the stem takes the raw uint8 / int32 / float histogram; later stages take the
         previous stage's h, NCHW-logical over channels-last memory).  Returns NHWC fp32."""
+        if isinstance(x, ops.PackedEvents):
+            return ops.stem_bits_fwd(x.data, x.bits, x.width, self._stem_pack_bits(), self.norm.weight, self.norm.bias, self.norm.eps)
         if isinstance(x, ops.EventsNHWC):
             return ops.stem_nhwc_fwd(x.xh, x.H, x.W, self._stem_pack_nhwc(), self.norm.weight, self.norm.bias, self.norm.eps)
         if torch.is_grad_enabled() and (x.requires_grad or self.conv.weight.requires_grad):
@@ -367,7 +385,9 @@ class RNNDetector(BaseDetector):
         output: Dict[int, Tensor] = {}
         stem = self.stages[0].downsample_cf2cl
         packed = isinstance(x, ops.PackedEvents)
-        if ((packed or (x.dtype == torch.uint8 and x.dim() == 4)) and x.is_cuda and hasattr(stem, "nhwc_stem_ok")
+        if packed and x.is_cuda and hasattr(stem, "bits_stem_ok") and stem.bits_stem_ok(x.bits, *x.shape[1:]):
+            r = ops.packed_nonzero_ratio(x.data, x.bits, x.width)       # the stem expands the bits itself: nothing unpacked
+        elif ((packed or (x.dtype == torch.uint8 and x.dim() == 4)) and x.is_cuda and hasattr(stem, "nhwc_stem_ok")
                 and stem.nhwc_stem_ok(x.shape[1], x.shape[2], x.shape[3])):
             # histogram -> fp16 NHWC (padding materialised) in one pass next to the scene sparsity ratios: the stem's TMA operand
             xh, r = ops.events_nhwc(x.data if packed else x, x.bits if packed else 8, x.shape[3], True)

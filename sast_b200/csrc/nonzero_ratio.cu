@@ -362,7 +362,8 @@ extern "C" int sast_unpack_nonzero_ratio(const uint8_t* packed, int32_t bits, in
 // sast_nonzero_ratio does (scratch: B*Cin*4 zeroed int32).  W % 32 == 0, Cin == 20.
 extern "C" int sast_events_nhwc(const uint8_t* src, int32_t bits, int32_t B, int32_t Cin, int32_t H, int32_t W, uint16_t* xh,
                                 float* r, int32_t* scratch, void* stream) {
-  SAST_CHECK_PTR(src); SAST_CHECK_PTR(xh);
+  SAST_CHECK_PTR(src);
+  if (!xh && !r) return SAST_E_NULL;                  // xh == NULL: only the ratios (the stem reads the packed bits itself)
   if (B <= 0 || Cin <= 0 || H < 32 || W < 32 || W % 32 != 0) return SAST_E_SHAPE;
   if ((bits != 1 && bits != 4 && bits != 8) || Cin != 20) return SAST_E_UNSUPPORTED;      // the stem it feeds is built for 20 event bins
   if ((reinterpret_cast<uintptr_t>(src) & 3) || (reinterpret_cast<uintptr_t>(xh) & 15)) return SAST_E_SHAPE;
@@ -386,6 +387,7 @@ extern "C" int sast_events_nhwc(const uint8_t* src, int32_t bits, int32_t B, int
                    f[1], f[2], f[3], r);
     SAST_LAUNCH_CHECK();
   }
+  if (!xh) return SAST_OK;
   const size_t smem2 = (size_t)Cin * W * bits / 8 + (size_t)(W + 8) * Cin * 2;
   if (smem2 > 48 * 1024) return SAST_E_UNSUPPORTED;
   const dim3 grid2(H + 8, B), block2(256);

@@ -1,0 +1,344 @@
+// Stem of the backbone straight from the 1-bit packed event histogram (replaces x.float() +
+// replicate padding + Conv2d(k=7, s=4, no bias) + NCHW->NHWC + LayerNorm, ops.py:54-91 / sast_rnn.py:153) for the 16-bit mode:
+//   packed uint8 [B, 20, H, W/8] (bit k of byte j = column 8 j + k)  ->  LayerNorm(conv(x)) fp32 NHWC [B, H/4, W/4, 64].
+//
+// The whole input is 4.9 MB at 1 Mpx B = 8 -- nothing is unpacked to memory.  Per output tile of 8 oy x 16 ox pixels
+// (M = 128) the 35 input rows x 20 bins x 72 columns the tile touches are 8.4 KB of bits: the producer warps stage them in
+// shared memory (shifted so that the 8-column window of output pixel ox_i starts at bit 4 ox_i, replicate padding applied)
+// and build the tcgen05 A operand from there: one (bin c, kernel row ky) group of an output pixel is an 8-bit window ->
+// one 16-byte chunk of 8 fp16 values (kx = 0..6 and a zero-weight 8th tap) through a 256-entry shared-memory table, i.e.
+// two LDS.32 + a funnel shift + LDS.128 + STS.128 per chunk.  K is ordered (ky, c, kx8): a k-block is 8 bins of one ky.
+// As in stem_nhwc.cu an operand tile holds 9 output rows (144 tile rows): rows 0..127 are the operand of kernel row ky,
+// rows 16..143 that of ky + 4 (one output row down = 4 input rows), so each window is expanded once for both.
+//
+// The fp16 weights (one rounding of 2^-12 relative per weight -- finer than the TF32 operand rounding of the cuDNN
+// convolution this replaces; event bits are exact) stay RESIDENT in shared memory: 7 x 20 KB.
+//
+//   warps 0-7   producers: expand the staged bits of this tile into operand k-blocks (2-stage ring)
+//   warp 8      TMEM allocator + MMA issuer (two 64-column accumulators: the epilogue of tile i overlaps tile i+1);
+//               also TMA-loads the weights once
+//   warp 9      stager: global -> shared memory copy of the NEXT tile's bits (double buffer; its load latency and the
+//               producers' proxy fences never meet)
+//   warps 10-13 epilogue: LayerNorm over the channels of each pixel straight from TMEM, swizzled shared-memory transpose,
+//               dense 256-byte row stores
+#include "common.cuh"
+#include "ptx.cuh"
+#include "fused_common.cuh"
+
+namespace sast {
+extern long long* g_trace;
+extern int g_trace_which;
+namespace sb {
+
+constexpr int kCout = 64, kCin = 20;
+constexpr int kKRow = 160;                          // halves per (output channel, ky): 20 bins x 8 taps
+constexpr int kStages = 2;
+constexpr int kABytes = 144 * 128;                  // one operand k-block: 9 oy x 16 ox rows of 128 bytes (8 bins)
+constexpr int kWRow = 2 * 8192 + 4096;              // weights of one ky: two [64 x 64] SW128 tiles + one [64 x 32] SW64 tile
+constexpr int kInRows = 35, kInWords = 3;           // staged bits: 35 input rows x 20 bins x 3 words (72 columns used)
+constexpr int kInBytes = (kInRows * kCin * kInWords * 4 + 1023) / 1024 * 1024;
+constexpr int kItems = kInRows * kCin;              // (row, bin) staging items of a tile
+constexpr int kProducers = 256;
+constexpr int kThreads = 14 * 32;
+
+struct Ctl {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t wbar;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+stem_bits_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w64,
+                 const uint32_t* __restrict__ packed, int B, int H, int W, const float* __restrict__ ln_w,
+                 const float* __restrict__ ln_b, float eps, float* __restrict__ out, long long* trace) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(16) float stage_smem[4][32 * 32];
+  [[maybe_unused]] long long* const trc = trace ? trace + (size_t)blockIdx.x * 32 : nullptr;     // trace build: stamps of the 2nd tile
+  SAST_STAMP(trc, threadIdx.x == 0, 20);
+  uint8_t* const wsm = smem_raw;                                       // 7 x kWRow
+  uint8_t* const ring = wsm + 7 * kWRow;                               // kStages x kABytes
+  uint32_t* const inb = reinterpret_cast<uint32_t*>(ring + kStages * kABytes);     // 2 x kInBytes
+  uint4* const lut = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(inb) + 2 * kInBytes);      // 256 x 16 bytes
+  Ctl* const ctl = reinterpret_cast<Ctl*>(lut + 256);
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
+  const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int Ho = H / 4, Wo = W / 4, words = W / 32;
+  const int tiles_x = (Wo + 15) / 16, tiles_y = (Ho + 7) / 8;
+  const int total_tiles = B * tiles_y * tiles_x;
+
+  if (threadIdx.x == 0) {
+    ptx::tma_prefetch_desc(&map_w); ptx::tma_prefetch_desc(&map_w64);
+    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&ctl->full[s], kProducers / 32); ptx::mbar_init(&ctl->empty[s], 1); }
+    ptx::mbar_init(&ctl->wbar, 1);
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&ctl->tmem_full[a], 1); ptx::mbar_init(&ctl->tmem_empty[a], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < 256) {                       // bit k of the window -> fp16 1.0 / 0.0 at tap k
+    const uint32_t b = threadIdx.x;
+    auto two = [&](int k) { return ((b >> k) & 1u) * 0x3C00u | ((b >> (k + 1)) & 1u) * 0x3C000000u; };
+    lut[b] = make_uint4(two(0), two(2), two(4), two(6));
+  }
+  if (warp == 8) ptx::tmem_alloc(&ctl->tmem_base, 128);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 8 && ptx::elect_one()) {             // the weights are parameters, not a predecessor's output: before the PDL wait
+    ptx::mbar_arrive_expect_tx(&ctl->wbar, 7 * kWRow);
+    for (int ky = 0; ky < 7; ++ky) {
+      ptx::tma_load_2d(wsm + ky * kWRow, &map_w, &ctl->wbar, 0, ky * kCout);
+      ptx::tma_load_2d(wsm + ky * kWRow + 8192, &map_w, &ctl->wbar, 64, ky * kCout);
+      ptx::tma_load_2d(wsm + ky * kWRow + 16384, &map_w64, &ctl->wbar, 128, ky * kCout);
+    }
+  }
+  __syncwarp();
+  pdl_entry();
+  SAST_STAMP(trc, threadIdx.x == 0, 21);
+
+  if (warp < 8) {
+    // ---------------- producers ----------------
+    const int t = threadIdx.x;
+    // static work assignment: a k-block is 144 rows x 8 chunks = 1152 chunks = 4.5 per thread; chunk `item` is bin j = item / 144
+    // of tile row m = item % 144 (lanes = consecutive rows: conflict-free STS.128, broadcast reads of the staged words)
+    constexpr int NC = (144 * 8 + kProducers - 1) / kProducers;      // 5
+    uint32_t src_off[NC], dst_off[NC], shift[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int item = t + i * kProducers;
+      const int j = item / 144, m = item - j * 144, oxi = m & 15;
+      src_off[i] = (uint32_t)((4 * (m >> 4) * kCin + j) * kInWords + (oxi >> 3));     // + (ky4 * kCin + 8 kb) * kInWords
+      shift[i] = (uint32_t)((oxi & 7) * 4) | (item < 144 * 8 ? (uint32_t)j << 8 : 0xFF00u);     // bits 8..: bin j (255: no such chunk)
+      dst_off[i] = (uint32_t)(m * 128 + ((j ^ (m & 7)) << 4));
+    }
+    uint32_t it = 0, ti = 0;
+    asm volatile("bar.sync 1, %0;" ::"n"(kProducers + 32) : "memory");                // tile 0 staged (warp 9)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t* in = inb + (ti & 1) * (kInBytes / 4);
+      SAST_STAMP(trc, t == 0 && ti == 1, 0);
+      for (int ky4 = 0; ky4 < 4; ++ky4) {
+        SAST_STAMP(trc, t == 0 && ti == 1, 1 + ky4);
+        for (int kb = 0; kb < 3; ++kb, ++it) {
+          const uint32_t s = it % kStages, round = it / kStages;
+          const uint32_t* inq = in + (ky4 * kCin + kb * 8) * kInWords;
+          const uint32_t nch = kb < 2 ? 8u : 4u;                       // bins in this k-block (rows 128..143 of ky4 = 3 are never read)
+          // all window reads, then all table reads, then all stores: three short dependent steps instead of five chains
+          uint32_t bits[NC];
+          uint4 v[NC];
+#pragma unroll
+          for (int i = 0; i < NC; ++i) {
+            const uint32_t* wp = inq + src_off[i];
+            bits[i] = (shift[i] >> 8) < nch ? __funnelshift_r(wp[0], wp[1], shift[i] & 31u) & 0xFFu : 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < NC; ++i) v[i] = lut[bits[i]];
+          ptx::mbar_wait(&ctl->empty[s], (round & 1) ^ 1);
+          const uint32_t st = ptx::smem_u32(ring + s * kABytes);
+#pragma unroll
+          for (int i = 0; i < NC; ++i)
+            if ((shift[i] >> 8) < nch) fl::sts128(st + dst_off[i], v[i].x, v[i].y, v[i].z, v[i].w);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&ctl->full[s]);
+        }
+      }
+      SAST_STAMP(trc, t == 0 && ti == 1, 5);
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducers + 32) : "memory");              // next tile staged, this tile's bits dead
+      SAST_STAMP(trc, t == 0 && ti == 1, 6);
+    }
+  } else if (warp == 9) {
+    // ---------------- stager: the bits of the NEXT tile, global -> shared memory, while the producers expand this one ----------------
+    // staged word j of a (row, bin) item holds columns 64 tx - 3 + 32 j ..: the window of output pixel ox_i starts at bit 4 ox_i
+    auto stage_tile = [&](int tile, uint32_t* dst) {
+      const int tx = tile % tiles_x, rest = tile / tiles_x;
+      const int ty = rest % tiles_y, b = rest / tiles_y;
+      constexpr int NB = 4;                                            // items in flight per lane
+      for (int i0 = lane; i0 < kItems; i0 += 32 * NB) {
+        uint32_t g[NB][4];
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const int item = min(i0 + 32 * u, kItems - 1);
+          const int yy = item / kCin, c = item - yy * kCin;
+          const int y = min(max(32 * ty - 3 + yy, 0), H - 1);          // replicate padding (rows)
+          const uint32_t* row = packed + (((size_t)b * kCin + c) * H + y) * words;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) g[u][k] = __ldg(row + min(max(2 * tx - 1 + k, 0), words - 1));
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const int item = i0 + 32 * u;
+          if (item < kItems) {
+            if (tx == 0) g[u][0] = (g[u][1] & 1u) ? 0xFFFFFFFFu : 0u;  // replicate padding (left edge): column 0 repeated
+#pragma unroll
+            for (int j = 0; j < 3; ++j) dst[item * kInWords + j] = __funnelshift_r(g[u][j], g[u][j + 1], 29);
+          }
+        }
+      }
+    };
+    uint32_t ti = 0;
+    if ((int)blockIdx.x < total_tiles) stage_tile(blockIdx.x, inb);
+    asm volatile("bar.sync 1, %0;" ::"n"(kProducers + 32) : "memory");
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int next = tile + gridDim.x;
+      if (next < total_tiles) stage_tile(next, inb + ((ti + 1) & 1) * (kInBytes / 4));
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducers + 32) : "memory");
+    }
+  } else if (warp == 8) {
+    // ---------------- MMA issuer ----------------
+    const bool leader = ptx::elect_one();
+    const uint32_t idesc = (1u << 4) | (((uint32_t)kCout >> 3) << 17) | ((128u >> 4) << 24);     // kind::f16: A = B = F16, D = F32, K-major
+    ptx::mbar_wait(&ctl->wbar, 0);
+    const uint32_t w0 = ptx::smem_u32(wsm), r0 = ptx::smem_u32(ring);
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t acc = ti & 1, use = ti >> 1;
+      SAST_STAMP(trc, lane == 0 && ti == 1, 8);
+      ptx::mbar_wait(&ctl->tmem_empty[acc], (use & 1) ^ 1);
+      ptx::tc_fence_after();
+      SAST_STAMP(trc, lane == 0 && ti == 1, 9);
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)kCout;
+      for (int ky4 = 0; ky4 < 4; ++ky4) {
+        for (int kb = 0; kb < 3; ++kb, ++it) {
+          const uint32_t s = it % kStages, round = it / kStages;
+          ptx::mbar_wait(&ctl->full[s], round & 1);
+          ptx::tc_fence_after();
+          const uint32_t sa = r0 + s * kABytes;
+          // whole warp on warp-uniform descriptors, only the instruction is guarded (no R2UR waterfall per UTCHMMA)
+          for (int g = 0; g < (ky4 < 3 ? 2 : 1); ++g) {             // kernel rows ky4 and ky4 + 4 share the operand tile
+            const uint32_t wt = w0 + (uint32_t)(ky4 + 4 * g) * kWRow + (uint32_t)kb * 8192;
+            const uint64_t da = ptx::umma_desc_sw128_kmajor(sa + (uint32_t)g * 16 * 128);
+            const uint64_t dw = kb < 2 ? ptx::umma_desc_sw128_kmajor(wt) : fl::desc_sw64_k(wt);
+            const int steps = kb < 2 ? 4 : 2;                         // K steps of 16 = 2 bins
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < steps && leader)
+                ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (ky4 | kb | g | k) ? 1u : 0u);
+          }
+          if (leader) ptx::umma_commit(&ctl->empty[s]);
+          __syncwarp();
+        }
+      }
+      if (leader) ptx::umma_commit(&ctl->tmem_full[acc]);
+      __syncwarp();
+      SAST_STAMP(trc, lane == 0 && ti == 1, 10);
+    }
+  } else if (warp >= 10) {
+    // ---------------- epilogue: LayerNorm over channels (thread = pixel row), transposed store ----------------
+    const int quarter = warp & 3;
+    float* stage = &stage_smem[quarter][0];
+    const int r_sub = lane >> 3, gq = lane & 7, c4 = gq * 4;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int tx = tile % tiles_x, rest = tile / tiles_x;
+      const int ty = rest % tiles_y, b = rest / tiles_y;
+      const uint32_t acc = ti & 1, use = ti >> 1;
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)kCout + ((uint32_t)(quarter * 32) << 16);
+      SAST_STAMP(trc, threadIdx.x == 320 && ti == 1, 12);
+      ptx::mbar_wait(&ctl->tmem_full[acc], use & 1);
+      ptx::tc_fence_after();
+      SAST_STAMP(trc, threadIdx.x == 320 && ti == 1, 13);
+      uint32_t raw0[32], raw1[32];
+      ptx::tmem_ld_32x32(tmem_d, raw0);
+      ptx::tmem_ld_32x32(tmem_d + 32u, raw1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[acc]);          // the whole row sits in registers: the accumulator is free
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += __uint_as_float(raw0[j]) + __uint_as_float(raw1[j]);
+      const float mean = sum * (1.0f / kCout);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d0 = __uint_as_float(raw0[j]) - mean, d1 = __uint_as_float(raw1[j]) - mean;
+        ss += d0 * d0 + d1 * d1;
+      }
+      const float rstd = rsqrtf(ss * (1.0f / kCout) + eps);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t* raw = half ? raw1 : raw0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4 v;
+          v.x = (__uint_as_float(raw[4 * k]) - mean) * rstd; v.y = (__uint_as_float(raw[4 * k + 1]) - mean) * rstd;
+          v.z = (__uint_as_float(raw[4 * k + 2]) - mean) * rstd; v.w = (__uint_as_float(raw[4 * k + 3]) - mean) * rstd;
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((k ^ (lane & 7)) << 2)) = v;
+        }
+        __syncwarp();
+        const int n = half * 32 + c4;
+        float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ln_w) g4 = __ldg(reinterpret_cast<const float4*>(ln_w + n));
+        if (ln_b) b4 = __ldg(reinterpret_cast<const float4*>(ln_b + n));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + r_sub;                                  // row of this warp's 32: tile row quarter*32 + r
+          const int m = quarter * 32 + r;
+          const int oy = 8 * ty + (m >> 4), ox = 16 * tx + (m & 15);
+          if (oy >= Ho || ox >= Wo) continue;
+          const float4 a4 = *reinterpret_cast<const float4*>(stage + r * 32 + ((gq ^ (r & 7)) << 2));
+          *reinterpret_cast<float4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * kCout + n) =
+              make_float4(a4.x * g4.x + b4.x, a4.y * g4.y + b4.y, a4.z * g4.z + b4.z, a4.w * g4.w + b4.w);
+        }
+        __syncwarp();
+      }
+      SAST_STAMP(trc, threadIdx.x == 320 && ti == 1, 14);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  SAST_STAMP(trc, threadIdx.x == 0, 22);
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 128);
+  }
+}
+
+}  // namespace sb
+
+int make_tmap_bf16_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows,
+                       int swizzle_bytes);
+
+}  // namespace sast
+
+// true if sast_stem_bits_fwd takes this geometry (the reference's stems: 20 event bins, embed_dim 64, patch_size 4)
+extern "C" int sast_stem_bits_supported(int32_t bits, int32_t Cin, int32_t H, int32_t W, int32_t Cout) {
+  return bits == 1 && Cin == sast::sb::kCin && Cout == sast::sb::kCout && H >= 32 && W >= 64 && H % 4 == 0 && W % 32 == 0;
+}
+
+// packed: 1-bit packed histogram uint8 [B, Cin, H, W/8] (the format of sast_unpack_nonzero_ratio) -> out [B,H/4,W/4,Cout] fp32
+// NHWC = LayerNorm(conv7x7 stride 4, replicate padding 3, no bias).  w16: fp16 [7 * Cout, 160]: row ky * Cout + n holds
+// conv.weight[n, c, ky, kx] at column c * 8 + kx (column c * 8 + 7 is zero).
+extern "C" int sast_stem_bits_fwd(const uint8_t* packed, int32_t bits, int32_t B, int32_t Cin, int32_t H, int32_t W,
+                                  const uint16_t* w16, int32_t Cout, const float* ln_w, const float* ln_b, float eps, float* out,
+                                  void* stream) {
+  using namespace sast;
+  SAST_CHECK_PTR(packed); SAST_CHECK_PTR(w16); SAST_CHECK_PTR(out);
+  if (B <= 0) return SAST_E_SHAPE;
+  if (!sast_stem_bits_supported(bits, Cin, H, W, Cout)) return SAST_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(packed) & 3) || (reinterpret_cast<uintptr_t>(w16) & 15)) return SAST_E_SHAPE;
+  CUtensorMap mw, mw64;
+  int rc;       // fp16 and bf16 are both 2-byte types without arithmetic in the copy engine: the bf16 map builder serves
+  if ((rc = make_tmap_bf16_box(&mw, w16, 7ll * Cout, sb::kKRow, sb::kKRow, 64, Cout, 128))) return rc;
+  if ((rc = make_tmap_bf16_box(&mw64, w16, 7ll * Cout, sb::kKRow, sb::kKRow, 32, Cout, 64))) return rc;
+  const size_t smem = (size_t)7 * sb::kWRow + (size_t)sb::kStages * sb::kABytes + 2 * sb::kInBytes + 4096 + sizeof(sb::Ctl) + 64;
+  static thread_local unsigned long long attr_mask = 0;
+  if (first_use_on_device(attr_mask)) {
+    cudaError_t e = cudaFuncSetAttribute(sb::stem_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int Ho = H / 4, Wo = W / 4;
+  const long long tiles = (long long)B * ((Ho + 7) / 8) * ((Wo + 15) / 16);
+  if (tiles >= (1ll << 31)) return SAST_E_UNSUPPORTED;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  launch_k(sb::stem_bits_kernel, dim3(grid), dim3(sb::kThreads), smem, (cudaStream_t)stream, mw, mw64, (const uint32_t*)packed, B, H, W,
+           ln_w, ln_b, eps, out, g_trace_which == 6 ? g_trace : nullptr);
+  SAST_LAUNCH_CHECK();
+  return SAST_OK;
+}

@@ -129,20 +129,18 @@ stem_nhwc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           ptx::mbar_wait(&ctl->full[s], round & 1);
           ptx::tc_fence_after();
           const uint32_t sa = r0 + s * kABytes;
-          if (leader) {
-            for (int g = 0; g < (ky4 < 3 ? 2 : 1); ++g) {           // kernel rows ky4 and ky4 + 4 share the operand box
-              const uint32_t wt = w0 + (uint32_t)(ky4 + 4 * g) * kWRow + (uint32_t)part * 8192;
-              if (part < 2) {
-                const uint64_t da = ptx::umma_desc_sw128_kmajor(sa + (uint32_t)g * 16 * 128), dw = ptx::umma_desc_sw128_kmajor(wt);
+          // whole warp on warp-uniform descriptors, only the instruction is guarded (no R2UR waterfall per UTCHMMA)
+          for (int g = 0; g < (ky4 < 3 ? 2 : 1); ++g) {             // kernel rows ky4 and ky4 + 4 share the operand box
+            const uint32_t wt = w0 + (uint32_t)(ky4 + 4 * g) * kWRow + (uint32_t)part * 8192;
+            const uint64_t da = part < 2 ? ptx::umma_desc_sw128_kmajor(sa + (uint32_t)g * 16 * 128) : desc_sw32_k(sa + (uint32_t)g * 16 * 32);
+            const uint64_t dw = part < 2 ? ptx::umma_desc_sw128_kmajor(wt) : desc_sw32_k(wt);
+            const int steps = part < 2 ? 4 : 1;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (ky4 | part | g | k) ? 1u : 0u);
-              } else {
-                ptx::umma_f16_ss(tmem_d, desc_sw32_k(sa + (uint32_t)g * 16 * 32), desc_sw32_k(wt), idesc, 1u);
-              }
-            }
-            ptx::umma_commit(&ctl->empty[s]);
+            for (int k = 0; k < 4; ++k)
+              if (k < steps && leader)
+                ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (ky4 | part | g | k) ? 1u : 0u);
           }
+          if (leader) ptx::umma_commit(&ctl->empty[s]);
           __syncwarp();
         }
       }

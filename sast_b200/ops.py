@@ -760,6 +760,58 @@ def stem_nhwc_supported(Cin: int, H: int, W: int, Cout: int) -> bool:
     return bool(L.lib().sast_stem_nhwc_supported(int(Cin), int(H), int(W), int(Cout)))
 
 
+def pack_stem_weight_bits(w: Tensor) -> Tensor:
+    """conv.weight [Cout,Cin,7,7] fp32 -> fp16 [7*Cout, Cin*8] for sast_stem_bits_fwd: row ky*Cout + n holds w[n, c, ky, kx] at
+    column c*8 + kx; the 8th tap of every bin is zero."""
+    Cout, Cin, kh, kw = w.shape
+    assert (kh, kw) == (7, 7)
+    wp = torch.zeros(7, Cout, Cin, 8, device=w.device, dtype=torch.float32)
+    wp[..., :7] = w.detach().float().permute(2, 0, 1, 3)                                        # [ky, n, c, kx]
+    return wp.reshape(7 * Cout, Cin * 8).to(torch.float16).contiguous()
+
+
+def stem_bits_supported(bits: int, Cin: int, H: int, W: int, Cout: int) -> bool:
+    return bool(L.lib().sast_stem_bits_supported(int(bits), int(Cin), int(H), int(W), int(Cout)))
+
+
+@torch.library.custom_op("sast::packed_nonzero_ratio", mutates_args=())
+def packed_nonzero_ratio(data: Tensor, bits: int, width: int) -> Tensor:
+    """packed uint8 [B,Cin,H,W*bits/8] -> r [B,4,Cin] without unpacking; see sast_events_nhwc (xh == NULL)."""
+    L.require_cuda(data, "data")
+    data = data.contiguous()
+    B, Cin, H, _ = data.shape
+    r = torch.empty(4, B, Cin, device=data.device, dtype=torch.float32)
+    scratch = torch.zeros(B * Cin * 4, device=data.device, dtype=torch.int32)
+    L.run(data.device, "sast_events_nhwc", data.data_ptr(), int(bits), B, Cin, H, int(width), 0, r.data_ptr(), scratch.data_ptr())
+    return r.permute(1, 0, 2)
+
+
+@packed_nonzero_ratio.register_fake
+def _(data, bits, width):
+    B, Cin = data.shape[:2]
+    return data.new_empty(4, B, Cin, dtype=torch.float32).permute(1, 0, 2)
+
+
+@torch.library.custom_op("sast::stem_bits_fwd", mutates_args=())
+def stem_bits_fwd(data: Tensor, bits: int, width: int, w16: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tensor],
+                  eps: float) -> Tensor:
+    """1-bit packed uint8 [B,Cin,H,W/8] -> LayerNorm(conv7x7/4) fp32 NHWC [B,H/4,W/4,Cout]; see sast_stem_bits_fwd."""
+    L.require_cuda(data, "data")
+    assert data.dtype == torch.uint8 and w16.dtype == torch.float16 and w16.is_contiguous()
+    data = data.contiguous()
+    B, Cin, H, _ = data.shape
+    Cout = w16.shape[0] // 7
+    out = torch.empty(B, H // 4, width // 4, Cout, device=data.device, dtype=torch.float32)
+    L.run(data.device, "sast_stem_bits_fwd", data.data_ptr(), int(bits), B, Cin, H, int(width), w16.data_ptr(), Cout, L.ptr(ln_w),
+          L.ptr(ln_b), float(eps), out.data_ptr())
+    return out
+
+
+@stem_bits_fwd.register_fake
+def _(data, bits, width, w16, ln_w, ln_b, eps):
+    return data.new_empty(data.shape[0], data.shape[2] // 4, width // 4, w16.shape[0] // 7, dtype=torch.float32)
+
+
 class EventsNHWC:
     """The stem's input after :func:`events_nhwc`: fp16 [B, H+8, W+8, Cin] with the replicate padding materialised."""
 

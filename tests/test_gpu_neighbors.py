@@ -126,7 +126,8 @@ def test_fused_stem(B, H, W, cout, density):
 
 
 @pytest.mark.parametrize("bits,B,H,W,density", [(1, 2, 384, 640, 0.03), (4, 1, 256, 320, 0.3), (8, 3, 100, 96, 0.5),
-                                                (1, 1, 64, 64, 0.01), (8, 2, 36, 160, 0.9)])
+                                                (1, 1, 64, 64, 0.01), (8, 2, 36, 160, 0.9), (1, 3, 100, 96, 0.5),
+                                                (1, 1, 256, 320, 0.97)])
 def test_nhwc_stem(bits, B, H, W, density):
     """The TMA-fed stem: sast_events_nhwc (histogram -> fp16 NHWC with the replicate padding materialised, + r) is
     EXACT against plain torch ops; sast_stem_nhwc_fwd (im2col by TMA, fp16 weights resident) against the oracle's fp32
@@ -136,6 +137,9 @@ def test_nhwc_stem(bits, B, H, W, density):
     p = make_params({"conv.weight": (cout, 20, 7, 7), "norm.weight": (cout,), "norm.bias": (cout,)}, seed=bits + H)
     if bits == 1:
         x = (torch.rand(B, 20, H, W, generator=torch.Generator().manual_seed(H)) < density).to(torch.uint8)
+        x[:, ::2, :, 0] = 1        # make the replicated borders matter
+        x[:, 1::3, 0, :] = 1
+        x[:, ::5, -1, :] = 1
     else:
         x = event_histogram(B, 20, H, W, density, seed=H).clamp_(max=15 if bits == 4 else 255)
         x[:, :, 0, :] = 7          # make the replicated borders matter
@@ -159,6 +163,13 @@ def test_nhwc_stem(bits, B, H, W, density):
     assert got.shape == ref.shape
     d = (got.cpu() - ref).abs()
     assert d.max() < 4e-3 and d.mean() < 4e-4, (d.max(), d.mean())
+    if bits == 1:
+        # the stem that expands the packed bits itself: same fp16 products as the NHWC route, other summation order
+        assert ops.stem_bits_supported(1, 20, H, W, cout)
+        got_b = ops.stem_bits_fwd(src, 1, W, ops.pack_stem_weight_bits(p["conv.weight"].to(DEV)), p["norm.weight"].to(DEV),
+                                  p["norm.bias"].to(DEV), 1e-5)
+        assert (got_b - got).abs().max() < 2e-4, (got_b - got).abs().max()
+        assert torch.equal(ops.packed_nonzero_ratio(src, 1, W), r)
     # the same through the module: a backbone stem in the 16-bit mode takes this path, the fp32 mode the split-weight kernel
     mod = sast_b200.ConvDownsampling_Cf2Cl(20, cout, 4, Config(type="patch", overlap=True, norm_affine=True)).eval()
     mod.load_state_dict(p)
