@@ -3,22 +3,23 @@
 //   packed uint8 [B, 20, H, W/8] (bit k of byte j = column 8 j + k)  ->  LayerNorm(conv(x)) fp32 NHWC [B, H/4, W/4, 64].
 //
 // The whole input is 4.9 MB at 1 Mpx B = 8 -- nothing is unpacked to memory.  Per output tile of 8 oy x 16 ox pixels
-// (M = 128) the 35 input rows x 20 bins x 72 columns the tile touches are 8.4 KB of bits: the producer warps stage them in
-// shared memory (shifted so that the 8-column window of output pixel ox_i starts at bit 4 ox_i, replicate padding applied)
-// and build the tcgen05 A operand from there: one (bin c, kernel row ky) group of an output pixel is an 8-bit window ->
-// one 16-byte chunk of 8 fp16 values (kx = 0..6 and a zero-weight 8th tap) through a 256-entry shared-memory table, i.e.
-// two LDS.32 + a funnel shift + LDS.128 + STS.128 per chunk.  K is ordered (ky, c, kx8): a k-block is 8 bins of one ky.
-// As in stem_nhwc.cu an operand tile holds 9 output rows (144 tile rows): rows 0..127 are the operand of kernel row ky,
-// rows 16..143 that of ky + 4 (one output row down = 4 input rows), so each window is expanded once for both.
+// (M = 128) the 35 input rows x 20 bins x 72 columns the tile touches are 8.4 KB of bits: a stager warp keeps the next
+// tile's bits in shared memory (shifted so that the 8-column window of output pixel ox_i starts at bit 4 ox_i, replicate
+// padding applied; double buffer).  The A operand never touches shared memory: with N = 64 an SS-form tcgen05.mma re-reads 4 KB of A per
+// 2 KB of B and is bound by shared-memory bandwidth (measured: ~100 clk per M128 N64 K16 instruction against the 32 clk
+// floor), so the operand lives in TENSOR MEMORY.  A producer thread owns one tile row (= TMEM lane): per kernel row ky and
+// bin c it reads the 8-bit window of its pixel (two LDS.32 + a funnel shift), expands it to 8 fp16 values (kx = 0..6 and
+// a zero-weight 8th tap) with a handful of integer instructions, and writes the 20 bins of a ky (80 TMEM columns) with
+// tcgen05.st; the MMA warp issues TS-form instructions (A from TMEM, B = weights from shared memory).
+// K is ordered (ky, c, kx8): one A buffer = one ky = 10 K steps of 2 bins.
 //
 // The fp16 weights (one rounding of 2^-12 relative per weight -- finer than the TF32 operand rounding of the cuDNN
 // convolution this replaces; event bits are exact) stay RESIDENT in shared memory: 7 x 20 KB.
 //
-//   warps 0-7   producers: expand the staged bits of this tile into operand k-blocks (2-stage ring)
+//   warps 0-7   producers: two per TMEM lane quarter (10 bins each); 4 A buffers of 80 TMEM columns
 //   warp 8      TMEM allocator + MMA issuer (two 64-column accumulators: the epilogue of tile i overlaps tile i+1);
 //               also TMA-loads the weights once
-//   warp 9      stager: global -> shared memory copy of the NEXT tile's bits (double buffer; its load latency and the
-//               producers' proxy fences never meet)
+//   warp 9      stager: global -> shared memory copy of the NEXT tile's bits (double buffer)
 //   warps 10-13 epilogue: LayerNorm over the channels of each pixel straight from TMEM, swizzled shared-memory transpose,
 //               dense 256-byte row stores
 #include "common.cuh"
@@ -32,8 +33,13 @@ namespace sb {
 
 constexpr int kCout = 64, kCin = 20;
 constexpr int kKRow = 160;                          // halves per (output channel, ky): 20 bins x 8 taps
-constexpr int kStages = 2;
-constexpr int kABytes = 144 * 128;                  // one operand k-block: 9 oy x 16 ox rows of 128 bytes (8 bins)
+constexpr int kABufs = 3;                           // A operand buffers in tensor memory
+constexpr int kACols = 80;                          // one buffer: the 20 bins of one ky = 160 halves = 80 columns
+constexpr int kChains = 2;                          // independent accumulation chains per tile (summed by the epilogue): a
+                                                    // tcgen05.mma that accumulates onto the result of the previous one waits for
+                                                    // it (~125 clk measured), 4x the 32 clk an M128 N64 K16 instruction occupies
+constexpr int kAcc0 = 0, kA0 = 2 * kChains * kCout; // TMEM columns: two sets of accumulators, then the A buffers
+static_assert(kA0 + kABufs * kACols <= 512, "tensor memory");
 constexpr int kWRow = 2 * 8192 + 4096;              // weights of one ky: two [64 x 64] SW128 tiles + one [64 x 32] SW64 tile
 constexpr int kInRows = 35, kInWords = 3;           // staged bits: 35 input rows x 20 bins x 3 words (72 columns used)
 constexpr int kInBytes = (kInRows * kCin * kInWords * 4 + 1023) / 1024 * 1024;
@@ -42,8 +48,8 @@ constexpr int kProducers = 256;
 constexpr int kThreads = 14 * 32;
 
 struct Ctl {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kABufs];
+  uint64_t empty[kABufs];
   uint64_t wbar;
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
@@ -56,13 +62,11 @@ stem_bits_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
                  const float* __restrict__ ln_b, float eps, float* __restrict__ out, long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(16) float stage_smem[4][32 * 32];
-  [[maybe_unused]] long long* const trc = trace ? trace + (size_t)blockIdx.x * 32 : nullptr;     // trace build: stamps of the 2nd tile
+  [[maybe_unused]] long long* const trc = trace ? trace + (size_t)blockIdx.x * 32 : nullptr;     // trace build: stamps of the 4th tile
   SAST_STAMP(trc, threadIdx.x == 0, 20);
   uint8_t* const wsm = smem_raw;                                       // 7 x kWRow
-  uint8_t* const ring = wsm + 7 * kWRow;                               // kStages x kABytes
-  uint32_t* const inb = reinterpret_cast<uint32_t*>(ring + kStages * kABytes);     // 2 x kInBytes
-  uint4* const lut = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(inb) + 2 * kInBytes);      // 256 x 16 bytes
-  Ctl* const ctl = reinterpret_cast<Ctl*>(lut + 256);
+  uint32_t* const inb = reinterpret_cast<uint32_t*>(wsm + 7 * kWRow);  // 2 x kInBytes
+  Ctl* const ctl = reinterpret_cast<Ctl*>(reinterpret_cast<uint8_t*>(inb) + 2 * kInBytes);
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
   const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int Ho = H / 4, Wo = W / 4, words = W / 32;
@@ -71,17 +75,12 @@ stem_bits_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
 
   if (threadIdx.x == 0) {
     ptx::tma_prefetch_desc(&map_w); ptx::tma_prefetch_desc(&map_w64);
-    for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&ctl->full[s], kProducers / 32); ptx::mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < kABufs; ++s) { ptx::mbar_init(&ctl->full[s], kProducers / 32); ptx::mbar_init(&ctl->empty[s], 1); }
     ptx::mbar_init(&ctl->wbar, 1);
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&ctl->tmem_full[a], 1); ptx::mbar_init(&ctl->tmem_empty[a], 4); }
     ptx::fence_barrier_init();
   }
-  if (threadIdx.x < 256) {                       // bit k of the window -> fp16 1.0 / 0.0 at tap k
-    const uint32_t b = threadIdx.x;
-    auto two = [&](int k) { return ((b >> k) & 1u) * 0x3C00u | ((b >> (k + 1)) & 1u) * 0x3C000000u; };
-    lut[b] = make_uint4(two(0), two(2), two(4), two(6));
-  }
-  if (warp == 8) ptx::tmem_alloc(&ctl->tmem_base, 128);
+  if (warp == 8) ptx::tmem_alloc(&ctl->tmem_base, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -101,80 +100,73 @@ stem_bits_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
 
   if (warp < 8) {
     // ---------------- producers ----------------
-    const int t = threadIdx.x;
-    // static work assignment: a k-block is 144 rows x 8 chunks = 1152 chunks = 4.5 per thread; chunk `item` is bin j = item / 144
-    // of tile row m = item % 144 (lanes = consecutive rows: conflict-free STS.128, broadcast reads of the staged words)
-    constexpr int NC = (144 * 8 + kProducers - 1) / kProducers;      // 5
-    uint32_t src_off[NC], dst_off[NC], shift[NC];
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      const int item = t + i * kProducers;
-      const int j = item / 144, m = item - j * 144, oxi = m & 15;
-      src_off[i] = (uint32_t)((4 * (m >> 4) * kCin + j) * kInWords + (oxi >> 3));     // + (ky4 * kCin + 8 kb) * kInWords
-      shift[i] = (uint32_t)((oxi & 7) * 4) | (item < 144 * 8 ? (uint32_t)j << 8 : 0xFF00u);     // bits 8..: bin j (255: no such chunk)
-      dst_off[i] = (uint32_t)(m * 128 + ((j ^ (m & 7)) << 4));
-    }
+    [[maybe_unused]] const int t = threadIdx.x;
+    const int m = (warp & 3) * 32 + lane;                             // tile row = TMEM lane (a warp reaches its own lane quarter)
+    const int h = warp >> 2;                                          // which 10 of the 20 bins
+    const int oxi = m & 15;
+    const uint32_t src0 = (uint32_t)((4 * (m >> 4) * kCin + 10 * h) * kInWords + (oxi >> 3));     // + ky * kCin * kInWords
+    const uint32_t sh = (uint32_t)((oxi & 7) * 4);
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t it = 0, ti = 0;
     asm volatile("bar.sync 1, %0;" ::"n"(kProducers + 32) : "memory");                // tile 0 staged (warp 9)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t* in = inb + (ti & 1) * (kInBytes / 4);
-      SAST_STAMP(trc, t == 0 && ti == 1, 0);
-      for (int ky4 = 0; ky4 < 4; ++ky4) {
-        SAST_STAMP(trc, t == 0 && ti == 1, 1 + ky4);
-        for (int kb = 0; kb < 3; ++kb, ++it) {
-          const uint32_t s = it % kStages, round = it / kStages;
-          const uint32_t* inq = in + (ky4 * kCin + kb * 8) * kInWords;
-          const uint32_t nch = kb < 2 ? 8u : 4u;                       // bins in this k-block (rows 128..143 of ky4 = 3 are never read)
-          // all window reads, then all table reads, then all stores: three short dependent steps instead of five chains
-          uint32_t bits[NC];
-          uint4 v[NC];
+      SAST_STAMP(trc, t == 0 && ti == 3, 0);
+      for (int ky = 0; ky < 7; ++ky, ++it) {
+        const uint32_t ab = it % kABufs, round = it / kABufs;
+        const uint32_t* wp = in + src0 + (uint32_t)(ky * kCin * kInWords);
+        uint32_t v[40];                                                // 10 bins x 8 halves
 #pragma unroll
-          for (int i = 0; i < NC; ++i) {
-            const uint32_t* wp = inq + src_off[i];
-            bits[i] = (shift[i] >> 8) < nch ? __funnelshift_r(wp[0], wp[1], shift[i] & 31u) & 0xFFu : 0u;
-          }
-#pragma unroll
-          for (int i = 0; i < NC; ++i) v[i] = lut[bits[i]];
-          ptx::mbar_wait(&ctl->empty[s], (round & 1) ^ 1);
-          const uint32_t st = ptx::smem_u32(ring + s * kABytes);
-#pragma unroll
-          for (int i = 0; i < NC; ++i)
-            if ((shift[i] >> 8) < nch) fl::sts128(st + dst_off[i], v[i].x, v[i].y, v[i].z, v[i].w);
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&ctl->full[s]);
+        for (int c = 0; c < 10; ++c) {
+          const uint32_t bits = __funnelshift_r(wp[c * kInWords], wp[c * kInWords + 1], sh);
+          // 4 bits -> 4 bytes of 0 / 1 (multiply-spread), x 0x3C -> the high bytes of fp16 1.0 / 0.0, two per word
+          const uint32_t lo = (((bits & 15u) * 0x00204081u) & 0x01010101u) * 0x3Cu;
+          const uint32_t hi = ((((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u) * 0x3Cu;
+          v[4 * c] = __byte_perm(lo, 0u, 0x1404);
+          v[4 * c + 1] = __byte_perm(lo, 0u, 0x3424);
+          v[4 * c + 2] = __byte_perm(hi, 0u, 0x1404);
+          v[4 * c + 3] = __byte_perm(hi, 0u, 0x3424);
         }
+        ptx::mbar_wait(&ctl->empty[ab], (round & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t ta = tmem_base + lane_sel + (uint32_t)(kA0 + ab * kACols + 40 * h);
+        ptx::tmem_st_32x32(ta, v);
+        ptx::tmem_st_32x8(ta + 32u, v + 32);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ctl->full[ab]);
       }
-      SAST_STAMP(trc, t == 0 && ti == 1, 5);
+      SAST_STAMP(trc, t == 0 && ti == 3, 5);
       asm volatile("bar.sync 1, %0;" ::"n"(kProducers + 32) : "memory");              // next tile staged, this tile's bits dead
-      SAST_STAMP(trc, t == 0 && ti == 1, 6);
+      SAST_STAMP(trc, t == 0 && ti == 3, 6);
     }
   } else if (warp == 9) {
     // ---------------- stager: the bits of the NEXT tile, global -> shared memory, while the producers expand this one ----------------
-    // staged word j of a (row, bin) item holds columns 64 tx - 3 + 32 j ..: the window of output pixel ox_i starts at bit 4 ox_i
+    // (row, bin) item = the four global words around the tile's 72 columns -> three staged words: word j holds columns
+    // 64 tx - 3 + 32 j .., so the window of output pixel ox_i starts at bit 4 ox_i.  All 88 loads of a lane are issued
+    // back to back (one latency per tile); a separate warp so that the producers' scoreboards never wait on global loads.
+    constexpr int NB = (kItems + 31) / 32;                             // items per lane (22)
     auto stage_tile = [&](int tile, uint32_t* dst) {
       const int tx = tile % tiles_x, rest = tile / tiles_x;
       const int ty = rest % tiles_y, b = rest / tiles_y;
-      constexpr int NB = 4;                                            // items in flight per lane
-      for (int i0 = lane; i0 < kItems; i0 += 32 * NB) {
-        uint32_t g[NB][4];
+      uint32_t g[NB][4];
 #pragma unroll
-        for (int u = 0; u < NB; ++u) {
-          const int item = min(i0 + 32 * u, kItems - 1);
-          const int yy = item / kCin, c = item - yy * kCin;
-          const int y = min(max(32 * ty - 3 + yy, 0), H - 1);          // replicate padding (rows)
-          const uint32_t* row = packed + (((size_t)b * kCin + c) * H + y) * words;
+      for (int u = 0; u < NB; ++u) {
+        const int item = min(lane + 32 * u, kItems - 1);
+        const int yy = item / kCin, c = item - yy * kCin;
+        const int y = min(max(32 * ty - 3 + yy, 0), H - 1);            // replicate padding (rows)
+        const uint32_t* row = packed + (((size_t)b * kCin + c) * H + y) * words;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) g[u][k] = __ldg(row + min(max(2 * tx - 1 + k, 0), words - 1));
-        }
+        for (int k = 0; k < 4; ++k) g[u][k] = __ldg(row + min(max(2 * tx - 1 + k, 0), words - 1));
+      }
 #pragma unroll
-        for (int u = 0; u < NB; ++u) {
-          const int item = i0 + 32 * u;
-          if (item < kItems) {
-            if (tx == 0) g[u][0] = (g[u][1] & 1u) ? 0xFFFFFFFFu : 0u;  // replicate padding (left edge): column 0 repeated
+      for (int u = 0; u < NB; ++u) {
+        const int item = lane + 32 * u;
+        if (item < kItems) {
+          if (tx == 0) g[u][0] = (g[u][1] & 1u) ? 0xFFFFFFFFu : 0u;    // replicate padding (left edge): column 0 repeated
 #pragma unroll
-            for (int j = 0; j < 3; ++j) dst[item * kInWords + j] = __funnelshift_r(g[u][j], g[u][j + 1], 29);
-          }
+          for (int j = 0; j < 3; ++j) dst[item * kInWords + j] = __funnelshift_r(g[u][j], g[u][j + 1], 29);
         }
       }
     };
@@ -183,7 +175,9 @@ stem_bits_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     asm volatile("bar.sync 1, %0;" ::"n"(kProducers + 32) : "memory");
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int next = tile + gridDim.x;
+      SAST_STAMP(trc, lane == 0 && ti == 3, 16);
       if (next < total_tiles) stage_tile(next, inb + ((ti + 1) & 1) * (kInBytes / 4));
+      SAST_STAMP(trc, lane == 0 && ti == 3, 17);
       asm volatile("bar.sync 1, %0;" ::"n"(kProducers + 32) : "memory");
     }
   } else if (warp == 8) {
@@ -191,39 +185,37 @@ stem_bits_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     const bool leader = ptx::elect_one();
     const uint32_t idesc = (1u << 4) | (((uint32_t)kCout >> 3) << 17) | ((128u >> 4) << 24);     // kind::f16: A = B = F16, D = F32, K-major
     ptx::mbar_wait(&ctl->wbar, 0);
-    const uint32_t w0 = ptx::smem_u32(wsm), r0 = ptx::smem_u32(ring);
+    const uint32_t w0 = ptx::smem_u32(wsm);
     uint32_t it = 0, ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const uint32_t acc = ti & 1, use = ti >> 1;
-      SAST_STAMP(trc, lane == 0 && ti == 1, 8);
+      SAST_STAMP(trc, lane == 0 && ti == 3, 8);
       ptx::mbar_wait(&ctl->tmem_empty[acc], (use & 1) ^ 1);
       ptx::tc_fence_after();
-      SAST_STAMP(trc, lane == 0 && ti == 1, 9);
-      const uint32_t tmem_d = tmem_base + acc * (uint32_t)kCout;
-      for (int ky4 = 0; ky4 < 4; ++ky4) {
-        for (int kb = 0; kb < 3; ++kb, ++it) {
-          const uint32_t s = it % kStages, round = it / kStages;
-          ptx::mbar_wait(&ctl->full[s], round & 1);
-          ptx::tc_fence_after();
-          const uint32_t sa = r0 + s * kABytes;
-          // whole warp on warp-uniform descriptors, only the instruction is guarded (no R2UR waterfall per UTCHMMA)
-          for (int g = 0; g < (ky4 < 3 ? 2 : 1); ++g) {             // kernel rows ky4 and ky4 + 4 share the operand tile
-            const uint32_t wt = w0 + (uint32_t)(ky4 + 4 * g) * kWRow + (uint32_t)kb * 8192;
-            const uint64_t da = ptx::umma_desc_sw128_kmajor(sa + (uint32_t)g * 16 * 128);
-            const uint64_t dw = kb < 2 ? ptx::umma_desc_sw128_kmajor(wt) : fl::desc_sw64_k(wt);
-            const int steps = kb < 2 ? 4 : 2;                         // K steps of 16 = 2 bins
+      SAST_STAMP(trc, lane == 0 && ti == 3, 9);
+      const uint32_t tmem_d = tmem_base + (uint32_t)kAcc0 + acc * (uint32_t)(kChains * kCout);
+      for (int ky = 0; ky < 7; ++ky, ++it) {
+        const uint32_t ab = it % kABufs, round = it / kABufs;
+        SAST_STAMP(trc, lane == 0 && ti == 3 && ky < 4, 24 + 2 * ky);
+        ptx::mbar_wait(&ctl->full[ab], round & 1);
+        ptx::tc_fence_after();
+        SAST_STAMP(trc, lane == 0 && ti == 3 && ky < 4, 25 + 2 * ky);
+        // whole warp on warp-uniform operands, only the instruction is guarded (no R2UR waterfall per UTCHMMA)
+        const uint32_t ta = tmem_base + (uint32_t)(kA0 + ab * kACols);
+        const uint32_t wt = w0 + (uint32_t)ky * kWRow;
+        const uint64_t d0 = ptx::umma_desc_sw128_kmajor(wt), d1 = ptx::umma_desc_sw128_kmajor(wt + 8192), d2 = fl::desc_sw64_k(wt + 16384);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < steps && leader)
-                ptx::umma_f16_ss(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (ky4 | kb | g | k) ? 1u : 0u);
-          }
-          if (leader) ptx::umma_commit(&ctl->empty[s]);
-          __syncwarp();
+        for (int k = 0; k < 10; ++k) {                                 // K steps of 16 = 2 bins = 8 TMEM columns
+          const uint64_t dw = (k < 4 ? d0 : k < 8 ? d1 : d2) + (uint64_t)((k & 3) * 2);
+          if (leader)
+            ptx::umma_f16_ts(tmem_d + (uint32_t)((k % kChains) * kCout), ta + (uint32_t)(8 * k), dw, idesc, (ky | (k / kChains)) ? 1u : 0u);
         }
+        if (leader) ptx::umma_commit(&ctl->empty[ab]);
+        __syncwarp();
       }
       if (leader) ptx::umma_commit(&ctl->tmem_full[acc]);
       __syncwarp();
-      SAST_STAMP(trc, lane == 0 && ti == 1, 10);
+      SAST_STAMP(trc, lane == 0 && ti == 3, 10);
     }
   } else if (warp >= 10) {
     // ---------------- epilogue: LayerNorm over channels (thread = pixel row), transposed store ----------------
@@ -235,15 +227,27 @@ stem_bits_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       const int tx = tile % tiles_x, rest = tile / tiles_x;
       const int ty = rest % tiles_y, b = rest / tiles_y;
       const uint32_t acc = ti & 1, use = ti >> 1;
-      const uint32_t tmem_d = tmem_base + acc * (uint32_t)kCout + ((uint32_t)(quarter * 32) << 16);
-      SAST_STAMP(trc, threadIdx.x == 320 && ti == 1, 12);
+      const uint32_t tmem_d = tmem_base + (uint32_t)kAcc0 + acc * (uint32_t)(kChains * kCout) + ((uint32_t)(quarter * 32) << 16);
+      SAST_STAMP(trc, threadIdx.x == 320 && ti == 3, 12);
       ptx::mbar_wait(&ctl->tmem_full[acc], use & 1);
       ptx::tc_fence_after();
-      SAST_STAMP(trc, threadIdx.x == 320 && ti == 1, 13);
+      SAST_STAMP(trc, threadIdx.x == 320 && ti == 3, 13);
       uint32_t raw0[32], raw1[32];
       ptx::tmem_ld_32x32(tmem_d, raw0);
       ptx::tmem_ld_32x32(tmem_d + 32u, raw1);
       ptx::tmem_ld_wait();
+#pragma unroll
+      for (int ch = 1; ch < kChains; ++ch) {                           // sum of the accumulation chains
+        uint32_t part[32];
+        ptx::tmem_ld_32x32(tmem_d + (uint32_t)(ch * kCout), part);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) raw0[j] = __float_as_uint(__uint_as_float(raw0[j]) + __uint_as_float(part[j]));
+        ptx::tmem_ld_32x32(tmem_d + (uint32_t)(ch * kCout) + 32u, part);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) raw1[j] = __float_as_uint(__uint_as_float(raw1[j]) + __uint_as_float(part[j]));
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[acc]);          // the whole row sits in registers: the accumulator is free
@@ -285,7 +289,7 @@ stem_bits_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         }
         __syncwarp();
       }
-      SAST_STAMP(trc, threadIdx.x == 320 && ti == 1, 14);
+      SAST_STAMP(trc, threadIdx.x == 320 && ti == 3, 14);
     }
   }
   ptx::tc_fence_before();
@@ -293,7 +297,7 @@ stem_bits_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   SAST_STAMP(trc, threadIdx.x == 0, 22);
   if (warp == 8) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 128);
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -324,7 +328,7 @@ extern "C" int sast_stem_bits_fwd(const uint8_t* packed, int32_t bits, int32_t B
   int rc;       // fp16 and bf16 are both 2-byte types without arithmetic in the copy engine: the bf16 map builder serves
   if ((rc = make_tmap_bf16_box(&mw, w16, 7ll * Cout, sb::kKRow, sb::kKRow, 64, Cout, 128))) return rc;
   if ((rc = make_tmap_bf16_box(&mw64, w16, 7ll * Cout, sb::kKRow, sb::kKRow, 32, Cout, 64))) return rc;
-  const size_t smem = (size_t)7 * sb::kWRow + (size_t)sb::kStages * sb::kABytes + 2 * sb::kInBytes + 4096 + sizeof(sb::Ctl) + 64;
+  const size_t smem = (size_t)7 * sb::kWRow + 2 * sb::kInBytes + sizeof(sb::Ctl) + 64;
   static thread_local unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(sb::stem_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Phase timeline of stem_bits_kernel CTAs (debug aid): runs the 1 Mpx B=8 stem from 1-bit packed input with
-sast_debug_trace(which=6) armed (trace build) and prints the clock deltas of each CTA's SECOND tile."""
+sast_debug_trace(which=6) armed (trace build) and prints the clock deltas of each CTA's FOURTH tile."""
 import os
 import sys
 
@@ -36,14 +36,16 @@ def show(name, a, b):
     print(f"  {name:46s} median {d.median():8.0f}  p90 {d.quantile(0.9):8.0f} clk")
 
 
-show("producer: ky4 = 0 (3 k-blocks)", 1, 2)
-show("producer: ky4 = 1", 2, 3)
-show("producer: ky4 = 2", 3, 4)
-show("producer: ky4 = 3", 4, 5)
-show("producer: store next tile's bits + barrier", 5, 6)
+show("producer: 7 kernel rows", 0, 5)
+show("producer: barrier with the stager", 5, 6)
 show("producer: whole tile", 0, 6)
 show("mma: wait for the accumulator", 8, 9)
-show("mma: 12 k-blocks", 9, 10)
+show("mma: 7 kernel rows x 10 K steps", 9, 10)
+for ky in range(4):
+    show(f"mma: ky {ky}: wait for the producers", 24 + 2 * ky, 25 + 2 * ky)
+    if ky < 3:
+        show(f"mma: ky {ky}: issue 10 + commit", 25 + 2 * ky, 26 + 2 * ky)
+show("stager: stage the next tile", 16, 17)
 show("epilogue: wait for the tile", 12, 13)
 show("epilogue: LayerNorm + stores", 13, 14)
 show("kernel: entry -> set-up done", 20, 21)
