@@ -251,7 +251,8 @@ def run_ours(args, workload):
     n_buf = 4
     raw = make_inputs(B, res, args.sparsity, n_buf, seed=1 + rank, kind=args.input)        # every rank: its own frames
     # Host side of the product API: the event histogram bit-packed (1 bit per bin for the binary benchmark input, 4 bits
-    # for counts clipped at 10), packed once OUTSIDE the timed region (a data loader's job); unpacked on the device INSIDE it.
+    # for counts clipped at 10), packed once OUTSIDE the timed region (a data loader's job); expanded on the device INSIDE it (1 bit: by the stem's
+    # producer warps, nothing is unpacked to memory; 4 bits: one fp16 NHWC pass).
     bits = {"auto": 1 if args.input == "binary" else 4, "0": 0, "1": 1, "4": 4}[args.pack]
     import sast_b200
     host = [(sast_b200.pack_events(t, bits) if bits else t).pin_memory() for t in raw]
@@ -376,7 +377,7 @@ def run_ours(args, workload):
                     "d2h_bytes_per_step": 64 * seq * world, "ms_per_step": t_e2e / args.steps * 1e3,
                     "pipeline": "H2D on a copy stream, double buffered against the compute stream",
                     "host_format": (f"event histogram bit-packed {bits} bit/bin (sast_b200.pack_events, outside the timed region); "
-                                    "unpacked on the device inside it" if bits else "uint8, 1 byte/bin"),
+                                    "expanded on the device inside it (1 bit: in the stem kernel itself)" if bits else "uint8, 1 byte/bin"),
                     "d2h": "per-layer selected-token counts (the backbone protocol's only host-visible result, benchmark.py:33-42)",
                     "numa": numa},
             "gpu_launches": int(launches_per_frame_batch) * seq * args.steps,
