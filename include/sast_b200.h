@@ -313,6 +313,21 @@ int sast_stem_bits_fwd(const uint8_t* packed, int32_t bits, int32_t B, int32_t C
                        int32_t Cout, const float* ln_w, const float* ln_b, float eps, float* out, void* stream);
 
 /*
+ * Downsample stem of stages 2-3 as one kernel (ref: ops.py:54-95 ConvDownsampling_Cf2Cl with downsample factor 2: Conv2d k=3,
+ * s=2, replicate padding 1, no bias + NCHW->NHWC + LayerNorm), 16-bit mode: xp bf16 [B,H+2,W+2,Cin] (replicate-padded NHWC,
+ * sast_pad_nhwc_bf16: the fp32 map of the previous stage, element strides as in sast_pad_nhwc) -> out [B,H/2,W/2,Cout] fp32
+ * NHWC.  Implicit GEMM on tcgen05 with bf16 operands (like every GEMM of the 16-bit mode): im2col by an overlapping-stride
+ * 5-D tensor map, weights resident (Cin 64) or streamed per k-block (Cin 128), LayerNorm in the epilogue.
+ * w9: bf16 [Cout, 9*Cin], column ky*3*Cin + kx*Cin + c = conv.weight[n,c,ky,kx].
+ * Geometry: sast_downsample_supported ((Cin,Cout) = (64,128) or (128,256), H and W even) -- else SAST_E_UNSUPPORTED.
+ */
+int sast_pad_nhwc_bf16(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t pad, int64_t stride_b,
+                       int64_t stride_y, int64_t stride_x, uint16_t* out, void* stream);
+int sast_downsample_supported(int32_t Cin, int32_t H, int32_t W, int32_t Cout);
+int sast_downsample_fwd(const uint16_t* xp, int32_t B, int32_t Cin, int32_t H, int32_t W, const uint16_t* w9, int32_t Cout,
+                        const float* ln_w, const float* ln_b, float eps, float* out, void* stream);
+
+/*
  * Conv-LSTM cell as one kernel (ref: models/layers/rnn.py:36-69 with dws_conv False): the 1x1 conv of
  * [x | h_prev] as a TF32 tcgen05 GEMM straight from the fp32 NHWC maps, gates in the epilogue.
  * x, h_prev, c_prev, h_out, c_out: [P,C] fp32 (NHWC rows); h_prev/c_prev both NULL = zero state.

@@ -107,6 +107,9 @@ def _load():
         "sast_events_nhwc": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "sast_stem_nhwc_supported": (C.c_int, [i32, i32, i32, i32]),
         "sast_stem_nhwc_fwd": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, vp, vp, f32, vp, vp]),
+        "sast_downsample_supported": (C.c_int, [i32, i32, i32, i32]),
+        "sast_pad_nhwc_bf16": (C.c_int, [vp, i32, i32, i32, i32, i32, i64, i64, i64, vp, vp]),
+        "sast_downsample_fwd": (C.c_int, [vp, i32, i32, i32, i32, vp, i32, vp, vp, f32, vp, vp]),
         "sast_stem_bits_supported": (C.c_int, [i32, i32, i32, i32, i32]),
         "sast_stem_bits_fwd": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, f32, vp, vp]),
         "sast_lstm_fwd": (C.c_int, [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),
@@ -128,7 +131,8 @@ EXPORTS = ("sast_abi_version", "sast_build_info", "sast_struct_size", "sast_laun
            "sast_layer_fwd", "sast_layer_is_fused", "sast_layer_bwd_workspace_bytes", "sast_layer_bwd",
            "sast_score_bwd_workspace_bytes", "sast_score_bwd", "sast_gather", "sast_scatter", "sast_gemm_bf16", "sast_gemm_bf16_glu", "sast_pad_input", "sast_pad_nhwc",
            "sast_layernorm", "sast_lstm_gates", "sast_lstm_fwd", "sast_stem_fwd", "sast_events_nhwc", "sast_stem_nhwc_supported",
-           "sast_stem_nhwc_fwd", "sast_stem_bits_supported", "sast_stem_bits_fwd", "sast_debug_trace")
+           "sast_stem_nhwc_fwd", "sast_stem_bits_supported", "sast_stem_bits_fwd", "sast_downsample_supported",
+           "sast_downsample_fwd", "sast_pad_nhwc_bf16", "sast_debug_trace")
 
 _lib = None
 

@@ -86,6 +86,7 @@ class ConvDownsampling_Cf2Cl(nn.Module):
         self.conv = nn.Conv2d(dim_in, dim_out, kernel_size=kernel_size, padding=padding, stride=downsample_factor,
                               bias=False, padding_mode='replicate')
         self.norm = nn.LayerNorm(dim_out, eps=1e-5, elementwise_affine=norm_affine)
+        self.precision = default_precision()     # BF16 (tensor-core mode): fused bf16 downsample kernel; FP32: cuDNN conv + LayerNorm
 
     def _fused_stem_ok(self, x: Tensor, pad: int) -> bool:
         """uint8 histograms through the one-kernel stem (implicit GEMM on tcgen05 + LayerNorm); other dtypes
@@ -130,6 +131,14 @@ class ConvDownsampling_Cf2Cl(nn.Module):
             self._nkey = key
         return self._npack
 
+    def _downsample_pack(self):
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version)
+        if getattr(self, "_dkey", None) != key:
+            self._dpack = ops.pack_downsample_weight(w)
+            self._dkey = key
+        return self._dpack
+
     def _stem_pack(self):
         w = self.conv.weight
         key = (w.data_ptr(), w._version)
@@ -162,6 +171,12 @@ class ConvDownsampling_Cf2Cl(nn.Module):
         if self._fused_stem_ok(x, pad):
             w_hi, w_lo, gpad = self._stem_pack()
             return ops.stem_fwd(x, w_hi, w_lo, gpad, self.norm.weight, self.norm.bias, self.norm.eps)
+        c = self.conv
+        if (tuple(c.kernel_size) == (3, 3) and tuple(c.stride) == (2, 2) and pad == 1 and x.dtype == torch.float32
+                and self.precision != L.FP32 and torch.backends.cudnn.allow_tf32 and getattr(self, "fused_downsample", True)
+                and ops.downsample_supported(c.in_channels, x.shape[2], x.shape[3], c.out_channels)):
+            # stages 2-3 in the 16-bit mode: replicate-padded bf16 copy, then conv + LayerNorm as ONE tcgen05 kernel (im2col by TMA)
+            return ops.downsample_fwd(x.permute(0, 2, 3, 1), self._downsample_pack(), self.norm.weight, self.norm.bias, self.norm.eps)
         if x.is_contiguous() and not (x.shape[1] == 1 or x.shape[2:] == (1, 1)):
             xp = ops.pad_input(x, pad)
         else:

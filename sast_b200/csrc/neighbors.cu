@@ -85,6 +85,25 @@ __global__ void __launch_bounds__(256) pad_nhwc_kernel(const float4* __restrict_
   }
 }
 
+// the same, written as bf16: the operand map of the fused downsample kernel (downsample_tc.cu)
+__global__ void __launch_bounds__(256) pad_nhwc_bf16_kernel(const float4* __restrict__ x, int B, int H, int W, int C4, int pad,
+                                                            long long sb, long long sy, long long sx, uint2* __restrict__ out) {
+  pdl_entry();
+  const int Ho = H + 2 * pad, Wo = W + 2 * pad;
+  const long long total = (long long)B * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long p = i / C4;
+    const int xo = (int)(p % Wo); p /= Wo;
+    const int yo = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const int xs = min(max(xo - pad, 0), W - 1), ys = min(max(yo - pad, 0), H - 1);
+    const float4 v = x[b * sb + ys * sy + xs * sx + c];
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    out[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+  }
+}
+
 template <int LPT, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                         const float* __restrict__ w, const float* __restrict__ b, float eps,
@@ -221,6 +240,19 @@ extern "C" int sast_pad_nhwc(const float* x, int32_t B, int32_t H, int32_t W, in
   const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad) * (C / 4);
   sast::launch_k(pad_nhwc_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const float4*)x, B, H, W, C / 4, pad, stride_b / 4,
                                                                          stride_y / 4, stride_x / 4, (float4*)out);
+  SAST_LAUNCH_CHECK();
+  return SAST_OK;
+}
+
+extern "C" int sast_pad_nhwc_bf16(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t pad, int64_t stride_b,
+                                  int64_t stride_y, int64_t stride_x, uint16_t* out, void* stream) {
+  using namespace sast;
+  SAST_CHECK_PTR(x); SAST_CHECK_PTR(out);
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 4 != 0 || pad < 0) return SAST_E_SHAPE;
+  if (stride_b % 4 || stride_y % 4 || stride_x % 4) return SAST_E_SHAPE;
+  const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad) * (C / 4);
+  sast::launch_k(pad_nhwc_bf16_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const float4*)x, B, H, W, C / 4, pad,
+                 stride_b / 4, stride_y / 4, stride_x / 4, (uint2*)out);
   SAST_LAUNCH_CHECK();
   return SAST_OK;
 }

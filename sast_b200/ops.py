@@ -760,6 +760,41 @@ def stem_nhwc_supported(Cin: int, H: int, W: int, Cout: int) -> bool:
     return bool(L.lib().sast_stem_nhwc_supported(int(Cin), int(H), int(W), int(Cout)))
 
 
+def pack_downsample_weight(w: Tensor) -> Tensor:
+    """conv.weight [Cout,Cin,3,3] fp32 -> bf16 [Cout, 9*Cin] for sast_downsample_fwd: column ky*3*Cin + kx*Cin + c."""
+    Cout, Cin, kh, kw = w.shape
+    assert (kh, kw) == (3, 3)
+    return w.detach().float().permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(torch.bfloat16).contiguous()
+
+
+def downsample_supported(Cin: int, H: int, W: int, Cout: int) -> bool:
+    return bool(L.lib().sast_downsample_supported(int(Cin), int(H), int(W), int(Cout)))
+
+
+@torch.library.custom_op("sast::downsample_fwd", mutates_args=())
+def downsample_fwd(x: Tensor, w9: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tensor], eps: float) -> Tensor:
+    """fp32 NHWC [B,H,W,Cin] (any strides with contiguous channels) -> LayerNorm(conv3x3/2, replicate padding) fp32 NHWC
+    [B,H/2,W/2,Cout]: sast_pad_nhwc_bf16 (padded bf16 operand map) + sast_downsample_fwd."""
+    L.require_cuda(x, "x")
+    assert x.dtype == torch.float32 and w9.dtype == torch.bfloat16 and w9.is_contiguous()
+    if x.stride(3) != 1 or any(s % 4 for s in x.stride()[:3]):
+        x = x.contiguous()
+    B, H, W, Cin = x.shape
+    Cout = w9.shape[0]
+    xp = torch.empty(B, H + 2, W + 2, Cin, device=x.device, dtype=torch.bfloat16)
+    L.run(x.device, "sast_pad_nhwc_bf16", x.data_ptr(), B, H, W, Cin, 1, x.stride(0), x.stride(1), x.stride(2), xp.data_ptr())
+    out = torch.empty(B, H // 2, W // 2, Cout, device=x.device, dtype=torch.float32)
+    L.run(x.device, "sast_downsample_fwd", xp.data_ptr(), B, Cin, H, W, w9.data_ptr(), Cout, L.ptr(ln_w), L.ptr(ln_b),
+          float(eps), out.data_ptr())
+    return out
+
+
+@downsample_fwd.register_fake
+def _(x, w9, ln_w, ln_b, eps):
+    B, H, W, _ = x.shape
+    return x.new_empty(B, H // 2, W // 2, w9.shape[0])
+
+
 def pack_stem_weight_bits(w: Tensor) -> Tensor:
     """conv.weight [Cout,Cin,7,7] fp32 -> fp16 [7*Cout, Cin*8] for sast_stem_bits_fwd: row ky*Cout + n holds w[n, c, ky, kx] at
     column c*8 + kx; the 8th tap of every bin is zero."""

@@ -126,3 +126,31 @@ def test_backbone_small_config_dim_head_24(precision):
         for st in (1, 2, 3, 4):
             d = (got_f[st].cpu() - ref_f[st]).abs()
             assert (d > tol).float().mean().item() < (2e-3 if precision == L.FP32 else 2e-2), (st, d.max().item())
+
+
+@pytest.mark.parametrize("wl,bits", [("1mpx_b8", 1), ("gen1_b1", 1), ("gen1_b1", 4)])
+def test_packed_input_equals_uint8_input(wl, bits):
+    """The three stems agree: the bit-packed histogram (1 bit: stem_bits.cu expands the bits itself; 4 bits: fp16 NHWC copy +
+    TMA-im2col stem) gives the backbone the same result as the uint8 tensor (NHWC route) -- same fp16 products, other
+    summation order -- and the fp32-grade split-weight stem (cudnn.allow_tf32 off) agrees within the fp16 weight rounding."""
+    workload = WORKLOADS[wl]
+    net = _build(workload, 0.5).to(DEV)
+    set_precision(net, L.BF16)
+    kind = "binary" if bits == 1 else "poisson"
+    x = make_inputs(workload["batch"], workload["res"], 0.97, 1, seed=11, kind=kind)[0].to(DEV)
+    with torch.no_grad():
+        f_u8, _, p_u8 = net(x, None)
+        f_pk, _, p_pk = net(sast_b200.pack_events(x, bits), None)
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            f_32, _, p_32 = net(x, None)
+        finally:
+            torch.backends.cudnn.allow_tf32 = True
+    tokens = 2 * (workload["res"][0] // 4) * (workload["res"][1] // 4)
+    for a, b, c in zip(p_u8, p_pk, p_32):
+        assert abs(int(a) - int(b)) <= max(2, 1e-3 * tokens) and abs(int(a) - int(c)) <= max(3, 1e-2 * tokens), (p_u8, p_pk, p_32)
+    for st in (1, 2, 3, 4):
+        d = (f_u8[st] - f_pk[st]).abs()
+        assert (d > 2e-2).float().mean().item() < 5e-3, (st, d.max().item())
+        d = (f_u8[st] - f_32[st]).abs()
+        assert (d > 6e-2).float().mean().item() < 2e-2, (st, d.max().item())

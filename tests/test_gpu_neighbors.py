@@ -7,7 +7,7 @@ import torch.nn.functional as F
 import sast_b200
 from oracle import sast_oracle as O
 from oracle.golden_common import event_histogram, make_params
-from sast_b200 import ops
+from sast_b200 import _lib as L, ops
 from sast_b200.config import Config
 
 pytestmark = pytest.mark.gpu
@@ -182,3 +182,38 @@ def test_nhwc_stem(bits, B, H, W, density):
             assert not mod.nhwc_stem_ok(20, H, W)
         finally:
             torch.backends.cudnn.allow_tf32 = True
+
+
+@pytest.mark.parametrize("cin,cout,B,H,W", [(64, 128, 8, 96, 160), (128, 256, 8, 48, 80), (64, 128, 1, 64, 80), (128, 256, 2, 22, 36),
+                                            (64, 128, 3, 10, 24)])
+def test_fused_downsample(cin, cout, B, H, W):
+    """sast_pad_nhwc_bf16 + sast_downsample_fwd (stages 2-3: k3 s2 conv with replicate padding + LayerNorm as ONE tcgen05
+    kernel, bf16 operands, im2col by an overlapping-stride TMA tensor map) against the oracle's fp32 conv + LayerNorm within
+    bf16 operand rounding (2^-9 relative per product, fp32 accumulation), and against the cuDNN TF32 route it replaces.
+    Geometries: both channel pairs at the 1 Mpx B=8 shapes, Gen1, ragged tiles (Ho % 16, Wo % 8 != 0)."""
+    mod = sast_b200.ConvDownsampling_Cf2Cl(cin, cout, 2, Config(type="patch", overlap=True, norm_affine=True)).eval()
+    p = make_params({"conv.weight": (cout, cin, 3, 3), "norm.weight": (cout,), "norm.bias": (cout,)}, seed=cin + H)
+    mod.load_state_dict(p)
+    mod = mod.to(DEV)
+    x = torch.randn(B, cin, H, W, generator=torch.Generator().manual_seed(H))
+    x[:, :, 0, :] += 2.0          # make the replicated borders matter
+    x[:, :, :, -1] -= 2.0
+    ref = O.conv_downsample(x, p, 2)
+    assert ops.downsample_supported(cin, H, W, cout)
+    with torch.no_grad():
+        xd = x.to(DEV).contiguous(memory_format=torch.channels_last)     # what the previous stage's LSTM hands over
+        before = L.lib().sast_launch_count()
+        got = mod(xd)
+        assert L.lib().sast_launch_count() - before == 2                  # bf16 pad + the fused kernel (cuDNN route: pad + LayerNorm)
+        mod.fused_downsample = False
+        got_cudnn = mod(xd)
+        mod.fused_downsample, mod.precision = True, L.FP32                # the fp32 validation mode never takes the bf16 kernel
+        before = L.lib().sast_launch_count()
+        got_fp32mode = mod(xd)
+        assert L.lib().sast_launch_count() - before == 2 and torch.equal(got_fp32mode, got_cudnn)
+    assert got.shape == ref.shape and got.is_contiguous()
+    d = (got.cpu() - ref).abs()
+    assert d.max() < 4e-2 and d.mean() < 4e-3, (d.max(), d.mean())
+    d2 = (got - got_cudnn).abs()
+    assert d2.max() < 4e-2 and d2.mean() < 4e-3, (d2.max(), d2.mean())
+    assert (got_cudnn.cpu() - ref).abs().mean() < 1e-3

@@ -60,6 +60,40 @@ def test_argument_validation_without_gpu():
     assert lib.sast_layer_workspace_bytes(1000, 64, 160, 2, L.BF16) > lib.sast_layer_workspace_bytes(1000, 64, 160, 2, L.FP32) // 2
     a = L.LayerArgs()
     assert lib.sast_layer_fwd(ctypes.byref(a), 0) == -1
+    # the stems by input format: null pointers, unsupported formats / geometries (no launch happens on any of these)
+    assert lib.sast_events_nhwc(0, 1, 1, 20, 64, 64, 16, 16, 16, 0) == -1
+    assert lib.sast_events_nhwc(16, 1, 1, 20, 64, 64, 0, 0, 0, 0) == -1                 # neither xh nor r requested
+    assert lib.sast_events_nhwc(16, 2, 1, 20, 64, 64, 16, 16, 16, 0) == -3              # bits must be 1 / 4 / 8
+    assert lib.sast_events_nhwc(16, 1, 1, 20, 64, 72, 16, 16, 16, 0) == -2              # W % 32
+    assert lib.sast_stem_bits_fwd(0, 1, 1, 20, 64, 64, 16, 64, 0, 0, 1e-5, 16, 0) == -1
+    assert lib.sast_stem_bits_fwd(16, 4, 1, 20, 64, 64, 16, 64, 0, 0, 1e-5, 16, 0) == -3
+    assert lib.sast_stem_nhwc_fwd(16, 1, 20, 64, 64, 16, 48, 0, 0, 1e-5, 16, 0) == -3   # Cout 48: the split-weight stem's case
+
+
+def test_stem_geometry_and_weight_packs():
+    """Which stem kernel takes which input (sast_stem_*_supported) and the weight layouts they expect."""
+    from sast_b200 import ops
+    assert ops.stem_bits_supported(1, 20, 384, 640, 64) and ops.stem_bits_supported(1, 20, 256, 320, 64)
+    assert not ops.stem_bits_supported(4, 20, 384, 640, 64) and not ops.stem_bits_supported(1, 20, 384, 640, 48)
+    assert not ops.stem_bits_supported(1, 20, 240, 304, 64)             # W % 32 != 0 (Gen1 raw 240 x 304 is padded to 256 x 320)
+    assert ops.stem_nhwc_supported(20, 384, 640, 64) and not ops.stem_nhwc_supported(3, 384, 640, 64)
+    w = torch.randn(64, 20, 7, 7)
+    wb = ops.pack_stem_weight_bits(w)                                   # [7*Cout, Cin*8]: (ky, n) x (c, kx8)
+    assert wb.shape == (448, 160) and wb.dtype == torch.float16
+    assert wb[3 * 64 + 5, 11 * 8 + 2] == w[5, 11, 3, 2].half() and float(wb.view(448, 20, 8)[:, :, 7].abs().max()) == 0
+    wn = ops.pack_stem_weight_nhwc(w)                                   # [7*Cout, 144]: (ky, n) x (kx, c) + 4 zeros
+    assert wn.shape == (448, 144) and wn[2 * 64 + 9, 4 * 20 + 13] == w[9, 13, 2, 4].half() and float(wn[:, 140:].abs().max()) == 0
+    # the module picks by input format and cuDNN's TF32 switch (the convolution it replaces), never under autograd
+    stem = sast_b200.build_recurrent_backbone(backbone_config((384, 640))).stages[0].downsample_cf2cl
+    with torch.no_grad():
+        assert stem.bits_stem_ok(1, 20, 384, 640) and stem.nhwc_stem_ok(20, 384, 640) and not stem.bits_stem_ok(4, 20, 384, 640)
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            assert not stem.bits_stem_ok(1, 20, 384, 640) and not stem.nhwc_stem_ok(20, 384, 640)
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+    assert not stem.bits_stem_ok(1, 20, 384, 640)                       # gradients enabled, weight requires grad: stock autograd path
 
 
 def test_state_dict_keys_match_reference(golden):
