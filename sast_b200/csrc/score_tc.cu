@@ -36,11 +36,10 @@ struct ScSmem {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
-}
+// round to TF32 (10-bit mantissa), nearest with ties away from zero == cvt.rna.tf32.f32 on finite values, as two integer
+// instructions: the conversion unit retires 16 cvt per clock and SM, and the loaders need 8 192 of them per k-block (a
+// quarter of their time in the phase tracer)
+__device__ __forceinline__ float to_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 using ptx::umma_tf32_ss;
 __host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);   // D=F32, A=B=TF32, K-major
@@ -110,6 +109,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t s = it % SC_STAGES, round = it / SC_STAGES;
+        SAST_STAMP(trc, threadIdx.x == 0 && pti == 2 && kb < 2, 110 + 4 * kb);
         float4 xv[8], pv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {         // global loads first: they do not depend on the ring slot
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
         }
         ptx::mbar_wait(&sm->empty[s], (round & 1) ^ 1);
         SAST_STAMP(trc, threadIdx.x == 0 && kb == 0 && pti < 8, 100 + pti);
+        SAST_STAMP(trc, threadIdx.x == 0 && pti == 2 && kb < 2, 111 + 4 * kb);
         uint8_t* st = base + (size_t)s * stage_bytes;
         if (warp == 0 && ptx::elect_one()) {     // warp-uniform operands, elected lane: no R2UR waterfall per TMA
           ptx::mbar_arrive_expect_tx(&sm->full[s], 2 * w_bytes);
@@ -137,9 +138,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
           *reinterpret_cast<float4*>(st + off) = make_float4(h0, h1, h2, h3);
           *reinterpret_cast<float4*>(st + a_bytes + off) = make_float4(to_tf32(a0 - h0), to_tf32(a1 - h1), to_tf32(a2 - h2), to_tf32(a3 - h3));
         }
+        SAST_STAMP(trc, threadIdx.x == 0 && pti == 2 && kb < 2, 112 + 4 * kb);
         ptx::fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&sm->full[s]);     // one arrive per warp, not per thread
+        SAST_STAMP(trc, threadIdx.x == 0 && pti == 2 && kb < 2, 113 + 4 * kb);
       }
     }
   } else if (warp == SC_MMA_WARP) {

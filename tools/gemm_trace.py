@@ -98,3 +98,12 @@ for ti in range(8):
     r = rel[m]
     print(f"  {ti:4d} | {med(r[:, 100 + ti])}            | {med(r[:, 8 + 4 * ti])} {med(r[:, 9 + 4 * ti])} {med(r[:, 10 + 4 * ti])}"
           f"                    | {med(r[:, 48 + 4 * ti])} {med(r[:, 49 + 4 * ti])} ({med(r[:, 49 + 4 * ti] - r[:, 48 + 4 * ti])})   [{int(m.sum())} CTAs]")
+if kind == "score" and (t[:, 113] != 0).any():      # loader phases of the third tile, both k-blocks
+    m = t[:, 113] != 0
+    r = rel[m]
+    for kb in range(2):
+        o = 110 + 4 * kb
+        if (t[m][:, o + 3] == 0).all():
+            continue
+        print(f"  loader tile 2 k-block {kb}: loads issued -> slot free {med(r[:, o + 1] - r[:, o])}, convert + stores {med(r[:, o + 2] - r[:, o + 1])}, "
+              f"fence + arrive {med(r[:, o + 3] - r[:, o + 2])}" + (f", to next k-block top {med(r[:, o + 4] - r[:, o + 3])}" if kb == 0 else ""))
