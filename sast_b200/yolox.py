@@ -54,26 +54,37 @@ class BaseConv(nn.Module):
         self._folded = False
 
     def forward(self, x: Tensor) -> Tensor:
-        if self._folded:
-            return self.act(self.conv(x))
+        if self._folded and not self.training:
+            c = self.conv
+            return self.act(F.conv2d(x, self._fw, self._fb, c.stride, c.padding, c.dilation, c.groups))
         return self.act(self.bn(self.conv(x)))
 
     @torch.no_grad()
     def fold_bn(self) -> None:
         """Eval-mode BN folded into the conv: w' = w * g / sqrt(var + eps), b' = beta + (b - mean) * g / sqrt(var + eps).
-        Call after load_state_dict: the BN module stays but is skipped, and the conv gains a bias entry."""
-        if self._folded:
-            return
+        The folded weight / bias live in NON-persistent buffers used only by the inference forward: parameters and state
+        dict stay exactly the reference's (a later strict load_state_dict works), and both ``train()`` and a state-dict load
+        drop the fold (call ``prepare_inference`` / ``fold_bn`` again afterwards)."""
         bn, conv = self.bn, self.conv
         scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
         bias0 = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
-        conv.weight.copy_(conv.weight * scale.view(-1, 1, 1, 1))
-        new_bias = bn.bias + (bias0 - bn.running_mean) * scale
-        if conv.bias is None:
-            conv.bias = nn.Parameter(new_bias.clone(), requires_grad=False)
-        else:
-            conv.bias.copy_(new_bias)
+        self.register_buffer("_fw", (conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last), persistent=False)
+        self.register_buffer("_fb", (bn.bias + (bias0 - bn.running_mean) * scale).contiguous(), persistent=False)
         self._folded = True
+
+    def _unfold(self) -> None:
+        if self._folded:
+            self._folded = False
+            self._fw = self._fb = None
+
+    def train(self, mode: bool = True):
+        if mode:
+            self._unfold()
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._unfold()                              # new statistics / weights: the fold is stale
+        return super()._load_from_state_dict(*args, **kwargs)
 
 
 class DWConv(nn.Module):

@@ -68,6 +68,16 @@ def test_neck_head_postprocess_match_reference(golden, name):
     with torch.no_grad():
         out2, _ = head(fpn({k: v.contiguous(memory_format=torch.channels_last) for k, v in feats.items()}))
     assert ((out2 - ref).abs() / (ref.abs() + 1.0)).max() < 2e-4
+    # the fold lives in non-persistent buffers: the state dict keeps the reference's keys, a strict reload works and drops
+    # the (now stale) fold, and so does train()
+    sd = head.state_dict()
+    assert not any("_fw" in k or "_fb" in k or k.endswith("conv.bias") and "pred" not in k and "stem" in k for k in sd)
+    head.load_state_dict(sd, strict=True)
+    assert not any(m._folded for m in head.modules() if isinstance(m, yolox.BaseConv))
+    yolox.YoloXDetector.prepare_inference(det)
+    fpn.train()
+    assert not any(m._folded for m in fpn.modules() if isinstance(m, yolox.BaseConv))
+    fpn.eval()
 
 
 def test_postprocess_semantics():
