@@ -566,7 +566,8 @@ layer_group_kernel(const __grid_constant__ CUtensorMap map_n2, const __grid_cons
       constexpr int TOK = 512 / LPT;
       const int l = ct % LPT;
       const long long step = (long long)gridDim.x * TOK;
-      for (long long q = (long long)blockIdx.x * TOK + ct / LPT; q - ct / LPT < p.g.P; q += step) {
+      const bool any_unselected = (long long)p.counts[1] < p.g.P;      // dense scene: every token selected, nothing to keep
+      for (long long q = (long long)blockIdx.x * TOK + ct / LPT; any_unselected && q - ct / LPT < p.g.P; q += step) {
         const bool todo = q < p.g.P && p.tok_row[q] < 0;
         if (!__any_sync(kFull, todo)) continue;
         const long long pix = todo ? token_pixel(q, p.g, p.flavor) : 0;

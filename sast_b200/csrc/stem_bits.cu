@@ -33,11 +33,11 @@ namespace sb {
 
 constexpr int kCout = 64, kCin = 20;
 constexpr int kKRow = 160;                          // halves per (output channel, ky): 20 bins x 8 taps
-constexpr int kABufs = 3;                           // A operand buffers in tensor memory
+constexpr int kABufs = 4;                           // A operand buffers in tensor memory
 constexpr int kACols = 80;                          // one buffer: the 20 bins of one ky = 160 halves = 80 columns
-constexpr int kChains = 2;                          // independent accumulation chains per tile (summed by the epilogue): a
-                                                    // tcgen05.mma that accumulates onto the result of the previous one waits for
-                                                    // it (~125 clk measured), 4x the 32 clk an M128 N64 K16 instruction occupies
+constexpr int kChains = 1;                          // accumulation chains per tile (summed by the epilogue).  2 was measured:
+                                                    // no effect -- back-to-back tcgen05.mma on ONE accumulator already run at the
+                                                    // instruction floor (tools/mma_bench.cu), the issuer just waited for operands
 constexpr int kAcc0 = 0, kA0 = 2 * kChains * kCout; // TMEM columns: two sets of accumulators, then the A buffers
 static_assert(kA0 + kABufs * kACols <= 512, "tensor memory");
 constexpr int kWRow = 2 * 8192 + 4096;              // weights of one ky: two [64 x 64] SW128 tiles + one [64 x 32] SW64 tile
