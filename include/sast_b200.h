@@ -70,7 +70,7 @@ typedef struct sast_geom {
  * [index_window, index_token, padding_index, asy_index, K] of SAST.py:123.
  */
 typedef struct sast_selection {
-  int32_t* counts;    /* [8]  0:M  1:S  2:Kmax  3:number of entries of tile_list  4..7 reserved */
+  int32_t* counts;    /* [8]  0:M  1:S  2:Kmax  3:number of entries of tile_list  4:work tickets of sast_layer_fwd (zero between launches)  5..7 reserved */
   int32_t* win_K;     /* [NW]   selected tokens in window w (0 when the window is dropped)  */
   int32_t* win_rank;  /* [NW]   rank m of window w among selected windows, or -1            */
   int32_t* win_row0;  /* [NW+1] first compacted row of window w (exclusive prefix of win_K) */

@@ -87,6 +87,7 @@ struct Ctl {
   uint64_t mma_bar[NCTX];
   uint32_t tmem_base;
   int pix[NCTX][128];
+  int pass_id[3];                  // unselected-token pass: chunk tickets of this CTA (ring of 3: current, next, next but one)
   uint8_t lo[NCTX][128], hi[NCTX][128];
   float pmax[TPR == 2 ? 2 : 1][TPR == 2 ? 2 : 1][TPR == 2 ? 128 : 1];     // cross-thread row maxima / row sums (two softmax threads per row only)
   float psum[TPR == 2 ? 2 : 1][TPR == 2 ? 2 : 1][TPR == 2 ? 128 : 1];
@@ -229,47 +230,71 @@ layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     // ---- unselected tokens keep norm1(x)  (SAST.py:251-254): this context's share of the map, 4 lanes per token.
     // With two contexts, context 1 does its share BEFORE its tiles and context 0 after: the contexts then sit in
     // different phases of their tiles (tensor-core waits of one under the epilogue arithmetic of the other).
+    // The chunks of 128 tokens are handed out DYNAMICALLY (a ticket counter in the selection record, counts[4]): at low keep
+    // ratios only some CTAs own a tile (55 of 148 at keep 5 %), and with a static share of the map those finished last --
+    // tile + share = 47-56 k clk against 30 k for the others.  Tickets are fetched two chunks ahead and the chunk's token
+    // flags one chunk ahead, so a chunk costs no more dependent latency than with a static stride.  Every CTA draws exactly
+    // two tickets past the end; the CTA that draws the very last one resets the counter for the next launch on this
+    // selection (a block reuses it for its second layer call and non-first blocks reuse index lists).
     auto unselected_pass = [&]() {
       constexpr int NV = C / 16;
-      constexpr int TOK = TPC / 4;                           // tokens per iteration of this context
+      constexpr int TOK = TPC / 4;                           // tokens per chunk
+      static_assert(NCTX == 1, "ticket accounting assumes one context per CTA");
+      if ((long long)p.counts[1] >= p.g.P) return;          // every token of the map is selected (dense scene): nothing to keep
       const int l = ct & 3;
       const float inv_c = 1.0f / (float)C;
-      if ((long long)p.counts[1] >= p.g.P) return;          // every token of the map is selected (dense scene): nothing to keep
-      // (batching 4 iterations of row loads per lane was measured: no gain at keep 5 %, slower at C = 128 -- registers)
-      const long long step = (long long)gridDim.x * NCTX * TOK;
-      long long q = ((long long)blockIdx.x * NCTX + ctx) * TOK + (ct >> 2);
-      int trow = q < p.g.P ? p.tok_row[q] : 0;
-      for (; q - (ct >> 2) < p.g.P; q += step) {
-        const bool todo = q < p.g.P && trow < 0;
-        const long long qn = q + step;
-        trow = qn < p.g.P ? p.tok_row[qn] : 0;                 // next iteration's flag, requested before this one's rows
-        if (!__any_sync(kFull, todo)) continue;
-        const long long pix = todo ? token_pixel(q, p.g, p.flavor) : 0;
-        float4 v[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-          v[i] = todo ? __ldg(reinterpret_cast<const float4*>(p.x + pix * C + (l + 4 * i) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        const float mean = group4_sum(s) * inv_c;
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-          ss += (a * a + b * b) + (c * c + d * d);
+      const int nchunks = (int)((p.g.P + TOK - 1) / TOK);
+      int* const ticket = const_cast<int*>(p.counts) + 4;
+      auto draw = [&](int slot) {
+        if (ct == 0) {
+          const int c = atomicAdd(ticket, 1);
+          if (c == nchunks + 2 * (int)gridDim.x - 1) atomicExch(ticket, 0);      // the last draw of the whole grid
+          ctl->pass_id[slot] = c;
         }
-        const float rstd = rsqrtf(group4_sum(ss) * inv_c + p.eps);
-        if (todo) {
+      };
+      draw(0);
+      draw(1);
+      ctx_sync<TPC>(ctx);
+      int c_cur = ctl->pass_id[0], c_nxt = ctl->pass_id[1];
+      long long q = (long long)c_cur * TOK + (ct >> 2);
+      int trow = (c_cur < nchunks && q < p.g.P) ? p.tok_row[q] : 0;
+      for (int k = 0; c_cur < nchunks; ++k) {
+        draw((k + 2) % 3);                                   // one draw per processed chunk: exactly two failed draws per CTA
+        q = (long long)c_cur * TOK + (ct >> 2);
+        const bool todo = q < p.g.P && trow < 0;
+        const long long qn = (long long)c_nxt * TOK + (ct >> 2);
+        trow = (c_nxt < nchunks && qn < p.g.P) ? p.tok_row[qn] : 0;      // next chunk's flags, requested before this chunk's rows
+        if (__any_sync(kFull, todo)) {
+          const long long pix = todo ? token_pixel(q, p.g, p.flavor) : 0;
+          float4 v[NV];
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            v[i] = todo ? __ldg(reinterpret_cast<const float4*>(p.x + pix * C + (l + 4 * i) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+          const float mean = group4_sum(s) * inv_c;
+          float ss = 0.f;
 #pragma unroll
           for (int i = 0; i < NV; ++i) {
-            const float4 w4 = lds128(sPV + (uint32_t)(K::PV_LN1W + (l + 4 * i) * 4) * 4);
-            const float4 b4 = lds128(sPV + (uint32_t)(K::PV_LN1B + (l + 4 * i) * 4) * 4);
-            *reinterpret_cast<float4*>(p.out + pix * C + (l + 4 * i) * 4) =
-                make_float4((v[i].x - mean) * rstd * w4.x + b4.x, (v[i].y - mean) * rstd * w4.y + b4.y,
-                            (v[i].z - mean) * rstd * w4.z + b4.z, (v[i].w - mean) * rstd * w4.w + b4.w);
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+          }
+          const float rstd = rsqrtf(group4_sum(ss) * inv_c + p.eps);
+          if (todo) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+              const float4 w4 = lds128(sPV + (uint32_t)(K::PV_LN1W + (l + 4 * i) * 4) * 4);
+              const float4 b4 = lds128(sPV + (uint32_t)(K::PV_LN1B + (l + 4 * i) * 4) * 4);
+              *reinterpret_cast<float4*>(p.out + pix * C + (l + 4 * i) * 4) =
+                  make_float4((v[i].x - mean) * rstd * w4.x + b4.x, (v[i].y - mean) * rstd * w4.y + b4.y,
+                              (v[i].z - mean) * rstd * w4.z + b4.z, (v[i].w - mean) * rstd * w4.w + b4.w);
+            }
           }
         }
+        ctx_sync<TPC>(ctx);                                  // the ticket drawn at the top of this iteration is in shared memory
+        c_cur = c_nxt;
+        c_nxt = ctl->pass_id[(k + 2) % 3];
       }
     };
     if (ctx == 1) unselected_pass();

@@ -74,7 +74,10 @@ __global__ void __launch_bounds__(kSelThreads) select_flags_kernel(SelectParams 
   const sast_select_args& a = p.a;
   const Geom g = make_geom(a.g, flavor);
   __shared__ float red[kSelWarps];
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) sel.counts[3] = 0;   // tile_list fill count (select_scan adds)
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    sel.counts[3] = 0;            // tile_list fill count (select_scan adds)
+    sel.counts[4] = 0;            // ticket counter of the layer kernels' unselected-token pass (self-resetting after each launch)
+  }
   const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int n = blockIdx.x * kSelWarps + wid;
   const int w = b * g.N + n;
