@@ -109,6 +109,8 @@ struct Params {
 #define FL_STAMP(i) SAST_STAMP(trc, tid == 0 && ti == 1, (i))
 
 template <int C, int NCTX_>
+// (the 544-thread ring variant gets 96 registers: the hardware budgets any block above 512 threads as 640 -- a launch with
+// __maxnreg__(100) and 544 threads fails with "too many resources requested", probed with a test kernel)
 __global__ void __launch_bounds__(Cfg<C, NCTX_>::kThreads, 1)
 layer_fused_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_proj,
                    const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const Params p) {
