@@ -238,7 +238,9 @@ int make_tmap_bf16_box(CUtensorMap* m, const void* ptr, long long rows, int cols
 
 // true if sast_stem_nhwc_fwd takes this geometry (the reference's stems: 20 event bins, embed_dim 64, patch_size 4)
 extern "C" int sast_stem_nhwc_supported(int32_t Cin, int32_t H, int32_t W, int32_t Cout) {
-  return Cin == sast::sn::kCin && Cout == sast::sn::kCout && H >= 32 && W >= 32 && H % 4 == 0 && W % 32 == 0;
+  // (the last term: sast_events_nhwc stages the source rows and one padded output row of the widest format in 48 KB)
+  return Cin == sast::sn::kCin && Cout == sast::sn::kCout && H >= 32 && W >= 32 && H % 4 == 0 && W % 32 == 0 &&
+         (size_t)Cin * W + (size_t)(W + 8) * Cin * 2 <= 48 * 1024;
 }
 
 // xh fp16 [B, H+8, W+8, Cin] (sast_events_nhwc) -> out [B,H/4,W/4,Cout] fp32 NHWC = LayerNorm(conv7x7 stride 4, replicate
