@@ -135,7 +135,7 @@ __global__ void add_pos_kernel(const float4* __restrict__ x, const float4* __res
   }
 }
 
-int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv, float* l1_part, int* n_slices, cudaStream_t st);
+int launch_score_tc(const sast_score_args* a, float* l1_part, int* n_slices, cudaStream_t st);
 
 }  // namespace sast
 
@@ -161,21 +161,23 @@ extern "C" int sast_score_fwd(const sast_score_args* a, void* stream) {
   SAST_CHECK_PTR(a->ctrl_scratch);
   float* sig = a->ctrl_scratch;
   float* inv = a->ctrl_scratch + (size_t)g.B * g.C;
-  sast::launch_k(sast::controls_kernel, g.B, 128, 0, st, a->r, a->ctrl_w, a->n_bins, g.C, a->amp, sig, inv);
-  SAST_LAUNCH_CHECK();
   float* part_buf = a->ctrl_scratch + 2 * (size_t)g.B * g.C;
   int ny;
-  if (a->score_w_hi && a->score_w_lo) {      // 3xTF32 on tcgen05
+  if (a->score_w_hi && a->score_w_lo) {      // 3xTF32 on tcgen05 (the kernel computes the control table itself)
     const int bn = g.C % 128 == 0 ? 128 : (g.C % 64 == 0 ? 64 : 32);
     float* part = g.C / bn == 1 ? a->tok_score : part_buf;
-    int rc = sast::launch_score_tc(a, sig, inv, part, &ny, st);
-    if (rc) return rc;
-    if (ny > 1) {
-      sast::launch_k(sast::score_reduce_kernel, (unsigned)((P + 255) / 256), 256, 0, st, part, ny, P, a->tok_score);
-      SAST_LAUNCH_CHECK();
+    int rc = sast::launch_score_tc(a, part, &ny, st);
+    if (rc == SAST_OK) {
+      if (ny > 1) {
+        sast::launch_k(sast::score_reduce_kernel, (unsigned)((P + 255) / 256), 256, 0, st, part, ny, P, a->tok_score);
+        SAST_LAUNCH_CHECK();
+      }
+      return SAST_OK;
     }
-    return SAST_OK;
+    if (rc != SAST_E_UNSUPPORTED) return rc;       // (control table of a very large batch does not fit: CUDA-core path below)
   }
+  sast::launch_k(sast::controls_kernel, g.B, 128, 0, st, a->r, a->ctrl_w, a->n_bins, g.C, a->amp, sig, inv);
+  SAST_LAUNCH_CHECK();
   ny = (g.C + sast::BN - 1) / sast::BN;
   const dim3 grid((unsigned)((P + sast::BM - 1) / sast::BM), ny);
   float* part = ny == 1 ? a->tok_score : part_buf;

@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap map_wlo,
                                                                  const float* __restrict__ x, const float* __restrict__ pos,
                                                                  long long pos_bstride, const float* __restrict__ bs,
-                                                                 const float* __restrict__ sig, const float* __restrict__ inv,
+                                                                 const float* __restrict__ r, const float* __restrict__ ctrl_w,
+                                                                 int n_bins, float amp, int B,
                                                                  int HW, int C, int BN, long long P, float* __restrict__ xw,
                                                                  float* __restrict__ l1_out, long long* __restrict__ trace) {
   // trace build only: same [CTA][128] slot layout as gemm_tc_kernel (0 entry, 1 set-up done, 2 end; per tile ti < 8: MMA
@@ -65,6 +66,12 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
   const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;         // A_hi, A_lo, W_hi, W_lo
   ScSmem* sm = reinterpret_cast<ScSmem*>(smem_raw + (size_t)SC_STAGES * stage_bytes);
   float* stage_all = reinterpret_cast<float*>(smem_raw + (size_t)SC_STAGES * stage_bytes + 256);
+  // controls of the STP weighting, per (frame, channel): sig = sigmoid(ctrl), inv = amp / ctrl (SAST.py:105-119 with the
+  // PositiveLinear of :305-328: ctrl[b,c] = sum_j exp(Wc[c,j]) (r[b,j] + 1e-6)).  Every CTA computes the whole table (B x C
+  // x n_bins exp: a few hundred per thread) into shared memory BEFORE the PDL wait -- r comes from the very first kernels of
+  // the forward -- instead of a separate 5 us launch per block in front of this kernel.
+  float* const sig = stage_all + (size_t)4 * SC_GROUPS * 32 * 33;
+  float* const inv = sig + (size_t)B * C;
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();
   const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // warp: provably uniform
   const int nkb = C / SC_BK;
@@ -83,7 +90,17 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
-  // PDL: everything above (barriers, TMEM, index loads of data written >= 2 kernels ago) overlapped the tail of the
+  for (int e = threadIdx.x; e < B * C; e += blockDim.x) {
+    const int b = e / C, c = e - b * C;
+    float acc = 0.f;
+    for (int j = 0; j < n_bins; ++j) acc += expf(ctrl_w[c * n_bins + j]) * (r[b * n_bins + j] + 1e-6f);
+    sig[e] = sigmoidf_acc(acc);
+    float iv = amp / acc;
+    if (isinf(iv)) iv = 0.f;
+    inv[e] = iv;
+  }
+  __syncthreads();
+  // PDL: everything above (barriers, TMEM, the control table from data written >= 2 kernels ago) overlapped the tail of the
   // preceding kernel; its output is read only from here on
   pdl_entry();
 
@@ -228,8 +245,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
           }
         }
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(bs + nc + c4));
-        float4 sg0 = __ldg(reinterpret_cast<const float4*>(sig + co[0] + nc));
-        float4 iv0 = __ldg(reinterpret_cast<const float4*>(inv + co[0] + nc));
+        float4 sg0 = *reinterpret_cast<const float4*>(sig + co[0] + nc);
+        float4 iv0 = *reinterpret_cast<const float4*>(inv + co[0] + nc);
         ptx::tmem_ld_wait();
         // transpose through shared memory: 8 x STS.128 / 8 x LDS.128, 16-byte groups XOR-swizzled by (row % 8)
 #pragma unroll
@@ -246,8 +263,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
         for (int i = 0; i < 8; ++i) {
           float4 sg = sg0, iv = iv0;
           if (!one_frame) {                       // warp-uniform
-            sg = __ldg(reinterpret_cast<const float4*>(sig + co[i] + nc));
-            iv = __ldg(reinterpret_cast<const float4*>(inv + co[i] + nc));
+            sg = *reinterpret_cast<const float4*>(sig + co[i] + nc);
+            iv = *reinterpret_cast<const float4*>(inv + co[i] + nc);
           }
           const float s0 = fmaxf(a4[i].x + b4.x, 0.f), s1 = fmaxf(a4[i].y + b4.y, 0.f), s2 = fmaxf(a4[i].z + b4.z, 0.f),
                       s3 = fmaxf(a4[i].w + b4.w, 0.f);
@@ -289,7 +306,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(const __grid_co
 int make_tmap_f32_box(CUtensorMap* m, const void* ptr, long long rows, int cols, int ld, int box_cols, int box_rows);
 
 // returns the number of channel slices (partials) written to l1_part, or <0 / >0 on error (negated for CUDA errors)
-int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv, float* l1_part, int* n_slices, cudaStream_t st) {
+int launch_score_tc(const sast_score_args* a, float* l1_part, int* n_slices, cudaStream_t st) {
   const sast_geom& g = a->g;
   const long long P = (long long)g.B * g.H * g.W;
   const int C = g.C;
@@ -301,7 +318,8 @@ int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv
   if (rc) return rc;
   if (P * C >= (1ll << 31)) return SAST_E_UNSUPPORTED;        // 32-bit element offsets inside the kernel
   const size_t smem = (size_t)SC_STAGES * (2 * SC_BM * SC_BK * 4 + 2 * (size_t)BN * SC_BK * 4) + 256 +
-                      (size_t)4 * SC_GROUPS * 32 * 33 * sizeof(float);
+                      (size_t)4 * SC_GROUPS * 32 * 33 * sizeof(float) + (size_t)2 * g.B * C * sizeof(float);
+  if (smem > 200 * 1024) return SAST_E_UNSUPPORTED;             // (B x C control table: 32 KB at B = 8, C = 512)
   static thread_local unsigned long long attr_mask = 0;
   if (first_use_on_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -312,7 +330,7 @@ int launch_score_tc(const sast_score_args* a, const float* sig, const float* inv
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long tiles = ((P + SC_BM - 1) / SC_BM) * (C / BN);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  sast::launch_k(score_tc_kernel, grid, SC_THREADS, smem, st, mh, ml, a->x, a->pos, a->pos_batch_stride, a->score_b, sig, inv, g.H * g.W, C, BN, P,
+  sast::launch_k(score_tc_kernel, grid, SC_THREADS, smem, st, mh, ml, a->x, a->pos, a->pos_batch_stride, a->score_b, a->r, a->ctrl_w, a->n_bins, a->amp, g.B, g.H * g.W, C, BN, P,
                                                   a->xw, l1_part, g_trace_which == 3 ? g_trace : nullptr);
   SAST_LAUNCH_CHECK();
   *n_slices = C / BN;
