@@ -7,4 +7,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k "regex:lay
     python tools/layer_bench.py 3 1.0 3 > gpurun_out/ncu_group256.log 2>&1
 SAST_B200_LIB=sast_b200/libsast_b200.so timeout 600 ncu --set full --clock-control none --import-source on -k "regex:stem_bits_kernel" -s 2 -c 1 -o gpurun_out/ncu_stem_bits -f \
     python tools/stem_trace.py 0.5 > gpurun_out/ncu_stem_bits.log 2>&1
-ls -la gpurun_out/*.ncu-rep; tail -2 gpurun_out/ncu_fused64.log gpurun_out/ncu_group256.log gpurun_out/ncu_stem_bits.log
+ls -la gpurun_out/*.ncu-rep; tail -n 2 gpurun_out/ncu_fused64.log
