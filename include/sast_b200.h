@@ -283,7 +283,8 @@ int sast_stem_fwd(const uint8_t* x, int32_t B, int32_t Cin, int32_t H, int32_t W
  * sast_unpack_nonzero_ratio) or plain uint8 (bits = 8), NCHW [B,Cin,H,W*bits/8] -- becomes xh = fp16 NHWC
  * [B, H+8, W+8, Cin] with the stem's replicate padding of 3 materialised (row yy = source row clamp(yy-3), column xx =
  * source column clamp(xx-3); the trailing 5 rows / columns are zeros).  With r != NULL it also computes the scene
- * sparsity ratios r [4,B,Cin] exactly as sast_nonzero_ratio does (scratch: B*Cin*4 zeroed int32, left zeroed).
+ * sparsity ratios r [4,B,Cin] exactly as sast_nonzero_ratio does (scratch: B*Cin*4 zeroed int32, left zeroed; not needed --
+ * may be NULL -- for bits = 1, where one CTA counts a whole plane and writes its ratios directly).
  * xh == NULL computes only r (the caller feeds sast_stem_bits_fwd).  W % 32 == 0, Cin == 20 (the stem it feeds).
  *
  * sast_stem_nhwc_fwd: xh -> out [B,H/4,W/4,Cout] fp32 NHWC = LayerNorm(conv 7x7, stride 4, no bias).  The im2col operand

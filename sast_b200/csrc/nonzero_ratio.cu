@@ -179,7 +179,9 @@ __global__ void __launch_bounds__(256) unpack_count_kernel(const uint8_t* __rest
 // four rows of each level-0 cell row; a level-0 / 1 / 2 / 3 cell (4 / 8 / 16 / 32 columns) is then a nibble / byte / half /
 // word of the OR of 1 / 2 / 4 / 8 such cell rows, so "cell != 0" is a few bit operations and a popcount.  Same counts as
 // nonzero_count_kernel (complete cells only: floor semantics on ragged heights), 32 independent coalesced loads per thread.
-__global__ void __launch_bounds__(256) packed1_count_kernel(const uint32_t* __restrict__ packed, int H, int W, int* __restrict__ counts) {
+// One CTA per plane, so the ratios are written directly (what nonzero_finalize_kernel does for the other formats).
+__global__ void __launch_bounds__(256) packed1_count_kernel(const uint32_t* __restrict__ packed, int H, int W, int B, int Cin, float f0,
+                                                             float f1, float f2, float f3, float* __restrict__ r) {
   pdl_entry();
   __shared__ int red[4][8];
   const int plane = blockIdx.x;
@@ -229,10 +231,12 @@ __global__ void __launch_bounds__(256) packed1_count_kernel(const uint32_t* __re
     if (lane == 0) red[lvl][wid] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 4) {
+  if (threadIdx.x < 4) {       // one CTA owns the whole plane: its totals ARE the plane's counts -- no scratch, no finalize launch
     int tot = 0;
     for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) tot += red[threadIdx.x][w2];
-    if (tot) atomicAdd(&counts[plane * 4 + threadIdx.x], tot);
+    const int lvl = threadIdx.x, b = plane / Cin, c = plane - b * Cin;
+    const float f = lvl == 0 ? f0 : lvl == 1 ? f1 : lvl == 2 ? f2 : f3;
+    r[((size_t)lvl * B + b) * Cin + c] = f * (float)(int16_t)tot;            // int16 wrap as in the reference
   }
 }
 
@@ -369,7 +373,7 @@ extern "C" int sast_events_nhwc(const uint8_t* src, int32_t bits, int32_t B, int
   if ((reinterpret_cast<uintptr_t>(src) & 3) || (reinterpret_cast<uintptr_t>(xh) & 15)) return SAST_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   if (r) {
-    SAST_CHECK_PTR(scratch);
+    if (bits != 1) SAST_CHECK_PTR(scratch);               // the 1-bit kernel needs no scratch
     float f[4];
     for (int l = 0; l < 4; ++l) {
       const long long cs = 4ll << l;
@@ -379,13 +383,17 @@ extern "C" int sast_events_nhwc(const uint8_t* src, int32_t bits, int32_t B, int
     if (smem > 48 * 1024) return SAST_E_UNSUPPORTED;
     const int planes = B * Cin;
     const dim3 grid(planes, (H / 4 + 7) / 8), block(256);
-    if (bits == 1) sast::launch_k(sast::packed1_count_kernel, dim3(planes), block, 0, st, (const uint32_t*)src, H, W, scratch);
-    else if (bits == 4) sast::launch_k(sast::unpack_count_kernel<4>, grid, block, smem, st, src, H, W, (uint8_t*)nullptr, scratch);
+    if (bits == 1) {
+      sast::launch_k(sast::packed1_count_kernel, dim3(planes), block, 0, st, (const uint32_t*)src, H, W, B, Cin, f[0], f[1], f[2], f[3], r);
+      SAST_LAUNCH_CHECK();
+    } else {
+    if (bits == 4) sast::launch_k(sast::unpack_count_kernel<4>, grid, block, smem, st, src, H, W, (uint8_t*)nullptr, scratch);
     else sast::launch_k(sast::nonzero_count_kernel<uint8_t>, grid, block, smem, st, src, H, W, scratch);
     SAST_LAUNCH_CHECK();
     sast::launch_k(sast::nonzero_finalize_kernel, dim3((planes * 4 + 127) / 128), dim3(128), 0, st, scratch, planes, B, Cin, f[0],
                    f[1], f[2], f[3], r);
     SAST_LAUNCH_CHECK();
+    }
   }
   if (!xh) return SAST_OK;
   const size_t smem2 = (size_t)Cin * W * bits / 8 + (size_t)(W + 8) * Cin * 2;

@@ -816,8 +816,8 @@ def packed_nonzero_ratio(data: Tensor, bits: int, width: int) -> Tensor:
     data = data.contiguous()
     B, Cin, H, _ = data.shape
     r = torch.empty(4, B, Cin, device=data.device, dtype=torch.float32)
-    scratch = torch.zeros(B * Cin * 4, device=data.device, dtype=torch.int32)
-    L.run(data.device, "sast_events_nhwc", data.data_ptr(), int(bits), B, Cin, H, int(width), 0, r.data_ptr(), scratch.data_ptr())
+    scratch = None if bits == 1 else torch.zeros(B * Cin * 4, device=data.device, dtype=torch.int32)   # 1 bit: one CTA per plane, no scratch
+    L.run(data.device, "sast_events_nhwc", data.data_ptr(), int(bits), B, Cin, H, int(width), 0, r.data_ptr(), L.ptr(scratch))
     return r.permute(1, 0, 2)
 
 
@@ -864,7 +864,7 @@ def events_nhwc(data: Tensor, bits: int, width: int, want_r: bool) -> Tuple[Tens
     B, Cin, H, _ = data.shape
     xh = torch.empty(B, H + 8, width + 8, Cin, device=data.device, dtype=torch.float16)
     r = torch.empty(4, B, Cin, device=data.device, dtype=torch.float32)
-    scratch = torch.zeros(B * Cin * 4, device=data.device, dtype=torch.int32) if want_r else None
+    scratch = torch.zeros(B * Cin * 4, device=data.device, dtype=torch.int32) if (want_r and bits != 1) else None
     L.run(data.device, "sast_events_nhwc", data.data_ptr(), int(bits), B, Cin, H, int(width), xh.data_ptr(),
           r.data_ptr() if want_r else 0, L.ptr(scratch))
     return xh, r.permute(1, 0, 2)
